@@ -1,0 +1,323 @@
+// attention_tcgen05.cu — flash attention (head dim 64) on tcgen05 for sm_100a.
+//
+// One CTA = 128 queries of one (batch, head); two CTAs are resident per SM so that one CTA's
+// tensor-core work (S = Q K^T, O_j = P V) overlaps the other's softmax.  Roles inside a CTA:
+//   warp 0 (1 thread)  TMA producer: Q once, then a 2-stage ring of (K_j, V_j) tiles of 128 keys
+//   warp 1 (1 thread)  tcgen05.mma issuer
+//   warp 2             TMEM allocator (128 columns S + 64 columns O_j -> 256 allocated)
+//   warps 4-7          softmax: one thread per query row (TMEM lane == row), online softmax in
+//                      base 2 with fp32 running max / sum, P written as bf16 into 128B-swizzled
+//                      smem (A operand of the second MMA), O accumulated in registers.
+// V is consumed in place as an MN-major B operand, so no transpose of V is ever materialised, and
+// Q/K/V/O are addressed in the [B, n, heads*64] layout the projections produce — the reference's
+// head split/merge permute+contiguous copies (sgm/modules/attention.py:393-401,413-418) vanish.
+//
+// Reference arithmetic replaced: xformers.ops.memory_efficient_attention (attention.py:406) =
+// softmax(Q K^T / sqrt(64)) V, exact (no approximation of the softmax other than bf16 P).
+#include <cstdio>
+
+#include "cd360_common.cuh"
+
+namespace cd360 {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+constexpr int ATT_D = 64;
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 128 B
+constexpr int ATT_SQ = 0;
+constexpr int ATT_SKV = ATT_TILE_BYTES;                               // stages x (K, V)
+constexpr int ATT_SP = ATT_SKV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 16 KiB halves
+constexpr int ATT_BAR = ATT_SP + 2 * ATT_TILE_BYTES;
+constexpr int ATT_SMEM_BYTES = ATT_BAR + 128;
+constexpr uint32_t ATT_TMEM_COLS = 256;
+constexpr uint32_t ATT_TMEM_S = 0;
+constexpr uint32_t ATT_TMEM_O = 128;
+
+struct AttnParams {
+  __nv_bfloat16* o;
+  long long ldo;
+  int nq, nkv;
+  int heads;
+  float scale_log2;  // (1/sqrt(d)) * log2(e)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
+                              const __grid_constant__ CUtensorMap tmK,
+                              const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [ATT_STAGES]
+  uint64_t* kv_empty = bars + 3;  // [ATT_STAGES]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int num_kv_tiles = (p.nkv + ATT_BKV - 1) / ATT_BKV;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("cd360 attention: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+    tma_load_4d(smem + ATT_SQ, &tmQ, q_full, 0, head, q_tile * ATT_BQ, batch);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      uint8_t* sk = smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES;
+      uint8_t* sv = sk + ATT_TILE_BYTES;
+      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+      tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * ATT_BKV, batch);
+      tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * ATT_BKV, batch);
+      if (++stage == ATT_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, true);  // V is MN-major
+    const uint32_t q_addr = smem_u32(smem + ATT_SQ);
+    const uint32_t p_addr = smem_u32(smem + ATT_SP);
+    mbar_wait(q_full, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      mbar_wait(&kv_full[stage], phase);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES);
+      const uint32_t v_addr = k_addr + ATT_TILE_BYTES;
+      // S = Q K^T : 4 k-steps of 16 over d = 64
+#pragma unroll
+      for (int k = 0; k < ATT_D / 16; ++k)
+        umma_bf16(tmem_base + ATT_TMEM_S, make_smem_desc_sw128(q_addr + k * 32),
+                  make_smem_desc_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(s_full);
+      // O_j = P V : 8 k-steps of 16 over the 128 keys of this tile
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < ATT_BKV / 16; ++k) {
+        const uint32_t a = p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32;
+        const uint32_t b = v_addr + k * 16 * 128;
+        umma_bf16(tmem_base + ATT_TMEM_O, make_smem_desc_sw128(a), make_smem_desc_sw128(b),
+                  idesc_o, k != 0 ? 1u : 0u);
+      }
+      umma_commit(o_full);
+      umma_commit(&kv_empty[stage]);
+      if (++stage == ATT_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ softmax / output ================================
+    const int q = warp - 4;
+    const int row = q * 32 + lane;  // row inside the Q tile == TMEM lane
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_S;
+    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_O;
+    uint8_t* sp_row = smem + ATT_SP + row * 128;
+    const int sw = row & 7;
+    float m = -INFINITY, l = 0.f;
+    float o[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        if (c * 32 + 32 <= valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);  // finite: every tile has >= 1 valid key
+      const float alpha = ex2_approx((m - m_new) * p.scale_log2);
+      const float mb = m_new * p.scale_log2;
+      // pass 2: exponentiate, row sum, write bf16 P into the swizzled A-operand buffer
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_s + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+          if (c * 32 + i >= valid) e = 0.f;
+          pv[i] = e;
+          sum += e;
+        }
+        uint8_t* half_base = sp_row + (c >> 1) * ATT_TILE_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
+          u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
+          u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
+          u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
+          const int chunk = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
+          *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
+        }
+      }
+      l = l * alpha + sum;
+      m = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // accumulate O_j
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_o + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+    }
+    const int qrow = q_tile * ATT_BQ + row;
+    if (qrow < p.nq) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* dst =
+          p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
+        u.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+        u.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
+        u.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+        d4[g] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool l2_256);
+
+static int make_qkv_map(CUtensorMap* tm, const void* base, long long ld, int heads, int n,
+                        int batch) {
+  // element (b, n, h, d) at ((b*n_total + n)*ld + h*64 + d)
+  uint64_t dims[4] = {ATT_D, static_cast<uint64_t>(heads), static_cast<uint64_t>(n),
+                      static_cast<uint64_t>(batch)};
+  uint64_t strides[3] = {ATT_D * 2, static_cast<uint64_t>(ld) * 2,
+                         static_cast<uint64_t>(n) * static_cast<uint64_t>(ld) * 2};
+  uint32_t box[4] = {ATT_D, 1, 128, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, strides, box, true);
+}
+
+}  // namespace cd360
+
+using namespace cd360;
+
+extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                    const void* v, int64_t ldv, void* o, int64_t ldo,
+                                    int32_t batch, int32_t heads, int32_t nq, int32_t nkv,
+                                    cd360_stream_t stream_) {
+  if (!q || !k || !v || !o) return CD360_ERR_NULL;
+  if (batch <= 0 || heads <= 0 || nq <= 0 || nkv <= 0) return CD360_ERR_SHAPE;
+  if (batch > 65535 || heads > 65535) return CD360_ERR_SHAPE;
+  if ((ldq & 7) || (ldk & 7) || (ldv & 7) || (ldo & 7)) return CD360_ERR_ALIGN;
+  if (ldq < heads * ATT_D || ldk < heads * ATT_D || ldv < heads * ATT_D || ldo < heads * ATT_D)
+    return CD360_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
+      (reinterpret_cast<uintptr_t>(v) & 15) || (reinterpret_cast<uintptr_t>(o) & 15))
+    return CD360_ERR_ALIGN;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CUtensorMap tq, tk, tv;
+  int rc = make_qkv_map(&tq, q, ldq, heads, nq, batch);
+  if (rc != CD360_OK) return rc;
+  rc = make_qkv_map(&tk, k, ldk, heads, nkv, batch);
+  if (rc != CD360_OK) return rc;
+  rc = make_qkv_map(&tv, v, ldv, heads, nkv, batch);
+  if (rc != CD360_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attention_bf16_tcgen05_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             ATT_SMEM_BYTES) != cudaSuccess)
+      return CD360_ERR_LAUNCH;
+    attr_set = true;
+  }
+  AttnParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.ldo = ldo;
+  p.nq = nq;
+  p.nkv = nkv;
+  p.heads = heads;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  dim3 grid((nq + ATT_BQ - 1) / ATT_BQ, heads, batch);
+  attention_bf16_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}

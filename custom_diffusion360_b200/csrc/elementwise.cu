@@ -1,0 +1,336 @@
+// elementwise.cu — small HBM/latency-bound kernels around the tensor-core path:
+// timestep embedding, the small-M embedding linears, im2col / resampling layout helpers, dtype
+// casts, and the fused denoiser-scaling + CFG + Euler update of the sampler.
+// Reference lines are cited per kernel.
+#include "cd360_common.cuh"
+
+namespace cd360 {
+
+// timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230): [cos(t f_k) | sin(t f_k)]
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out,
+                                          int batch, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i - b * half;
+  // freqs = exp(-ln(10000) * k / half), computed in fp32 like the reference
+  const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+  const float arg = t[b] * freq;
+  float s, c;
+  sincosf(arg, &s, &c);
+  out[static_cast<long long>(b) * dim + k] = c;
+  out[static_cast<long long>(b) * dim + half + k] = s;
+  if ((dim & 1) && k == 0) out[static_cast<long long>(b) * dim + dim - 1] = 0.f;
+}
+
+// out[b, n] = act_out(sum_k act_in(x[b,k]) W[n,k] + bias[n]) + add[b,n]
+// (time_embed / label_emb, openaimodel.py:679-713,1026-1031; ResBlock.emb_layers, :307-313,363)
+constexpr int SL_BCHUNK = 4;
+constexpr int SL_OUT_PER_WARP = 4;
+__global__ void __launch_bounds__(256)
+small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                    const float* __restrict__ bias, const float* __restrict__ add,
+                    float* __restrict__ out, int batch, int n, int k, int act_in, int act_out) {
+  extern __shared__ float s_x[];  // [SL_BCHUNK][k]
+  const int b0 = blockIdx.y * SL_BCHUNK;
+  const int nb = min(SL_BCHUNK, batch - b0);
+  for (int i = threadIdx.x; i < SL_BCHUNK * k; i += blockDim.x) {
+    const int bi = i / k, kk = i - bi * k;
+    float v = 0.f;
+    if (bi < nb) {
+      v = x[static_cast<long long>(b0 + bi) * k + kk];
+      if (act_in == CD360_ACT_SILU) v = v / (1.0f + expf(-v));
+    }
+    s_x[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = k >> 3;
+  for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi) {
+    const int col = (blockIdx.x * 8 + warp) * SL_OUT_PER_WARP + oi;
+    if (col >= n) break;
+    const __nv_bfloat16* wr = w + static_cast<long long>(col) * k;
+    float acc[SL_BCHUNK];
+#pragma unroll
+    for (int bi = 0; bi < SL_BCHUNK; ++bi) acc[bi] = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + v * 8));
+      const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z),
+                   w3 = unpack_bf16x2(u.w);
+      const float wf[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+#pragma unroll
+      for (int bi = 0; bi < SL_BCHUNK; ++bi) {
+        const float* xr = s_x + bi * k + v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[bi] = fmaf(wf[j], xr[j], acc[bi]);
+      }
+    }
+#pragma unroll
+    for (int bi = 0; bi < SL_BCHUNK; ++bi) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[bi] += __shfl_xor_sync(0xffffffffu, acc[bi], o);
+    }
+    if (lane == 0) {
+      for (int bi = 0; bi < nb; ++bi) {
+        float r = acc[bi] + (bias ? bias[col] : 0.f);
+        if (act_out == CD360_ACT_SILU) r = r / (1.0f + expf(-r));
+        const long long o = static_cast<long long>(b0 + bi) * n + col;
+        if (add) r += add[o];
+        out[o] = r;
+      }
+    }
+  }
+}
+
+// input conv im2col: x fp32 NCHW * scale[b] -> bf16 [B*H*W, kpad], k = (ky*3+kx)*Cin + c
+// (UNetModel.input_blocks[0], openaimodel.py:719-721; c_in scaling denoiser.py:42-43)
+__global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                      __nv_bfloat16* __restrict__ out, int batch, int cin, int h,
+                                      int w, int kpad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(batch) * h * w * kpad;
+  if (i >= total) return;
+  const int kk = static_cast<int>(i % kpad);
+  const long long pix = i / kpad;
+  const int px = static_cast<int>(pix % w);
+  const int py = static_cast<int>((pix / w) % h);
+  const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+  float v = 0.f;
+  if (kk < 9 * cin) {
+    const int tap = kk / cin, c = kk - tap * cin;
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      v = x[((static_cast<long long>(b) * cin + c) * h + yy) * w + xx];
+      if (scale) v *= scale[b];
+    }
+  }
+  out[i] = __float2bfloat16_rn(v);
+}
+
+// stride-2 pad-1 3x3 im2col of an NHWC bf16 tensor, 8 channels per thread
+// (Downsample.op, openaimodel.py:215-222)
+__global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x,
+                                    __nv_bfloat16* __restrict__ out, int batch, int h, int w,
+                                    int c) {
+  const int ho = h / 2, wo = w / 2, cv = c / 8;
+  const long long total = static_cast<long long>(batch) * ho * wo * 9 * cv;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % cv);
+  long long r = i / cv;
+  const int tap = static_cast<int>(r % 9);
+  r /= 9;
+  const int ox = static_cast<int>(r % wo);
+  const int oy = static_cast<int>((r / wo) % ho);
+  const int b = static_cast<int>(r / (static_cast<long long>(wo) * ho));
+  const int yy = oy * 2 + tap / 3 - 1, xx = ox * 2 + tap % 3 - 1;
+  uint4 u = make_uint4(0, 0, 0, 0);
+  if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+    u = __ldg(reinterpret_cast<const uint4*>(
+        x + ((static_cast<long long>(b) * h + yy) * w + xx) * c + v * 8));
+  *reinterpret_cast<uint4*>(out + (r * 9 + tap) * c + v * 8) = u;
+}
+
+// nearest x2 (Upsample.forward, openaimodel.py:161), NHWC, 8 channels per thread
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
+                                  __nv_bfloat16* __restrict__ out, int batch, int h, int w, int c) {
+  const int cv = c / 8;
+  const long long total = static_cast<long long>(batch) * (2 * h) * (2 * w) * cv;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = static_cast<int>(i % cv);
+  long long r = i / cv;
+  const int ox = static_cast<int>(r % (2 * w));
+  const int oy = static_cast<int>((r / (2 * w)) % (2 * h));
+  const int b = static_cast<int>(r / (static_cast<long long>(4) * w * h));
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+      x + ((static_cast<long long>(b) * h + oy / 2) * w + ox / 2) * c + v * 8));
+  *reinterpret_cast<uint4*>(out + r * c + v * 8) = u;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                     long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                     long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(x[i]);
+}
+
+// [B, hw, C] (bf16 or fp32) -> NCHW fp32 [B, C, hw]
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
+                                    float* __restrict__ out, int batch, int hw, int c) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(batch) * hw * c;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % hw);
+  const int ch = static_cast<int>((i / hw) % c);
+  const int b = static_cast<int>(i / (static_cast<long long>(hw) * c));
+  const long long src = (static_cast<long long>(b) * hw + p) * c + ch;
+  out[i] = x_is_fp32 ? reinterpret_cast<const float*>(x)[src]
+                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
+}
+
+// Fused EpsScaling denoiser output + CFG combine + Euler step.  See include/cd360.h.
+__global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                 float* __restrict__ denoised_out, int n_img, int g, int hw,
+                                 float sigma_q, float sigma, float sigma_next, float scale,
+                                 float scale_im) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_img) * 4 * hw;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % hw);
+  const int ch = static_cast<int>((i / hw) % 4);
+  const int img = static_cast<int>(i / (static_cast<long long>(hw) * 4));
+  const float xv = x[i];
+  float d[3];
+  for (int r = 0; r < g; ++r) {
+    const float e = eps[((static_cast<long long>(r) * n_img + img) * hw + p) * 4 + ch];
+    d[r] = e * (-sigma_q) + xv;  // predict * c_out + input * c_skip
+  }
+  float den;
+  if (g == 3) {
+    den = d[0] + scale * (d[2] - d[1]) + scale_im * (d[1] - d[0]);
+  } else if (g == 2) {
+    den = d[0] + scale * (d[1] - d[0]);
+  } else {
+    den = d[0];
+  }
+  if (denoised_out) denoised_out[i] = den;
+  const float dd = (xv - den) / sigma;  // to_d
+  x[i] = xv + (sigma_next - sigma) * dd;
+}
+
+static inline int blocks_for(long long n, int t) { return static_cast<int>((n + t - 1) / t); }
+
+}  // namespace cd360
+
+using namespace cd360;
+
+extern "C" int cd360_timestep_embedding(const float* t, float* out, int32_t batch, int32_t dim,
+                                        cd360_stream_t stream_) {
+  if (!t || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || dim < 2) return CD360_ERR_SHAPE;
+  const int n = batch * (dim / 2);
+  timestep_embedding_kernel<<<blocks_for(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      t, out, batch, dim);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_small_linear(const float* x, const void* w, const float* bias,
+                                  const float* add, float* out, int32_t batch, int32_t n,
+                                  int32_t k, int32_t act_in, int32_t act_out,
+                                  cd360_stream_t stream_) {
+  if (!x || !w || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || n <= 0 || k <= 0 || (k & 7)) return CD360_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(w) & 15) return CD360_ERR_ALIGN;
+  const size_t smem = static_cast<size_t>(SL_BCHUNK) * k * sizeof(float);
+  if (smem > 48 * 1024) return CD360_ERR_SHAPE;
+  dim3 grid((n + 8 * SL_OUT_PER_WARP - 1) / (8 * SL_OUT_PER_WARP),
+            (batch + SL_BCHUNK - 1) / SL_BCHUNK);
+  small_linear_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, reinterpret_cast<const __nv_bfloat16*>(w), bias, add, out, batch, n, k, act_in, act_out);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_im2col3x3_nchw_f32(const float* x, const float* scale, void* out,
+                                        int32_t batch, int32_t cin, int32_t h, int32_t w,
+                                        int32_t kpad, cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || cin <= 0 || h <= 0 || w <= 0 || kpad < 9 * cin || (kpad & 7))
+    return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(batch) * h * w * kpad;
+  im2col3x3_nchw_kernel<<<blocks_for(total, 256), 256, 0,
+                          reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, scale, reinterpret_cast<__nv_bfloat16*>(out), batch, cin, h, w, kpad);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_im2col3x3_s2_bf16(const void* x, void* out, int32_t batch, int32_t h,
+                                       int32_t w, int32_t c, cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || c <= 0 || (c & 7))
+    return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col3x3_s2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w,
+      c);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_upsample_nearest2x_bf16(const void* x, void* out, int32_t batch, int32_t h,
+                                             int32_t w, int32_t c, cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7)) return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w,
+      c);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_cast_f32_to_bf16(const float* x, void* out, int64_t n,
+                                      cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (n <= 0) return CD360_ERR_SHAPE;
+  cast_f32_bf16_kernel<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n,
+                                      cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (n <= 0) return CD360_ERR_SHAPE;
+  cast_bf16_f32_kernel<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), out, n);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t batch,
+                                      int32_t hw, int32_t c, cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || hw <= 0 || c <= 0) return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(batch) * hw * c;
+  nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, x_is_fp32, out, batch, hw, c);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_out, int32_t n_img,
+                                    int32_t guidance_rows, int32_t hw, float sigma_q, float sigma,
+                                    float sigma_next, float scale, float scale_im,
+                                    cd360_stream_t stream_) {
+  if (!x || !eps) return CD360_ERR_NULL;
+  if (n_img <= 0 || hw <= 0 || guidance_rows < 1 || guidance_rows > 3) return CD360_ERR_SHAPE;
+  if (!(sigma > 0.f)) return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(n_img) * 4 * hw;
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, eps, denoised_out, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next, scale, scale_im);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_abi_version(void) { return 1; }
+
+extern "C" const char* cd360_strerror(int code) {
+  switch (code) {
+    case CD360_OK: return "ok";
+    case CD360_ERR_SHAPE: return "unsupported or inconsistent shape";
+    case CD360_ERR_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case CD360_ERR_UNSUPPORTED: return "dtype or mode not built";
+    case CD360_ERR_LAUNCH: return "CUDA launch or driver error";
+    case CD360_ERR_NULL: return "required pointer is NULL";
+    default: return "unknown error";
+  }
+}

@@ -1,0 +1,522 @@
+// gemm_tcgen05.cu — persistent, warp-specialised bf16 GEMM / implicit-GEMM 3x3 convolution for
+// sm_100a.  One CTA per SM; roles:
+//   warp 0 (1 thread)  TMA producer: A and W tiles -> 128B-swizzled smem ring (mbarrier full/empty)
+//   warp 1 (1 thread)  tcgen05.mma issuer: 128 x BN x 16 UMMAs accumulate into TMEM
+//   warp 2             TMEM allocator / deallocator
+//   warps 4-7          epilogue: tcgen05.ld -> bias / emb-add / activation / GEGLU / residual -> HBM
+// The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+//
+// Convolution mode feeds the SAME main loop from a 4-D NHWC tensor map: the A tile of K-block
+// (tap, c-chunk) is the box [64 ch, tw, th, tb] at pixel offset (dx-1, dy-1); out-of-image
+// coordinates are zero-filled by TMA, which implements the pad-1 border without a halo copy.
+//
+// Reference arithmetic replaced: see include/cd360.h (cd360_gemm_bf16).
+#include "cd360_common.cuh"
+
+namespace cd360 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+
+struct GemmKParams {
+  int M, N, N_out;
+  int num_m_blocks, num_n_blocks;
+  int kb0, kb1;  // 64-wide K blocks of the two A segments (linear mode)
+  int conv;      // 0 / 1
+  int cblocks;   // C / 64 (conv)
+  int H, W;      // conv geometry
+  int tw, th, tb;  // conv A box (pixels x rows x images), tw*th*tb == 128
+  const float* bias;
+  const float* row_bias;
+  int rows_per_group;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  void* out;
+  long long ldo;
+  int out_fp32;
+  int act;
+  int geglu;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+};
+
+// ---- epilogue helpers --------------------------------------------------------------------------
+__device__ __forceinline__ void load_bias32(float (&v)[32], const float* __restrict__ p, int col0,
+                                            int nvalid) {
+  if (nvalid == 32) {
+    const float4* p4 = reinterpret_cast<const float4*>(p + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(p4 + j);
+      v[4 * j + 0] += b.x;
+      v[4 * j + 1] += b.y;
+      v[4 * j + 2] += b.z;
+      v[4 * j + 3] += b.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) v[j] += __ldg(p + col0 + j);
+  }
+}
+
+__device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams& p, long long row,
+                                              int ocol0, int nvalid) {
+  if (p.residual != nullptr) {
+    const __nv_bfloat16* r = p.residual + row * p.ldr + ocol0;
+    if (nvalid == 32) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u = r4[j];
+        float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+               f3 = unpack_bf16x2(u.w);
+        v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+        v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) v[j] += __bfloat162float(r[j]);
+    }
+  }
+  if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + ocol0;
+    if (nvalid == 32 && (p.ldo & 3) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + ocol0;
+    if (nvalid == 32 && (p.ldo & 7) == 0) {
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        o4[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// ---- kernel ------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
+                         const __grid_constant__ CUtensorMap tmA1,
+                         const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int nkb = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int m0 = m_blk * BM;
+      const int n0 = n_blk * BN;
+      int cb = 0, cy = 0, cx = 0;
+      if (p.conv) {
+        const int hw = p.H * p.W;
+        cb = m0 / hw;
+        const int rem = m0 - cb * hw;
+        cy = rem / p.W;
+        cx = rem - cy * p.W;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + A_TILE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        if (p.conv) {
+          const int tap = kb / p.cblocks;
+          const int kc = kb - tap * p.cblocks;
+          const int dy = tap / 3, dx = tap - dy * 3;
+          tma_load_4d(sa, &tmA0, &full_bar[stage], kc * BK, cx + dx - 1, cy + dy - 1, cb);
+        } else if (kb < p.kb0) {
+          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m0);
+        } else {
+          tma_load_2d(sa, &tmA1, &full_bar[stage], (kb - p.kb0) * BK, m0);
+        }
+        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
+          umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        if (kb == nkb - 1) umma_commit(&tmem_full[buf]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================
+    const int q = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      const int buf = t & 1;
+      const uint32_t acc_phase = (t >> 1) & 1;
+      const long long row = static_cast<long long>(m_blk) * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BN;
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      const float* rb = nullptr;
+      if (p.row_bias != nullptr && row_ok)
+        rb = p.row_bias + (row / p.rows_per_group) * static_cast<long long>(p.N);
+
+      if (!p.geglu) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int nvalid = min(32, p.N - col0);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr) load_bias32(v, p.bias, col0, nvalid);
+            if (rb != nullptr) load_bias32(v, rb, col0, nvalid);
+            if (p.act == CD360_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
+            store_chunk32(v, p, row, col0, nvalid);
+          }
+        }
+      } else {
+        // tile columns [0, BN/2) hold x, [BN/2, BN) hold the matching gates (pre-interleaved W)
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          uint32_t rx[32], rg[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, rx);
+          tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
+          tmem_ld_wait();
+          if (row_ok) {
+            float v[32], g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(rx[j]);
+              g[j] = __uint_as_float(rg[j]);
+            }
+            if (p.bias != nullptr) {
+              load_bias32(v, p.bias, n0 + c * 32, 32);
+              load_bias32(g, p.bias, n0 + BN / 2 + c * 32, 32);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
+            store_chunk32(v, p, row, n_blk * (BN / 2) + c * 32, 32);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map of rank `rank`; dims/strides innermost first; strides in BYTES for dims 1..rank-1
+int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool l2_256) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return CD360_ERR_LAUNCH;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B,
+                  l2_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CD360_OK : CD360_ERR_LAUNCH;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsB200;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = kNumSMsB200;
+  }
+  return n;
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                       const GemmKParams& p, int max_ctas, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
+        cudaSuccess)
+      return CD360_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = num_sms();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (tiles < grid) grid = tiles;
+  kern<<<grid, kGemmThreads, L::DYN_BYTES, stream>>>(a0, a1, b, p);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+static int pick_block_n(int M, int N, int geglu, int requested) {
+  if (requested == 128 || requested == 256) return requested;
+  if (geglu) return (N % 256 == 0) ? 256 : 128;
+  if (N <= 128) return 128;
+  const long long t256 = static_cast<long long>((M + BM - 1) / BM) * ((N + 255) / 256);
+  return t256 >= 100 ? 256 : 128;
+}
+
+}  // namespace cd360
+
+using namespace cd360;
+
+extern "C" int cd360_geglu_pack_block(int32_t n_total) {
+  if (n_total % 256 == 0) return 128;
+  if (n_total % 128 == 0) return 64;
+  return CD360_ERR_SHAPE;
+}
+
+extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_) {
+  if (a == nullptr || a->a0 == nullptr || a->w == nullptr || a->out == nullptr)
+    return CD360_ERR_NULL;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (a->M <= 0 || a->N <= 0) return CD360_ERR_SHAPE;
+  const int BN = pick_block_n(a->M, a->N, a->geglu, a->block_n);
+  if (a->geglu && (a->N % BN != 0 || (a->N & 1))) return CD360_ERR_SHAPE;
+  if (a->geglu && a->act != CD360_ACT_NONE) return CD360_ERR_UNSUPPORTED;
+
+  GemmKParams p{};
+  p.M = a->M;
+  p.N = a->N;
+  p.N_out = a->geglu ? a->N / 2 : a->N;
+  p.num_m_blocks = (a->M + BM - 1) / BM;
+  p.num_n_blocks = (a->N + BN - 1) / BN;
+  p.bias = a->bias;
+  p.row_bias = a->row_bias;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.ldr = a->ldr;
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.out_fp32 = a->out_fp32;
+  p.act = a->act;
+  p.geglu = a->geglu;
+  if (a->row_bias != nullptr && a->geglu) return CD360_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(a->a0) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->out) & 15) ||
+      (a->residual && (reinterpret_cast<uintptr_t>(a->residual) & 15)) ||
+      (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15)) ||
+      (a->row_bias && (reinterpret_cast<uintptr_t>(a->row_bias) & 15)))
+    return CD360_ERR_ALIGN;
+  if (a->residual && (a->ldr & 7)) return CD360_ERR_ALIGN;
+  if (a->ldo < p.N_out) return CD360_ERR_SHAPE;
+  if ((a->bias || a->row_bias) && (a->N & 3)) return CD360_ERR_ALIGN;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  int ktot;
+  int rc;
+  if (a->conv) {
+    const int C = a->C, H = a->H, W = a->W, B = a->B;
+    if (C <= 0 || (C % BK) != 0 || !is_pow2(H) || !is_pow2(W) || W > 128 || B <= 0)
+      return CD360_ERR_SHAPE;
+    if (static_cast<long long>(B) * H * W != a->M) return CD360_ERR_SHAPE;
+    const int tw = W;  // W <= 128: a tile always covers whole image rows
+    int th = BM / tw;
+    if (th > H) th = H;
+    const int tb = BM / (tw * th);
+    p.conv = 1;
+    p.cblocks = C / BK;
+    p.H = H;
+    p.W = W;
+    p.tw = tw;
+    p.th = th;
+    p.tb = tb;
+    ktot = 9 * C;
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W),
+                        static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(W) * C * 2,
+                           static_cast<uint64_t>(H) * W * C * 2};
+    uint32_t box[4] = {BK, static_cast<uint32_t>(tw), static_cast<uint32_t>(th),
+                       static_cast<uint32_t>(tb)};
+    rc = encode_tmap_bf16(&tmA0, a->a0, 4, dims, strides, box, false);
+    if (rc != CD360_OK) return rc;
+    tmA1 = tmA0;
+  } else {
+    if (a->k0 <= 0 || (a->k0 & 7) || (a->lda0 & 7) || a->lda0 < a->k0) return CD360_ERR_ALIGN;
+    if (a->k1 < 0) return CD360_ERR_SHAPE;
+    if (a->k1 > 0) {
+      if (a->a1 == nullptr) return CD360_ERR_NULL;
+      if ((a->k0 % BK) != 0 || (a->k1 & 7) || (a->lda1 & 7) || a->lda1 < a->k1 ||
+          (reinterpret_cast<uintptr_t>(a->a1) & 15))
+        return CD360_ERR_ALIGN;
+    }
+    p.kb0 = (a->k0 + BK - 1) / BK;
+    p.kb1 = (a->k1 + BK - 1) / BK;
+    ktot = a->k0 + a->k1;
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(a->k0), static_cast<uint64_t>(a->M)};
+      uint64_t strides[1] = {static_cast<uint64_t>(a->lda0) * 2};
+      uint32_t box[2] = {BK, BM};
+      rc = encode_tmap_bf16(&tmA0, a->a0, 2, dims, strides, box, false);
+      if (rc != CD360_OK) return rc;
+    }
+    if (a->k1 > 0) {
+      uint64_t dims[2] = {static_cast<uint64_t>(a->k1), static_cast<uint64_t>(a->M)};
+      uint64_t strides[1] = {static_cast<uint64_t>(a->lda1) * 2};
+      uint32_t box[2] = {BK, BM};
+      rc = encode_tmap_bf16(&tmA1, a->a1, 2, dims, strides, box, false);
+      if (rc != CD360_OK) return rc;
+    } else {
+      tmA1 = tmA0;
+    }
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(a->N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(BN)};
+    rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, true);
+    if (rc != CD360_OK) return rc;
+  }
+  if (BN == 256) return launch_gemm<256, 4>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+  return launch_gemm<128, 6>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+}

@@ -1,0 +1,275 @@
+// norm.cu — HBM-bound normalisation kernels (NHWC bf16 activations, fp32 statistics).
+//
+//  * GroupNorm(32) [+ SiLU]: GroupNorm32 (sgm/modules/diffusionmodules/util.py:309-311) followed
+//    by nn.SiLU in ResBlock.in_layers/out_layers and UNetModel.out (openaimodel.py:280-283,
+//    315-317, 968-971) and Normalize() in SpatialTransformer (sgm/modules/attention.py:118,748).
+//    Pass 1 reduces per-(image, chunk) partial moments with 16-byte coalesced loads; pass 2
+//    finalises mean/rstd (double), folds them with gamma/beta into per-channel scale/shift in
+//    smem, and streams x -> y.  The input may be a virtual channel concat of two tensors.
+//  * LayerNorm: nn.LayerNorm(dim) x3 per BasicTransformerBlock (attention.py:531-533);
+//    one warp per token row, values held in registers, two-pass variance.
+#include "cd360_common.cuh"
+
+namespace cd360 {
+
+constexpr int GN_MAX_CHUNKS = 32;
+constexpr int GN_GROUPS = 32;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+         d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's rows and the group's channels
+__global__ void __launch_bounds__(1024)
+groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
+                       const __nv_bfloat16* __restrict__ x1, int c1, float* __restrict__ partial,
+                       int hw, int rows_per_chunk, int nvec, int rlanes) {
+  __shared__ float s_acc[GN_GROUPS * 2];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int ctot = c0 + c1;
+  const int cg = ctot / GN_GROUPS;
+  if (threadIdx.x < GN_GROUPS * 2) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int vec = threadIdx.x % nvec;
+  const int rl = threadIdx.x / nvec;
+  if (rl < rlanes) {
+    const int ch0 = vec * 8;
+    const __nv_bfloat16* src;
+    long long ld;
+    int ch;
+    if (ch0 < c0) { src = x0; ld = c0; ch = ch0; } else { src = x1; ld = c1; ch = ch0 - c0; }
+    const int r_begin = chunk * rows_per_chunk;
+    const int r_end = min(hw, r_begin + rows_per_chunk);
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+    for (int r = r_begin + rl; r < r_end; r += rlanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+          src + (static_cast<long long>(b) * hw + r) * ld + ch));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+    }
+    // fold the 8 channels into their groups (<= 8 distinct groups), then one smem atomic each
+    int g_prev = ch0 / cg;
+    float as = 0.f, ass = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (ch0 + i) / cg;
+      if (g != g_prev) {
+        atomicAdd(&s_acc[g_prev * 2], as);
+        atomicAdd(&s_acc[g_prev * 2 + 1], ass);
+        as = 0.f; ass = 0.f; g_prev = g;
+      }
+      as += s[i]; ass += ss[i];
+    }
+    atomicAdd(&s_acc[g_prev * 2], as);
+    atomicAdd(&s_acc[g_prev * 2 + 1], ass);
+  }
+  __syncthreads();
+  if (threadIdx.x < GN_GROUPS * 2)
+    partial[(static_cast<long long>(b) * gridDim.x + chunk) * GN_GROUPS * 2 + threadIdx.x] =
+        s_acc[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
+                       const __nv_bfloat16* __restrict__ x1, int c1,
+                       const float* __restrict__ partial, int nchunks,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       __nv_bfloat16* __restrict__ out, int hw, int rows_per_block, float eps,
+                       int apply_silu) {
+  extern __shared__ float s_dyn[];  // scale[ctot] | shift[ctot]
+  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  const int b = blockIdx.y;
+  const int ctot = c0 + c1;
+  const int cg = ctot / GN_GROUPS;
+  float* s_scale = s_dyn;
+  float* s_shift = s_dyn + ctot;
+  if (threadIdx.x < GN_GROUPS) {
+    double su = 0.0, sq = 0.0;
+    const float* pp = partial + static_cast<long long>(b) * nchunks * GN_GROUPS * 2;
+    for (int c = 0; c < nchunks; ++c) {
+      su += pp[(c * GN_GROUPS + threadIdx.x) * 2];
+      sq += pp[(c * GN_GROUPS + threadIdx.x) * 2 + 1];
+    }
+    const double n = static_cast<double>(hw) * cg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ctot; c += blockDim.x) {
+    const int g = c / cg;
+    const float sc = s_rstd[g] * gamma[c];
+    s_scale[c] = sc;
+    s_shift[c] = beta[c] - s_mean[g] * sc;
+  }
+  __syncthreads();
+  const int nvec = ctot / 8;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(hw, r_begin + rows_per_block);
+  const long long total = static_cast<long long>(r_end - r_begin) * nvec;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = r_begin + static_cast<int>(i / nvec);
+    const int ch0 = static_cast<int>(i % nvec) * 8;
+    const long long grow = static_cast<long long>(b) * hw + r;
+    const __nv_bfloat16* src = (ch0 < c0) ? (x0 + grow * c0 + ch0) : (x1 + grow * c1 + (ch0 - c0));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float y = fmaf(f[k], s_scale[ch0 + k], s_shift[ch0 + k]);
+      f[k] = apply_silu ? silu_f(y) : y;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f[0], f[1]);
+    o.y = pack_bf16x2(f[2], f[3]);
+    o.z = pack_bf16x2(f[4], f[5]);
+    o.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + grow * ctot + ch0) = o;
+  }
+}
+
+constexpr int LN_MAXV = 8;  // c <= 2048
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, int c,
+                 float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = c >> 3;
+  const __nv_bfloat16* src = x + static_cast<long long>(warp) * c;
+  float v[LN_MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + vi * 8));
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / c;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = v[i][k] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / c + eps);
+  __nv_bfloat16* dst = out + static_cast<long long>(warp) * c;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) y[k] = fmaf((v[i][k] - mean) * rstd, gg[k], bb[k]);
+      uint4 o;
+      o.x = pack_bf16x2(y[0], y[1]);
+      o.y = pack_bf16x2(y[2], y[3]);
+      o.z = pack_bf16x2(y[4], y[5]);
+      o.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(dst + vi * 8) = o;
+    }
+  }
+}
+
+static int gn_chunks(int batch, int hw) {
+  int chunks = (4 * kNumSMsB200 + batch - 1) / batch;
+  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+  const int max_by_rows = (hw + 15) / 16;
+  if (chunks > max_by_rows) chunks = max_by_rows;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+}  // namespace cd360
+
+using namespace cd360;
+
+extern "C" int64_t cd360_groupnorm_workspace_floats(int32_t batch, int32_t hw) {
+  (void)hw;
+  return static_cast<int64_t>(batch) * GN_MAX_CHUNKS * GN_GROUPS * 2;
+}
+
+extern "C" int cd360_groupnorm_silu_bf16(const void* x0, int32_t c0, const void* x1, int32_t c1,
+                                         const float* gamma, const float* beta, void* out,
+                                         float* workspace, int32_t batch, int32_t hw, float eps,
+                                         int32_t apply_silu, cd360_stream_t stream_) {
+  if (!x0 || !gamma || !beta || !out || !workspace) return CD360_ERR_NULL;
+  if (c1 > 0 && !x1) return CD360_ERR_NULL;
+  if (c1 < 0 || c0 <= 0 || batch <= 0 || hw <= 0 || batch > 65535) return CD360_ERR_SHAPE;
+  const int ctot = c0 + c1;
+  if ((c0 & 7) || (c1 & 7) || (ctot % GN_GROUPS) != 0) return CD360_ERR_SHAPE;
+  const int nvec = ctot / 8;
+  if (nvec > 1024) return CD360_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x0) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (x1 && (reinterpret_cast<uintptr_t>(x1) & 15)))
+    return CD360_ERR_ALIGN;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int chunks = gn_chunks(batch, hw);
+  const int rows_per_chunk = (hw + chunks - 1) / chunks;
+  int rlanes = nvec <= 256 ? 256 / nvec : 1;
+  if (rlanes < 1) rlanes = 1;
+  const int threads = ((nvec * rlanes + 31) / 32) * 32;
+  groupnorm_stats_kernel<<<dim3(chunks, batch), threads, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1),
+      c1, workspace, hw, rows_per_chunk, nvec, rlanes);
+  CD360_CHECK_LAUNCH();
+  int row_blocks = (8 * kNumSMsB200 + batch - 1) / batch;
+  if (row_blocks > hw) row_blocks = hw;
+  const int rows_per_block = (hw + row_blocks - 1) / row_blocks;
+  row_blocks = (hw + rows_per_block - 1) / rows_per_block;
+  const size_t smem = static_cast<size_t>(ctot) * 2 * sizeof(float);
+  groupnorm_apply_kernel<<<dim3(row_blocks, batch), 256, smem, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1),
+      c1, workspace, chunks, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), hw,
+      rows_per_block, eps, apply_silu);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out,
+                                    int32_t rows, int32_t c, float eps, cd360_stream_t stream_) {
+  if (!x || !gamma || !beta || !out) return CD360_ERR_NULL;
+  if (rows <= 0 || c <= 0 || (c & 7) || c > LN_MAXV * 256) return CD360_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(gamma) & 15) || (reinterpret_cast<uintptr_t>(beta) & 15))
+    return CD360_ERR_ALIGN;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int warps_per_block = 8;
+  const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+  layernorm_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out),
+      rows, c, eps);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}

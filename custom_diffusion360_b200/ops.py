@@ -1,0 +1,283 @@
+"""Torch-tensor front end of the C ABI.  Tensors supply device memory and the stream only;
+every arithmetic op below is a hand-written sm_100a kernel in libcd360.so.
+
+All wrappers require CUDA tensors and raise `Cd360Error` on any non-zero status — there is no
+fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, Cd360Error, GemmArgs, check
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise Cd360Error(f"{name}: expected a CUDA tensor (libcd360 has no CPU path)")
+    if t.dtype != dtype:
+        raise Cd360Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise Cd360Error(f"{name}: expected a contiguous tensor")
+
+
+def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out=None,
+         out_fp32=False, act=ACT_NONE, geglu=False, a1=None, block_n=0, max_ctas=0,
+         lda=None, lda1=None, k0=None, k1=None, M=None):
+    """out = epilogue(A @ W^T).  a: bf16 [M, K0] (row stride `lda` if given), optional second
+    K-segment a1 [M, K1]; w: bf16 [N, K0+K1]."""
+    lib = _lib.load()
+    _req(w, bf16, "w")
+    M = a.shape[0] if M is None else M
+    k0 = a.shape[-1] if k0 is None else k0
+    lda = (a.stride(0) if a.dim() == 2 else k0) if lda is None else lda
+    if a1 is not None:
+        k1 = a1.shape[-1] if k1 is None else k1
+        lda1 = a1.stride(0) if lda1 is None else lda1
+    else:
+        k1, lda1 = 0, 0
+    N = w.shape[0]
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=f32 if out_fp32 else bf16)
+    args = GemmArgs(
+        a0=_ptr(a), lda0=lda, k0=k0, a1=_ptr(a1), lda1=lda1, k1=k1, w=_ptr(w),
+        bias=_ptr(bias), row_bias=_ptr(row_bias), rows_per_group=rows_per_group,
+        residual=_ptr(residual), ldr=(residual.stride(0) if residual is not None else 0),
+        out=_ptr(out), ldo=out.stride(0), out_fp32=int(out.dtype == f32), M=M, N=N,
+        conv=0, B=0, H=0, W=0, C=0, act=act, geglu=int(geglu), block_n=block_n, max_ctas=max_ctas)
+    check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16")
+    return out
+
+
+def conv3x3(x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None, out_fp32=False,
+            block_n=0, max_ctas=0):
+    """Stride-1 pad-1 3x3 convolution as implicit GEMM.  x: bf16 [B*H*W, C] (NHWC);
+    w: bf16 [N, 9*C] packed (ky, kx, c)."""
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    _req(w, bf16, "w")
+    Cin = x.shape[-1]
+    N = w.shape[0]
+    M = B * H * W
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=f32 if out_fp32 else bf16)
+    args = GemmArgs(
+        a0=_ptr(x), lda0=Cin, k0=9 * Cin, a1=0, lda1=0, k1=0, w=_ptr(w), bias=_ptr(bias),
+        row_bias=_ptr(row_bias), rows_per_group=H * W, residual=_ptr(residual),
+        ldr=(residual.stride(0) if residual is not None else 0), out=_ptr(out), ldo=out.stride(0),
+        out_fp32=int(out.dtype == f32), M=M, N=N, conv=1, B=B, H=H, W=W, C=Cin, act=ACT_NONE,
+        geglu=0, block_n=block_n, max_ctas=max_ctas)
+    check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(conv)")
+    return out
+
+
+def geglu_pack_block(n_total: int) -> int:
+    r = _lib.load().cd360_geglu_pack_block(n_total)
+    if r < 0:
+        check(r, "cd360_geglu_pack_block")
+    return r
+
+
+def attention(q, k, v, batch, heads, nq, nkv, *, out=None, ldq=None, ldk=None, ldv=None):
+    """q: [batch*nq, >=heads*64] view (row stride ldq), k/v: [batch*nkv, ...]; returns
+    [batch*nq, heads*64] bf16."""
+    lib = _lib.load()
+    ldq = q.stride(0) if ldq is None else ldq
+    ldk = k.stride(0) if ldk is None else ldk
+    ldv = v.stride(0) if ldv is None else ldv
+    if out is None:
+        out = torch.empty((batch * nq, heads * 64), device=q.device, dtype=bf16)
+    check(lib.cd360_attention_bf16(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out),
+                                   out.stride(0), batch, heads, nq, nkv, _stream()),
+          "cd360_attention_bf16")
+    return out
+
+
+_gn_ws: dict = {}
+
+
+def groupnorm_workspace(batch: int, hw: int, device) -> torch.Tensor:
+    n = _lib.load().cd360_groupnorm_workspace_floats(batch, hw)
+    key = (str(device), int(n))
+    ws = _gn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(n), device=device, dtype=f32)
+        _gn_ws[key] = ws
+    return ws
+
+
+def groupnorm(x0, gamma, beta, batch, hw, *, x1=None, eps=1e-5, silu=True, out=None,
+              workspace=None):
+    """GroupNorm(32)+optional SiLU over NHWC bf16 [batch*hw, c0 (+c1)]."""
+    lib = _lib.load()
+    _req(x0, bf16, "x0")
+    c0 = x0.shape[-1]
+    c1 = 0 if x1 is None else x1.shape[-1]
+    if out is None:
+        out = torch.empty((batch * hw, c0 + c1), device=x0.device, dtype=bf16)
+    if workspace is None:
+        workspace = groupnorm_workspace(batch, hw, x0.device)
+    check(lib.cd360_groupnorm_silu_bf16(_ptr(x0), c0, _ptr(x1), c1, _ptr(gamma), _ptr(beta),
+                                        _ptr(out), _ptr(workspace), batch, hw, eps, int(silu),
+                                        _stream()), "cd360_groupnorm_silu_bf16")
+    return out
+
+
+def layernorm(x, gamma, beta, *, eps=1e-5, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.cd360_layernorm_bf16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), rows, c, eps,
+                                   _stream()), "cd360_layernorm_bf16")
+    return out
+
+
+def small_linear(x, w, bias=None, *, add=None, act_in=ACT_NONE, act_out=ACT_NONE, out=None):
+    lib = _lib.load()
+    _req(x, f32, "x")
+    _req(w, bf16, "w")
+    batch, k = x.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((batch, n), device=x.device, dtype=f32)
+    check(lib.cd360_small_linear(_ptr(x), _ptr(w), _ptr(bias), _ptr(add), _ptr(out), batch, n, k,
+                                 act_in, act_out, _stream()), "cd360_small_linear")
+    return out
+
+
+def timestep_embedding(t, dim, *, out=None):
+    lib = _lib.load()
+    _req(t, f32, "t")
+    batch = t.shape[0]
+    if out is None:
+        out = torch.empty((batch, dim), device=t.device, dtype=f32)
+    check(lib.cd360_timestep_embedding(_ptr(t), _ptr(out), batch, dim, _stream()),
+          "cd360_timestep_embedding")
+    return out
+
+
+def im2col3x3_nchw(x, kpad, *, scale=None, out=None):
+    lib = _lib.load()
+    _req(x, f32, "x")
+    b, cin, h, w = x.shape
+    if out is None:
+        out = torch.empty((b * h * w, kpad), device=x.device, dtype=bf16)
+    check(lib.cd360_im2col3x3_nchw_f32(_ptr(x), _ptr(scale), _ptr(out), b, cin, h, w, kpad,
+                                       _stream()), "cd360_im2col3x3_nchw_f32")
+    return out
+
+
+def im2col3x3_s2(x, batch, h, w, *, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * (h // 2) * (w // 2), 9 * c), device=x.device, dtype=bf16)
+    check(lib.cd360_im2col3x3_s2_bf16(_ptr(x), _ptr(out), batch, h, w, c, _stream()),
+          "cd360_im2col3x3_s2_bf16")
+    return out
+
+
+def upsample_nearest2x(x, batch, h, w, *, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty((batch * 4 * h * w, c), device=x.device, dtype=bf16)
+    check(lib.cd360_upsample_nearest2x_bf16(_ptr(x), _ptr(out), batch, h, w, c, _stream()),
+          "cd360_upsample_nearest2x_bf16")
+    return out
+
+
+def cfg_euler_step(x, eps, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next, scale, scale_im,
+                   *, denoised_out=None):
+    lib = _lib.load()
+    _req(x, f32, "x")
+    _req(eps, f32, "eps")
+    check(lib.cd360_cfg_euler_step(_ptr(x), _ptr(eps), _ptr(denoised_out), n_img, guidance_rows,
+                                   hw, float(sigma_q), float(sigma), float(sigma_next),
+                                   float(scale), float(scale_im), _stream()),
+          "cd360_cfg_euler_step")
+    return x
+
+
+def cast_bf16(x, *, out=None):
+    lib = _lib.load()
+    _req(x, f32, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=bf16)
+    check(lib.cd360_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()),
+          "cd360_cast_f32_to_bf16")
+    return out
+
+
+def cast_f32(x, *, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=f32)
+    check(lib.cd360_cast_bf16_to_f32(_ptr(x), _ptr(out), x.numel(), _stream()),
+          "cd360_cast_bf16_to_f32")
+    return out
+
+
+def nhwc_to_nchw_f32(x, batch, hw, c, *, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((batch, c, hw), device=x.device, dtype=f32)
+    check(lib.cd360_nhwc_to_nchw_f32(_ptr(x), int(x.dtype == f32), _ptr(out), batch, hw, c,
+                                     _stream()), "cd360_nhwc_to_nchw_f32")
+    return out
+
+
+def nerf_points(cams, xy, depths, w_nv_geo, b_nv, b, n, res, d, kpe):
+    lib = _lib.load()
+    dev = cams.device
+    hw = res * res
+    pe = torch.empty((b * n * hw * d, kpe), device=dev, dtype=bf16)
+    gidx = torch.empty((b * n * hw * d, 4), device=dev, dtype=torch.int32)
+    gwgt = torch.empty((b * n * hw * d, 4), device=dev, dtype=f32)
+    vlogit = torch.empty((b, n, hw * d), device=dev, dtype=f32)
+    check(lib.cd360_nerf_points(_ptr(cams), _ptr(xy), _ptr(depths), _ptr(w_nv_geo), float(b_nv),
+                                _ptr(pe), _ptr(gidx), _ptr(gwgt), _ptr(vlogit), b, n, res, d, kpe,
+                                _stream()), "cd360_nerf_points")
+    return pe, gidx, gwgt, vlogit
+
+
+def nerf_combine(g, hpre, gidx, gwgt, vlogit, b, n, hw, d, c):
+    lib = _lib.load()
+    s = torch.empty((b * hw * d, c), device=g.device, dtype=bf16)
+    vs = torch.empty((b, n, hw * d), device=g.device, dtype=f32)
+    check(lib.cd360_nerf_combine(_ptr(g), g.stride(0), _ptr(hpre), _ptr(gidx), _ptr(gwgt),
+                                 _ptr(vlogit), _ptr(s), _ptr(vs), b, n, hw, d, c, _stream()),
+          "cd360_nerf_combine")
+    return s, vs
+
+
+def nerf_volrender(feats, raw, dists, b, hw, d, c):
+    lib = _lib.load()
+    dev = feats.device
+    rendered = torch.empty((b * hw, c), device=dev, dtype=bf16)
+    fg = torch.empty((b, hw), device=dev, dtype=f32)
+    alphas = torch.empty((b, hw, d), device=dev, dtype=f32)
+    rgb = torch.empty((b, hw, 3), device=dev, dtype=f32)
+    check(lib.cd360_nerf_volrender(_ptr(feats), _ptr(raw), _ptr(dists), _ptr(rendered), _ptr(fg),
+                                   _ptr(alphas), _ptr(rgb), b, hw, d, c, _stream()),
+          "cd360_nerf_volrender")
+    return rendered, fg, alphas, rgb

@@ -1,0 +1,218 @@
+/* cd360.h — C ABI of libcd360.so, the sm_100a (B200) kernels behind the pose-conditioned SDXL
+ * UNet denoising step of customdiffusion360/custom-diffusion360.
+ *
+ * The reference has no FFI: its "plugin API" is Python (sgm module classes selected by `target:`
+ * strings).  This header is the boundary WE define below that Python surface; every
+ * entry point names the reference code whose arithmetic it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name says host;
+ *   - the caller owns all buffers (inputs, outputs, workspaces); nothing is allocated, nothing
+ *     synchronises, no global state is kept; launches go to `stream` and are CUDA-graph capturable;
+ *   - activations are row-major bf16 "tokens x channels" ([B*H*W, C], i.e. NHWC) unless stated;
+ *   - return value: CD360_OK or a negative CD360_ERR_* code; nothing is launched on error.
+ */
+#ifndef CD360_H_
+#define CD360_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cd360_stream_t; /* cudaStream_t */
+
+enum {
+  CD360_OK = 0,
+  CD360_ERR_SHAPE = -1,       /* unsupported / inconsistent shape */
+  CD360_ERR_ALIGN = -2,       /* pointer or leading dimension not 16-byte aligned */
+  CD360_ERR_UNSUPPORTED = -3, /* dtype / mode not built */
+  CD360_ERR_LAUNCH = -4,      /* CUDA launch or driver error */
+  CD360_ERR_NULL = -5         /* required pointer is NULL */
+};
+
+enum { CD360_ACT_NONE = 0, CD360_ACT_SILU = 1 };
+
+/* Library / build info: returns the ABI version (bumped on any signature change). */
+int cd360_abi_version(void);
+/* Human-readable name of an error code (static string). */
+const char* cd360_strerror(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ *
+ *   out[M, N'] = epilogue( A[M, K] * W[N, K]^T )
+ *
+ * Replaces every nn.Linear / nn.Conv2d on the path: to_q/to_k/to_v/to_out
+ * (sgm/modules/attention.py:323-329), GEGLU + FF out (attention.py:89-115), proj_in/proj_out
+ * (attention.py:758,795), pose_emb_layers (attention.py:515), ResBlock/Downsample/Upsample 3x3 and
+ * 1x1 convs (sgm/modules/diffusionmodules/openaimodel.py:142,215,283,320,337,720,971), FeatureNeRF
+ * plane_coefs / decoder (sgm/modules/nerfsd_pytorch3d.py:40-51).
+ *
+ * A operand, linear mode (conv == 0): up to two K-segments, a0 [M, k0] (row stride lda0 elements)
+ *   followed by a1 [M, k1] — the second segment is how a channel concatenation
+ *   (th.cat([h, hs.pop()], 1), openaimodel.py:1074) is consumed without materialising it.
+ * A operand, conv mode (conv == 1): a0 is an NHWC activation [B, H, W, C]; the kernel is an
+ *   implicit GEMM over the 9 taps of a stride-1, pad-1 3x3 convolution, K = 9*C, W packed as
+ *   [N, 9*C] with k = (ky*3+kx)*C + c.  Zero padding comes from TMA out-of-bounds fill.
+ * W: bf16 [N, K] row-major (nn.Linear layout).  K segments must be multiples of 8.
+ * Epilogue, in order: + bias[n] (fp32) ; + row_bias[m / rows_per_group, n] (fp32, the ResBlock
+ *   timestep-embedding add, openaimodel.py:374) ; activation ; [GEGLU] ; + residual[m, n] (bf16) ;
+ *   store bf16 or fp32.
+ * GEGLU (geglu == 1): W/bias rows are pre-interleaved in blocks of `BN/2` so that every N tile
+ *   holds [x-part | gate-part]; out[m, j] = x * gelu_erf(gate), out has N/2 columns
+ *   (attention.py:94-96).  Use cd360_geglu_pack_block() to learn the block size.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct cd360_gemm_args {
+  const void* a0;
+  int64_t lda0; /* elements; ignored in conv mode */
+  int32_t k0;
+  const void* a1;
+  int64_t lda1;
+  int32_t k1;
+  const void* w;
+  const float* bias;     /* [N] or NULL */
+  const float* row_bias; /* [ceil(M / rows_per_group), N] or NULL */
+  int32_t rows_per_group;
+  const void* residual; /* bf16 [M, N_out] or NULL */
+  int64_t ldr;
+  void* out; /* bf16 (out_fp32 == 0) or fp32 [M, N_out] */
+  int64_t ldo;
+  int32_t out_fp32;
+  int32_t M, N;
+  int32_t conv; /* 0 linear, 1 conv3x3 stride 1 pad 1 */
+  int32_t B, H, W, C;
+  int32_t act;   /* CD360_ACT_* */
+  int32_t geglu; /* 0 / 1 */
+  int32_t block_n; /* 0 = auto, else 128 or 256 */
+  int32_t max_ctas; /* 0 = one per SM */
+} cd360_gemm_args;
+
+int cd360_gemm_bf16(const cd360_gemm_args* args, cd360_stream_t stream);
+/* Rows of the interleave block used by the GEGLU epilogue for a given N (= BN/2). */
+int cd360_geglu_pack_block(int32_t n_total);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention, head dim 64, softmax(Q K^T / 8) V, bf16 in / fp32 softmax / bf16 out.
+ * Replaces xformers.ops.memory_efficient_attention as called from
+ * MemoryEfficientCrossAttention.forward (attention.py:393-418), including the head
+ * split/merge permutes: Q/K/V are read in place from [B, n, heads*64] projections (row strides
+ * ldq/ldk/ldv elements, so a fused QKV buffer works) and O is written as [B, nq, heads*64].
+ * nkv need not be a multiple of the tile (77 text tokens): the tail is masked.
+ * --------------------------------------------------------------------------------------------- */
+int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                         int64_t ldv, void* o, int64_t ldo, int32_t batch, int32_t heads,
+                         int32_t nq, int32_t nkv, cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups) [+ SiLU] over NHWC bf16, fp32 statistics (GroupNorm32, util.py:309-311;
+ * Normalize, attention.py:118).  Two launches inside: partial moments, then normalise(+SiLU).
+ * The input may be the channel concatenation of two tensors (x0 [B*HW, c0] ‖ x1 [B*HW, c1]).
+ * workspace: fp32, at least cd360_groupnorm_workspace_floats(B, HW) floats.
+ * --------------------------------------------------------------------------------------------- */
+int64_t cd360_groupnorm_workspace_floats(int32_t batch, int32_t hw);
+int cd360_groupnorm_silu_bf16(const void* x0, int32_t c0, const void* x1, int32_t c1,
+                              const float* gamma, const float* beta, void* out, float* workspace,
+                              int32_t batch, int32_t hw, float eps, int32_t apply_silu,
+                              cd360_stream_t stream);
+
+/* LayerNorm over the channel dim of [rows, c] bf16 -> bf16 (nn.LayerNorm, attention.py:531-533). */
+int cd360_layernorm_bf16(const void* x, const float* gamma, const float* beta, void* out,
+                         int32_t rows, int32_t c, float eps, cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small-M linear for the embedding path: out[b, n] = act_out( sum_k act_in(x[b,k]) W[n,k] + bias[n] )
+ * (+ add[b, n]).  x, out, add fp32; W bf16.  time_embed / label_emb (openaimodel.py:679-713,
+ * 1026-1031) and ResBlock.emb_layers (openaimodel.py:307-313) for all blocks at once.
+ * --------------------------------------------------------------------------------------------- */
+int cd360_small_linear(const float* x, const void* w, const float* bias, const float* add,
+                       float* out, int32_t batch, int32_t n, int32_t k, int32_t act_in,
+                       int32_t act_out, cd360_stream_t stream);
+
+/* timestep_embedding(t, dim) = [cos(t f_k) ‖ sin(t f_k)], f_k = exp(-ln(1e4) k / (dim/2))
+ * (util.py:206-230).  t fp32 [batch]; out fp32 [batch, dim]. */
+int cd360_timestep_embedding(const float* t, float* out, int32_t batch, int32_t dim,
+                             cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / resampling helpers around the convolutions.
+ * --------------------------------------------------------------------------------------------- */
+/* x fp32 NCHW [B, Cin, H, W] * scale[b] -> im2col bf16 [B*H*W, kpad] for the 3x3 pad-1 input conv
+ * (openaimodel.py:720); k = (ky*3+kx)*Cin + c, zero padded to kpad.  scale may be NULL. */
+int cd360_im2col3x3_nchw_f32(const float* x, const float* scale, void* out, int32_t batch,
+                             int32_t cin, int32_t h, int32_t w, int32_t kpad,
+                             cd360_stream_t stream);
+/* NHWC bf16 [B,H,W,C] -> im2col bf16 [B*(H/2)*(W/2), 9*C] of a stride-2 pad-1 3x3 conv
+ * (Downsample, openaimodel.py:215-222). */
+int cd360_im2col3x3_s2_bf16(const void* x, void* out, int32_t batch, int32_t h, int32_t w,
+                            int32_t c, cd360_stream_t stream);
+/* nearest x2 upsample, NHWC bf16 (Upsample.forward, openaimodel.py:161). */
+int cd360_upsample_nearest2x_bf16(const void* x, void* out, int32_t batch, int32_t h, int32_t w,
+                                  int32_t c, cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sampler-side elementwise math (fp32, NCHW latents).
+ * --------------------------------------------------------------------------------------------- */
+/* One guided Euler step, fused: eps is the UNet output for the G guidance rows of each image,
+ * fp32 [G*N, hw, 4] (NHWC); x fp32 NCHW [N,4,h,w] updated in place.
+ *   D_g   = x - sigma_q * eps_g   (EpsScaling c_out=-sigma_q, c_skip=1, denoiser.py:44; sigma_q is
+ *                                  sigma after DiscreteDenoiser's table quantisation, :65-73)
+ *   G==3: D = D_u + s (D_c - D_ic) + s_im (D_ic - D_u)   (ScheduledCFGImgTextRef, guiders.py:111-114)
+ *   G==2: D = D_u + s (D_c - D_u)                        (VanillaCFGImgRef, guiders.py:147-150)
+ *   x    += (x - D) / sigma * (sigma_next - sigma)       (to_d + Euler, sampling.py:103-106)
+ * denoised_out (optional) receives D. */
+int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_out, int32_t n_img,
+                         int32_t guidance_rows, int32_t hw, float sigma_q, float sigma,
+                         float sigma_next, float scale, float scale_im, cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * FeatureNeRF (sgm/modules/nerfsd_pytorch3d.py, sgm/modules/utils_cameraray.py).
+ * Cameras are packed fp32 [b, n+1, 16] = R(9, row-major, PyTorch3D row-vector convention
+ * X_cam = X_world R + T) | T(3) | focal(2) | principal point(2); index 0 = target camera.
+ * --------------------------------------------------------------------------------------------- */
+/* Per (b, ray, sample, view) geometry: projects the target-ray sample points into every reference
+ * view and emits
+ *   pe      bf16 [b, n, hw, d, kpe]   the 198 positional features of plane_coefs' input
+ *                                     (nerfsd_pytorch3d.py:102-134), zero padded to kpe
+ *   gidx    int32 [b, n, hw, d, 4]    flat pixel indices of the 4 bilinear corners (or -1)
+ *   gwgt    fp32  [b, n, hw, d, 4]    bilinear weights (grid_sample align_corners=True, zeros
+ *                                     padding, grid = clip(nan_to_num(-ndc), +-1.2); :79-98)
+ *   vlogit  fp32  [b, n, hw, d]       geometry part of the nviews logit (:139-151), without the
+ *                                     gathered-feature term
+ * depths: fp32 [hw, d] sample depths along each target ray (Raymarcher, :308-330);
+ * xy: fp32 [hw, 2] NDC ray positions (get_patch_raybundle, utils_cameraray.py:103-158).
+ * w_nv_geo: fp32 [198] the non-feature columns of nviews.weight, b_nv its bias. */
+int cd360_nerf_points(const float* cams, const float* xy, const float* depths,
+                      const float* w_nv_geo, float b_nv, void* pe, int32_t* gidx, float* gwgt,
+                      float* vlogit, int32_t b, int32_t n, int32_t res, int32_t d, int32_t kpe,
+                      cd360_stream_t stream);
+/* Combine: for every (b, ray, sample): h_v = SiLU(hpre[b,v,p,:] + bilinear(G[b,v], gidx,gwgt)[:c]);
+ * logit_v = vlogit + bilinear(G[b,v])[c]; a = softmax_v(logit); s = sum_v a_v h_v.
+ * G: bf16 [b, n, hw, ldg] (first Linear hoisted through the gather: G = xref W1f^T ‖ xref w_nv_f),
+ * hpre: bf16 [b, n, hw*d, c] (= pe W1p^T + b1).  Outputs s bf16 [b, hw*d, c] and the view softmax
+ * fp32 [b, n, hw*d] (plane_features_attn, :139-155). */
+int cd360_nerf_combine(const void* g, int64_t ldg, const void* hpre, const int32_t* gidx,
+                       const float* gwgt, const float* vlogit, void* s, float* view_softmax,
+                       int32_t b, int32_t n, int32_t hw, int32_t d, int32_t c,
+                       cd360_stream_t stream);
+/* Volume rendering (VolRender.forward, nerfsd_pytorch3d.py:170-231; trunc_exp attention.py:192-208;
+ * sigmoid on rgb attention.py:594).  feats bf16 [b, hw, d, c]; raw fp32 [b, hw, d, 4] =
+ * (rgb_raw 3, sigma_raw 1); dists fp32 [hw, d].  Outputs rendered bf16 [b, hw, c],
+ * fg fp32 [b, hw], alphas fp32 [b, hw, d], rgb fp32 [b, hw, 3]. */
+int cd360_nerf_volrender(const void* feats, const float* raw, const float* dists, void* rendered,
+                         float* fg, float* alphas, float* rgb, int32_t b, int32_t hw, int32_t d,
+                         int32_t c, cd360_stream_t stream);
+
+/* Utility: fp32 -> bf16 and bf16 -> fp32 contiguous conversion (weight prepack, I/O). */
+int cd360_cast_f32_to_bf16(const float* x, void* out, int64_t n, cd360_stream_t stream);
+int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n, cd360_stream_t stream);
+/* NHWC bf16/fp32 [B, hw, C] -> NCHW fp32 [B, C, hw] (module outputs at the sgm boundary). */
+int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t batch,
+                           int32_t hw, int32_t c, cd360_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CD360_H_ */

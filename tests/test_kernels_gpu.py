@@ -1,0 +1,289 @@
+"""Per-kernel numerics: every CUDA kernel in libcd360.so against a plain PyTorch fp32 reference of
+the same op, called through the C ABI (ctypes).  Inputs are bf16-rounded before the fp32 reference
+so the only differences are accumulation order and the final bf16 rounding of the output.
+
+Tolerances (stated per test): bf16 output rounding is 2^-9 relative; fp32-accumulated contractions
+of bf16 inputs add ~1e-6 relative, so |err| <= 1.5 * 2^-9 * |ref| + small absolute floor.
+"""
+import math
+
+import pytest
+import torch
+
+gpu = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rt(x):
+    """round-trip through bf16, return (bf16 tensor, fp32 value of it)"""
+    xb = x.to(torch.bfloat16)
+    return xb, xb.float()
+
+
+def _assert_close(out, ref, rel=2.0 ** -8, abs_=1e-3, what=""):
+    out = out.float()
+    err = (out - ref).abs()
+    tol = rel * ref.abs() + abs_
+    bad = (err > tol)
+    assert not bad.any(), (
+        f"{what}: {int(bad.sum())} / {bad.numel()} elements out of tolerance; "
+        f"max err {float(err.max()):.4g} at ref {float(ref.flatten()[err.argmax()]):.4g}")
+
+
+@gpu
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128),
+    (256, 256, 128, 256),
+    (300, 384, 200, 0),       # ragged M, K tail (zero-filled by TMA)
+    (1024, 640, 640, 0),
+    (3072, 1280, 1280, 256),
+    (231, 2560, 2048, 0),     # text-context K/V projection shape (3 x 77 tokens)
+    (777, 72, 136, 128),      # N not a multiple of 32: scalar tail path
+])
+def test_gemm_linear(M, N, K, bn):
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(0)
+    a, af = _rt(torch.randn(M, K, device=_dev()))
+    w, wf = _rt(torch.randn(N, K, device=_dev()) / math.sqrt(K))
+    bias = torch.randn(N, device=_dev())
+    res, resf = _rt(torch.randn(M, N, device=_dev()))
+    out = ops.gemm(a, w, bias=bias, residual=res, block_n=bn)
+    ref = af @ wf.t() + bias + resf
+    _assert_close(out, ref, what="gemm+bias+residual")
+    out32 = ops.gemm(a, w, out_fp32=True, block_n=bn)
+    _assert_close(out32, af @ wf.t(), rel=1e-4, abs_=1e-4, what="gemm fp32 out")
+
+
+@gpu
+def test_gemm_persistent_many_tiles():
+    """More tiles than CTAs: exercises the smem ring wrap-around and TMEM double buffering."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 2048, 1024, 320
+    a, af = _rt(torch.randn(M, K, device=_dev()))
+    w, wf = _rt(torch.randn(N, K, device=_dev()) / math.sqrt(K))
+    for max_ctas in (1, 3, 0):
+        out = ops.gemm(a, w, max_ctas=max_ctas, block_n=128)
+        _assert_close(out, af @ wf.t(), what=f"gemm max_ctas={max_ctas}")
+
+
+@gpu
+def test_gemm_two_segments_silu_rowbias():
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200._lib import ACT_SILU
+    torch.manual_seed(2)
+    M, N, K0, K1 = 512, 320, 128, 64
+    a0, a0f = _rt(torch.randn(M, K0, device=_dev()))
+    a1, a1f = _rt(torch.randn(M, K1, device=_dev()))
+    w, wf = _rt(torch.randn(N, K0 + K1, device=_dev()) / math.sqrt(K0 + K1))
+    rb = torch.randn(4, N, device=_dev())
+    out = ops.gemm(a0, w, a1=a1, row_bias=rb, rows_per_group=128, act=ACT_SILU)
+    ref = torch.cat([a0f, a1f], 1) @ wf.t() + rb.repeat_interleave(128, 0)
+    ref = torch.nn.functional.silu(ref)
+    _assert_close(out, ref, what="gemm cat+row_bias+silu")
+
+
+@gpu
+@pytest.mark.parametrize("c", [64, 128, 640])
+def test_gemm_geglu(c):
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200.sgm.prepack import pack_geglu
+    torch.manual_seed(3)
+    M = 384
+    a, af = _rt(torch.randn(M, c, device=_dev()))
+    w, wf = _rt(torch.randn(8 * c, c, device=_dev()) / math.sqrt(c))
+    bias = torch.randn(8 * c, device=_dev())
+    wp, bp = pack_geglu(w, bias)
+    out = ops.gemm(a, wp, bias=bp, geglu=True)
+    h = af @ wf.t() + bias
+    x, gate = h.chunk(2, dim=-1)
+    ref = x * torch.nn.functional.gelu(gate)
+    _assert_close(out, ref, abs_=2e-3, what="geglu")
+
+
+@gpu
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (1, 16, 16, 64, 64),
+    (3, 8, 8, 128, 192),      # tile spans two images (H*W = 64)
+    (2, 4, 4, 64, 64),        # 8 images per tile, ragged last tile
+    (2, 32, 32, 320, 640),
+    (1, 128, 128, 64, 128),   # tw = 128, one image row per tile
+])
+def test_conv3x3(B, H, W, Cin, Cout):
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200.sgm.prepack import pack_conv3x3
+    torch.manual_seed(4)
+    x, xf = _rt(torch.randn(B, Cin, H, W, device=_dev()))
+    w, wf = _rt(torch.randn(Cout, Cin, 3, 3, device=_dev()) / math.sqrt(9 * Cin))
+    bias = torch.randn(Cout, device=_dev())
+    emb = torch.randn(B, Cout, device=_dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cin)
+    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, bias=bias, row_bias=emb)
+    ref = torch.nn.functional.conv2d(xf, wf, bias, padding=1) + emb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    _assert_close(out, ref, what="conv3x3")
+
+
+@gpu
+@pytest.mark.parametrize("batch,heads,nq,nkv", [
+    (1, 1, 128, 128),
+    (2, 2, 256, 256),
+    (3, 10, 1024, 1024),
+    (3, 4, 256, 77),          # text cross-attention: masked KV tail
+    (1, 2, 64, 200),          # ragged queries and keys
+    (2, 20, 384, 77),
+])
+def test_attention(batch, heads, nq, nkv):
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(5)
+    c = heads * 64
+    q, qf = _rt(torch.randn(batch * nq, c, device=_dev()))
+    k, kf = _rt(torch.randn(batch * nkv, c, device=_dev()))
+    v, vf = _rt(torch.randn(batch * nkv, c, device=_dev()))
+    out = ops.attention(q, k, v, batch, heads, nq, nkv)
+
+    def split(t, n):
+        return t.view(batch, n, heads, 64).permute(0, 2, 1, 3)
+    ref = torch.nn.functional.scaled_dot_product_attention(split(qf, nq), split(kf, nkv),
+                                                           split(vf, nkv))
+    ref = ref.permute(0, 2, 1, 3).reshape(batch * nq, c)
+    # P is rounded to bf16 before the PV product (flash-attention practice): 2^-9 relative on
+    # each probability, averaged over the row -> well below 2^-7 relative on the output
+    _assert_close(out, ref, rel=2.0 ** -6, abs_=4e-3, what="attention")
+
+
+@gpu
+def test_attention_fused_qkv_strides():
+    """Q/K/V read in place from one [M, 3c] projection buffer."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(6)
+    batch, heads, n = 2, 5, 256
+    c = heads * 64
+    qkv, qkvf = _rt(torch.randn(batch * n, 3 * c, device=_dev()))
+    out = ops.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], batch, heads, n, n,
+                        ldq=3 * c, ldk=3 * c, ldv=3 * c)
+
+    def split(t):
+        return t.reshape(batch, n, heads, 64).permute(0, 2, 1, 3)
+    ref = torch.nn.functional.scaled_dot_product_attention(
+        split(qkvf[:, :c]), split(qkvf[:, c:2 * c]), split(qkvf[:, 2 * c:]))
+    ref = ref.permute(0, 2, 1, 3).reshape(batch * n, c)
+    _assert_close(out, ref, rel=2.0 ** -6, abs_=4e-3, what="attention fused qkv")
+
+
+@gpu
+@pytest.mark.parametrize("B,HW,c0,c1,silu,eps", [
+    (2, 256, 64, 0, True, 1e-5),
+    (3, 1024, 320, 0, True, 1e-5),
+    (3, 4096, 640, 320, True, 1e-5),    # virtual concat (decoder skip)
+    (2, 64, 1280, 1280, True, 1e-5),    # 2560 channels: > 256 vectors per row
+    (3, 1024, 640, 0, False, 1e-6),     # SpatialTransformer.norm
+])
+def test_groupnorm(B, HW, c0, c1, silu, eps):
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(7)
+    x0, x0f = _rt(torch.randn(B * HW, c0, device=_dev()) * 2 + 0.5)
+    x1 = x1f = None
+    if c1:
+        x1, x1f = _rt(torch.randn(B * HW, c1, device=_dev()) - 0.3)
+    c = c0 + c1
+    gamma = torch.randn(c, device=_dev())
+    beta = torch.randn(c, device=_dev())
+    out = ops.groupnorm(x0, gamma, beta, B, HW, x1=x1, eps=eps, silu=silu)
+    xf = x0f if x1f is None else torch.cat([x0f, x1f], 1)
+    xn = xf.view(B, HW, c).permute(0, 2, 1)
+    ref = torch.nn.functional.group_norm(xn, 32, gamma, beta, eps)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(B * HW, c)
+    _assert_close(out, ref, abs_=2e-3, what="groupnorm")
+
+
+@gpu
+@pytest.mark.parametrize("rows,c", [(77, 64), (1000, 640), (3072, 1280), (5, 2048)])
+def test_layernorm(rows, c):
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(8)
+    x, xf = _rt(torch.randn(rows, c, device=_dev()) * 3 + 1)
+    gamma = torch.randn(c, device=_dev())
+    beta = torch.randn(c, device=_dev())
+    out = ops.layernorm(x, gamma, beta)
+    ref = torch.nn.functional.layer_norm(xf, (c,), gamma, beta, 1e-5)
+    _assert_close(out, ref, abs_=2e-3, what="layernorm")
+
+
+@gpu
+def test_timestep_embedding_and_small_linear():
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200._lib import ACT_SILU
+    torch.manual_seed(9)
+    t = torch.tensor([0.0, 1.0, 500.0, 999.0, 37.5], device=_dev())
+    emb = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=_dev()) / half)
+    args = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (emb - ref).abs().max() < 2e-4  # fp32 sincos of arguments up to ~1e3 rad
+    w, wf = _rt(torch.randn(1280, 320, device=_dev()) / math.sqrt(320))
+    bias = torch.randn(1280, device=_dev())
+    add = torch.randn(5, 1280, device=_dev())
+    out = ops.small_linear(emb, w, bias, add=add, act_in=ACT_SILU, act_out=ACT_SILU)
+    ref2 = torch.nn.functional.silu(torch.nn.functional.silu(emb) @ wf.t() + bias) + add
+    assert (out - ref2).abs().max() < 1e-3
+    # K = 2816 (label_emb input), batch > chunk
+    x = torch.randn(7, 2816, device=_dev())
+    w2, w2f = _rt(torch.randn(96, 2816, device=_dev()) / math.sqrt(2816))
+    out2 = ops.small_linear(x, w2)
+    assert (out2 - x @ w2f.t()).abs().max() < 1e-3
+
+
+@gpu
+def test_layout_helpers():
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(10)
+    B, Cin, H, W = 2, 4, 16, 16
+    x = torch.randn(B, Cin, H, W, device=_dev())
+    scale = torch.tensor([0.5, 2.0], device=_dev())
+    col = ops.im2col3x3_nchw(x, 64, scale=scale)
+    ref = torch.nn.functional.unfold(x * scale[:, None, None, None], 3, padding=1)  # [B, C*9, HW]
+    ref = ref.view(B, Cin, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 36)
+    assert (col[:, :36].float() - ref.to(torch.bfloat16).float()).abs().max() == 0
+    assert col[:, 36:].abs().max() == 0
+    # stride-2 im2col
+    C = 64
+    xb, xbf = _rt(torch.randn(B, C, H, W, device=_dev()))
+    x_nhwc = xb.permute(0, 2, 3, 1).contiguous().view(B * H * W, C)
+    col2 = ops.im2col3x3_s2(x_nhwc, B, H, W)
+    ref2 = torch.nn.functional.unfold(xbf, 3, padding=1, stride=2)
+    ref2 = ref2.view(B, C, 9, (H // 2) * (W // 2)).permute(0, 3, 2, 1).reshape(-1, 9 * C)
+    assert (col2.float() - ref2).abs().max() == 0
+    up = ops.upsample_nearest2x(x_nhwc, B, H, W)
+    ref3 = torch.nn.functional.interpolate(xbf, scale_factor=2, mode="nearest")
+    ref3 = ref3.permute(0, 2, 3, 1).reshape(-1, C)
+    assert (up.float() - ref3).abs().max() == 0
+    back = ops.nhwc_to_nchw_f32(x_nhwc, B, H * W, C)
+    assert (back.view(B, C, H, W) - xbf).abs().max() == 0
+
+
+@gpu
+def test_cfg_euler_step():
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(11)
+    N, L = 2, 8
+    hw = L * L
+    x = torch.randn(N, 4, L, L, device=_dev())
+    eps = torch.randn(3 * N, hw, 4, device=_dev())
+    sigma, sigma_next, s, s_im = 3.7, 2.9, 7.5, 3.5
+    eps_nchw = eps.view(3 * N, L, L, 4).permute(0, 3, 1, 2)
+    den = torch.cat([x] * 3) - sigma * eps_nchw
+    d_u, d_ic, d_c = den.chunk(3)
+    D = d_u + s * (d_c - d_ic) + s_im * (d_ic - d_u)
+    ref = x + (x - D) / sigma * (sigma_next - sigma)
+    den_out = torch.empty_like(x)
+    out = ops.cfg_euler_step(x.clone(), eps, N, 3, hw, sigma, sigma, sigma_next, s, s_im,
+                             denoised_out=den_out)
+    assert (out - ref).abs().max() < 1e-4
+    assert (den_out - D).abs().max() < 1e-4
