@@ -1,0 +1,96 @@
+"""Oracle (oracle/sgm_oracle.py) against the committed golden vectors, which were produced by
+the reference's own modules (tests/golden/make_golden.py, reference commit 1a23f97).
+Runs anywhere (CPU, no reference checkout needed).  fp32 vs fp32: tolerance 2e-5 absolute on
+O(1) tensors (different op order / fused vs unfused kernels inside torch), exact for the schedule."""
+import os
+
+import pytest
+import torch
+
+from oracle import sgm_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "tiny_unet_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, map_location="cpu")
+
+
+def _inputs(cfg, gold):
+    inp = O.synthetic_inputs(cfg, gold["latent"], n_img=1, seed=0, n_views=gold["n_views"])
+    c = {"crossattn": inp["crossattn"], "vector": inp["vector"]}
+    uc = {"crossattn": torch.zeros_like(inp["crossattn"]), "vector": inp["vector"].clone()}
+    uc["vector"][:, : cfg["adm_in_channels"] // 2] = 0
+    return inp, c, uc
+
+
+def test_sigma_schedule_bit_exact(gold):
+    assert torch.equal(O.legacy_ddpm_sigmas(50), gold["sigmas_50"])
+    assert torch.equal(O.legacy_ddpm_sigmas(1000, do_append_zero=False, flip=True), gold["sigmas_1000_flip"])
+    assert torch.equal(O.legacy_ddpm_sigmas(gold["steps"]), gold["sigmas_%d" % gold["steps"]])
+
+
+def test_timestep_embedding(gold):
+    assert torch.equal(O.timestep_embedding(gold["t_emb_in"], 320), gold["t_emb_320"])
+
+
+def test_unet_pose_off(gold):
+    cfg = dict(O.TINY_CFG, image_cross_blocks=[])
+    sd = O.synthetic_state_dict(cfg, seed=1)
+    inp, c, _ = _inputs(dict(O.TINY_CFG), gold)
+    with torch.no_grad():
+        eps, aux = O.unet_forward(sd, cfg, inp["x"], torch.tensor([500]), c["crossattn"], c["vector"])
+    assert aux == []
+    assert (eps - gold["unet_eps_pose_off"]).abs().max() < 2e-5
+
+
+def test_unet_pose_on_and_cache(gold):
+    cfg = dict(O.TINY_CFG)
+    L, nv = gold["latent"], gold["n_views"]
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=nv + 1)
+    inp, c, uc = _inputs(cfg, gold)
+    x3 = torch.cat([inp["x"]] * 3)
+    ctx3 = torch.cat([uc["crossattn"], uc["crossattn"], c["crossattn"]])
+    y3 = torch.cat([uc["vector"], uc["vector"], c["vector"]])
+    t3 = torch.tensor([500, 500, 500])
+    cams = inp["cams"][0][None].expand(3, -1, -1)
+    cache = {}
+    with torch.no_grad():
+        eps, aux = O.unet_forward(sd, cfg, x3, t3, ctx3, y3, cams=cams, choices=list(range(nv)), cache=cache)
+        eps2, aux2 = O.unet_forward(sd, cfg, 0.9 * x3, t3 - 100, ctx3, y3, cams=cams,
+                                    choices=list(range(nv)), cache=cache)
+    assert (eps - gold["unet_eps_step0"]).abs().max() < 2e-5
+    assert (eps2 - gold["unet_eps_cached"]).abs().max() < 2e-5
+    assert aux2 == [] and len(aux) == len(gold["fg_masks"]) == len(O.pose_block_prefixes(cfg))
+    for (fg, al, rgb), gfg, gal, grgb in zip(aux, gold["fg_masks"], gold["alphas"], gold["rgbs"]):
+        assert (fg - gfg).abs().max() < 2e-6
+        assert (al - gal).abs().max() < 2e-6
+        assert (rgb - grgb).abs().max() < 2e-6
+
+
+def test_guided_euler_sampler(gold):
+    """EulerEDMSampler + DiscreteDenoiser + ScheduledCFGImgTextRef around the UNet, 4 steps."""
+    cfg = dict(O.TINY_CFG)
+    L, nv = gold["latent"], gold["n_views"]
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=nv + 1)
+    inp, c, uc = _inputs(cfg, gold)
+    cams = inp["cams"][0][None].expand(3, -1, -1)
+    cache = {}
+    den = O.DiscreteDenoiserOracle()
+
+    def network(x, c_noise, cond):
+        return O.unet_forward(sd, cfg, x, c_noise, cond["crossattn"], cond["vector"], cams=cams,
+                              choices=list(range(nv)), cache=cache) + (None, None)
+
+    def net4(x, c_noise, cond):
+        eps, aux = O.unet_forward(sd, cfg, x, c_noise, cond["crossattn"], cond["vector"], cams=cams,
+                                  choices=list(range(nv)), cache=cache)
+        return eps, None, None, None
+
+    denoise_fn = lambda x, s, cc: den(net4, x, s, cc)[0]
+    with torch.no_grad():
+        out = O.euler_edm_sample(denoise_fn, inp["x"].clone(), c, uc, gold["steps"], rows=3,
+                                 scale=7.5, scale_im=3.5)
+    ref = gold["sample_final"]
+    assert (out - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max()))
