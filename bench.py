@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — denoising-steps/sec of the pose-conditioned SDXL UNet step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" is one guided denoising step of ONE image = one EulerEDMSampler.sampler_step: UNet batch 3
+(ScheduledCFGImgTextRef) at 128x128 latents (1024^2 images, BASELINE configs[1] "sample.py car0"),
+FeatureNeRF pose conditioning on (8 reference views, 24 depth samples; rendered features cached
+after step 0 exactly as sample.py:123-133 does), CFG combine + Euler update included.
+Multi-GPU (torchrun, one rank per GPU): images shard across ranks (weak scaling, `n_img` images per
+GPU), no collective inside the loop, one all_gather of the final latents at the end.
+
+Prints ONE JSON line on rank 0 (see README / task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "denoising-steps/sec SDXL 1024^2 pose-cond"
+UNIT = "steps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p["bf16_tflops"], sustained=p["bf16_tflops_sustained"], hbm=p["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (restatement of the reference algorithm) on host cores
+# ------------------------------------------------------------------------------------------------
+
+def _oracle_forward_seconds(O, sd, cfg, latent, cache_feats, threads):
+    torch.set_num_threads(threads)
+    x = torch.randn(1, 4, latent, latent)
+    ctx = torch.randn(1, 77, cfg["context_dim"])
+    y = torch.randn(1, cfg["adm_in_channels"])
+    cache = {p: torch.randn(1, (latent // ds) ** 2, c) for p, c, ds in O.pose_block_prefixes(cfg)} if cache_feats else None
+    cams = torch.zeros(1, 9, 16) if cache_feats else None
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.unet_forward(sd, cfg, x, torch.tensor([500]), ctx, y, cams=cams, choices=list(range(8)), cache=cache)
+    return time.perf_counter() - t0
+
+
+def cpu_reference(steps: int, warmup: int, budget_s: float, latent: int = 128):
+    """Times the oracle's UNet forward for ONE CFG row (batch 1) with the pose blocks in their
+    steady state (cached rendered features -> pose_emb_layers only), fp32, all host threads;
+    a guided step is 3 such rows (CPU time is linear in batch).  Picks the largest latent
+    (128 preferred, else 64 scaled by the algorithmic FLOP ratio) that fits the time budget."""
+    from oracle import sgm_oracle as O
+    from custom_diffusion360_b200.synthetic import UNET_TFLOP_PER_ROW
+    threads = os.cpu_count() or 1
+    cfg = dict(O.SDXL_CFG)
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for name, shape in O.param_shapes(cfg).items():
+        if len(shape) == 1:
+            sd[name] = (torch.ones(shape) if name.endswith("weight") else torch.zeros(shape))
+        else:
+            sd[name] = torch.randn(shape, generator=g) / math.sqrt(float(torch.tensor(shape[1:]).prod()))
+    t32 = _oracle_forward_seconds(O, sd, cfg, 32, True, threads)   # thread-pool / allocator warm-up
+    t32 = _oracle_forward_seconds(O, sd, cfg, 32, True, threads)
+    n = max(1, steps + warmup)
+    est128 = t32 * 17.0
+    use = 128 if (latent == 128 and est128 * n <= budget_s) else 64
+    if use == 64 and t32 * 4.1 * n > budget_s:
+        n = max(1, int(budget_s / (t32 * 4.1)))
+    times = [_oracle_forward_seconds(O, sd, cfg, use, True, threads) for _ in range(n)]
+    timed = times[min(warmup, len(times) - 1):] or times
+    t_row = sum(timed) / len(timed)
+    scale = UNET_TFLOP_PER_ROW[latent] / UNET_TFLOP_PER_ROW[use]
+    t_step = 3.0 * t_row * scale
+    sample = (f"oracle (fp32 torch CPU restatement of the reference UNet) forward of 1 of the 3 CFG rows at "
+              f"{use}x{use} latents, pose blocks in cached steady state, {len(timed)} timed evaluation(s); "
+              f"step time = 3 rows x {t_row:.2f} s" + (f" x FLOP ratio {scale:.3f} ({use}->{latent})" if use != latent else ""))
+    return dict(value=1.0 / t_step, unit=UNIT, cores=threads, kind="port", sample=sample), t_step, len(timed)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base, t_step, n_timed = cpu_reference(args.steps, args.warmup, budget_s=200.0, latent=args.latent)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"sample.py car0: SDXL UNet, {args.latent}x{args.latent} latents ({8 * args.latent}^2 px), "
+                        f"guided step (CFG rows 3, scale 7.5 / image scale 3.5), FeatureNeRF pose-cond "
+                        f"(8 reference views, 24 samples, cached after step 0), EDM Euler, 50-step DDPM sigma table",
+            "n_img_per_gpu": args.n_img, "unet_batch_per_gpu": 3 * args.n_img, "parallelism": f"image-parallel x{args.gpus}",
+            "l2": "inputs larger than L2: 5.1 GB of bf16 weights stream per step (L2 126 MB); no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--latent", type=int, default=128)
+    ap.add_argument("--n-img", dest="n_img", type=int, default=1, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    from custom_diffusion360_b200 import synthetic as S
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    cfg = dict(S.SDXL_CFG)
+    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+    with torch.device(dev):
+        engine = DiffusionEngine(
+            network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+            denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+                "num_idx": 1000,
+                "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+                "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"},
+                "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"}}},
+            sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+                "num_steps": 50, "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"},
+                "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef",
+                                  "params": {"scale": 7.5, "scale_im": 3.5}}}})
+    engine = engine.to(dev).eval()
+    net = engine.model.diffusion_model
+    S.init_random_weights_(net, seed=0)
+    net.register_references(S.make_references(net, args.latent, 8, dev, seed=rank))
+    engine.set_reference_choices(list(range(8)))
+    net.packed()
+    for m in net.modules():  # build the bf16 operand copies, then drop the fp32 masters' grads etc.
+        if hasattr(m, "packed") and m is not net:
+            try:
+                m.packed()
+            except StopIteration:
+                pass
+    cond, uc = S.make_conditioning(cfg, args.n_img, dev, seed=rank)
+    poses = [S.lookat_cameras(8, seed=rank * 100 + i, target_azimuth=0.35 + 0.5 * i) for i in range(args.n_img)]
+    shape = (4, args.latent, args.latent)
+    step = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, cond, uc, pose=poses, n_img=args.n_img,
+                           latent_shape=shape, use_graph=not args.no_graph)
+    sigmas = engine.sampler.discretization(50, device="cpu")
+    g = torch.Generator(device=dev).manual_seed(30 + rank)  # sample.py seeds 30 (sample.py:213)
+    x_init = torch.randn(args.n_img, *shape, device=dev, generator=g) * float(torch.sqrt(1.0 + sigmas[0] ** 2))
+    x = x_init.clone()
+    nsig = len(sigmas) - 1
+
+    def sched(i):  # steady-state positions 1..48 of the 50-step schedule, cyclic
+        j = 1 + (i % (nsig - 1))
+        return float(sigmas[j]), float(sigmas[j + 1])
+
+    with torch.no_grad():
+        # ---- step 0: FeatureNeRF (once per image), timed on its own ----
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        step(x, float(sigmas[0]), float(sigmas[1]))
+        e1.record()
+        torch.cuda.synchronize()
+        step0_ms = e0.elapsed_time(e1)
+        # ---- warm-up (also captures the CUDA graph) ----
+        n0 = ops.LaunchStats.launches
+        step(x, *sched(0))
+        launches_per_step = ops.LaunchStats.launches - n0
+        for i in range(1, max(args.warmup, 3) + 1):
+            step(x, *sched(i))
+        torch.cuda.synchronize()
+        # ---- timed: K steps, device-resident latents ----
+        clocks = ClockSampler(local_rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks.start()
+        e0.record()
+        for i in range(args.steps):
+            if i % (nsig - 1) == 0:
+                x.copy_(x_init)
+            step(x, *sched(i))
+        if world > 1:  # the path's only collective: gather the final latents of all images
+            gathered = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(gathered, x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        # ---- e2e: same step through the host-buffer entry point (H2D + step + D2H every step) ----
+        xh = x_init.cpu().pin_memory()
+        step.step_host(xh, *sched(0))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            step.step_host(xh, *sched(i))
+        e1.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2)
+        # ---- per-kernel pass for the roofline: CUDA events around every tensor-core launch of one
+        #      eager steady-state step (same stream, after the timed region) ----
+        rec = {}
+
+        def hook(name, flops, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            rec.setdefault(name, []).append((flops, a, b))
+            return r
+
+        step.use_graph = False
+        ops.LaunchStats.hook = hook
+        step(x, *sched(1))
+        ops.LaunchStats.hook = None
+        torch.cuda.synchronize()
+        kern = {}
+        for name, items in rec.items():
+            fl = sum(f for f, _, _ in items)
+            tt = sum(a.elapsed_time(b) for _, a, b in items)
+            kern[name] = {"launches": len(items), "algorithmic_tflop": fl / 1e12, "ms": tt,
+                          "tflops": fl / 1e9 / tt if tt > 0 else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_img_total = args.n_img * world
+    value = n_img_total * args.steps / (ms / 1e3)
+    e2e_value = n_img_total * args.steps / (e2e_ms / 1e3)
+    tflop_step = 3 * S.UNET_TFLOP_PER_ROW.get(args.latent, float("nan")) * args.n_img
+    step_tflops = tflop_step * args.steps / (ms / 1e3)
+    gk = kern.get("gemm", {})
+    lat_bytes = args.n_img * 4 * args.latent * args.latent * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic (random-init SDXL-shaped weights, seeded latents / embeddings / cameras)",
+        "config": workload_config(args),
+        "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all linear + implicit-GEMM conv launches of one step)",
+                     "bound": "tensor", "achieved": gk.get("tflops"), "peak": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None, "traffic": None,
+                     "launches_per_step": gk.get("launches"), "algorithmic_tflop_per_step": gk.get("algorithmic_tflop"),
+                     "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
+        "roofline_step": {"bound": "tensor", "algorithmic_tflop_per_step": tflop_step,
+                          "achieved": step_tflops / world, "peak": peaks["sustained"], "unit": "TFLOP/s per GPU",
+                          "frac": step_tflops / world / peaks["sustained"],
+                          "peak_source": peaks["source"] + " sustained (kernel inside a long step)"},
+        "kernels": kern, "step0_featurenerf_ms": step0_ms,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": lat_bytes + 4 * (2 * 3 * args.n_img + 4),
+                "d2h_bytes_per_step": lat_bytes, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "cuda_graph": not args.no_graph, "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            base, _, _ = cpu_reference(1, 0, budget_s=30.0, latent=args.latent)
+            line["cpu_baseline"] = base
+        except Exception as e:  # the baseline is a reported extra, never the thing measured
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,15 +40,29 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libcd360.so")
 
 
-def _deps_mtime() -> float:
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+HASH_FILE = LIB + ".srchash"
+
+
+def _src_hash() -> str:
+    """Content hash of every input of the build (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    paths = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
     paths.append(os.path.join(HERE, "..", "include", "cd360.h"))
-    paths.append(os.path.abspath(__file__))
-    return max(os.path.getmtime(p) for p in paths)
+    for p in paths:
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
 
 
 def is_stale() -> bool:
-    return (not os.path.exists(LIB)) or os.path.getmtime(LIB) < _deps_mtime()
+    if not os.path.exists(LIB) or not os.path.exists(HASH_FILE):
+        return True
+    with open(HASH_FILE) as f:
+        return f.read().strip() != _src_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -86,6 +100,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     os.replace(LIB + ".tmp", LIB)
+    with open(HASH_FILE, "w") as f:
+        f.write(_src_hash())
     return LIB
 
 

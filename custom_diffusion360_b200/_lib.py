@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("a1", C.c_void_p), ("lda1", C.c_int64), ("k1", C.c_int32),
         ("w", C.c_void_p),
         ("bias", C.c_void_p),
-        ("row_bias", C.c_void_p), ("rows_per_group", C.c_int32),
+        ("row_bias", C.c_void_p), ("rows_per_group", C.c_int32), ("ld_row_bias", C.c_int64),
         ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64), ("out_fp32", C.c_int32),
         ("M", C.c_int32), ("N", C.c_int32),
@@ -53,16 +53,18 @@ SIGNATURES = {
     "cd360_layernorm_bf16": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "cd360_small_linear": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_timestep_embedding": (C.c_int, [_P, _P, _I, _I, _P]),
-    "cd360_im2col3x3_nchw_f32": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "cd360_im2col3x3_nchw_f32": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "cd360_im2col3x3_s2_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "cd360_upsample_nearest2x_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "cd360_cfg_euler_step": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _P]),
+    "cd360_cfg_euler_step_dev": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _F, _F, _P]),
     "cd360_nerf_points": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_combine": (C.c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
     "cd360_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
+    "cd360_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None

@@ -85,8 +85,8 @@ small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 // input conv im2col: x fp32 NCHW * scale[b] -> bf16 [B*H*W, kpad], k = (ky*3+kx)*Cin + c
 // (UNetModel.input_blocks[0], openaimodel.py:719-721; c_in scaling denoiser.py:42-43)
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                      __nv_bfloat16* __restrict__ out, int batch, int cin, int h,
-                                      int w, int kpad) {
+                                      __nv_bfloat16* __restrict__ out, int batch, int src_batch,
+                                      int cin, int h, int w, int kpad) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batch) * h * w * kpad;
   if (i >= total) return;
@@ -100,7 +100,9 @@ __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* 
     const int tap = kk / cin, c = kk - tap * cin;
     const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
     if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-      v = x[((static_cast<long long>(b) * cin + c) * h + yy) * w + xx];
+      // batch row b reads image b % src_batch: the CFG replication `torch.cat([x] * rows)`
+      // (guiders.py:133) is folded into the load
+      v = x[((static_cast<long long>(b % src_batch) * cin + c) * h + yy) * w + xx];
       if (scale) v *= scale[b];
     }
   }
@@ -173,11 +175,28 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
 }
 
+// NCHW fp32 [B, C, hw] -> [B, hw, C] bf16 (module inputs at the sgm boundary)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                    int batch, int hw, int c) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(batch) * hw * c;
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c);
+  const int p = static_cast<int>((i / c) % hw);
+  const int b = static_cast<int>(i / (static_cast<long long>(hw) * c));
+  out[i] = __float2bfloat16_rn(x[(static_cast<long long>(b) * c + ch) * hw + p]);
+}
+
 // Fused EpsScaling denoiser output + CFG combine + Euler step.  See include/cd360.h.
 __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict__ eps,
                                  float* __restrict__ denoised_out, int n_img, int g, int hw,
                                  float sigma_q, float sigma, float sigma_next, float scale,
-                                 float scale_im) {
+                                 float scale_im, const float* __restrict__ sig_dev) {
+  if (sig_dev != nullptr) {  // (sigma_q, sigma, sigma_next) live in device memory: graph-replayable
+    sigma_q = sig_dev[0];
+    sigma = sig_dev[1];
+    sigma_next = sig_dev[2];
+  }
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(n_img) * 4 * hw;
   if (i >= total) return;
@@ -238,15 +257,16 @@ extern "C" int cd360_small_linear(const float* x, const void* w, const float* bi
 }
 
 extern "C" int cd360_im2col3x3_nchw_f32(const float* x, const float* scale, void* out,
-                                        int32_t batch, int32_t cin, int32_t h, int32_t w,
-                                        int32_t kpad, cd360_stream_t stream_) {
+                                        int32_t batch, int32_t src_batch, int32_t cin, int32_t h,
+                                        int32_t w, int32_t kpad, cd360_stream_t stream_) {
   if (!x || !out) return CD360_ERR_NULL;
+  if (src_batch <= 0) src_batch = batch;
   if (batch <= 0 || cin <= 0 || h <= 0 || w <= 0 || kpad < 9 * cin || (kpad & 7))
     return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * h * w * kpad;
   im2col3x3_nchw_kernel<<<blocks_for(total, 256), 256, 0,
                           reinterpret_cast<cudaStream_t>(stream_)>>>(
-      x, scale, reinterpret_cast<__nv_bfloat16*>(out), batch, cin, h, w, kpad);
+      x, scale, reinterpret_cast<__nv_bfloat16*>(out), batch, src_batch, cin, h, w, kpad);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
@@ -307,6 +327,17 @@ extern "C" int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* o
   return CD360_OK;
 }
 
+extern "C" int cd360_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t batch, int32_t hw,
+                                           int32_t c, cd360_stream_t stream_) {
+  if (!x || !out) return CD360_ERR_NULL;
+  if (batch <= 0 || hw <= 0 || c <= 0) return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(batch) * hw * c;
+  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), batch, hw, c);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
 extern "C" int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_out, int32_t n_img,
                                     int32_t guidance_rows, int32_t hw, float sigma_q, float sigma,
                                     float sigma_next, float scale, float scale_im,
@@ -316,12 +347,26 @@ extern "C" int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_
   if (!(sigma > 0.f)) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(n_img) * 4 * hw;
   cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
-      x, eps, denoised_out, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next, scale, scale_im);
+      x, eps, denoised_out, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next, scale, scale_im,
+      nullptr);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
 
-extern "C" int cd360_abi_version(void) { return 1; }
+extern "C" int cd360_cfg_euler_step_dev(float* x, const float* eps, float* denoised_out,
+                                        int32_t n_img, int32_t guidance_rows, int32_t hw,
+                                        const float* sigmas3, float scale, float scale_im,
+                                        cd360_stream_t stream_) {
+  if (!x || !eps || !sigmas3) return CD360_ERR_NULL;
+  if (n_img <= 0 || hw <= 0 || guidance_rows < 1 || guidance_rows > 3) return CD360_ERR_SHAPE;
+  const long long total = static_cast<long long>(n_img) * 4 * hw;
+  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      x, eps, denoised_out, n_img, guidance_rows, hw, 0.f, 1.f, 0.f, scale, scale_im, sigmas3);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_abi_version(void) { return 2; }
 
 extern "C" const char* cd360_strerror(int code) {
   switch (code) {

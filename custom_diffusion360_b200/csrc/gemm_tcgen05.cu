@@ -32,6 +32,7 @@ struct GemmKParams {
   const float* bias;
   const float* row_bias;
   int rows_per_group;
+  long long ld_row_bias;
   const __nv_bfloat16* residual;
   long long ldr;
   void* out;
@@ -260,7 +261,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       const float* rb = nullptr;
       if (p.row_bias != nullptr && row_ok)
-        rb = p.row_bias + (row / p.rows_per_group) * static_cast<long long>(p.N);
+        rb = p.row_bias + (row / p.rows_per_group) * p.ld_row_bias;
 
       if (!p.geglu) {
 #pragma unroll 1
@@ -434,6 +435,8 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   p.bias = a->bias;
   p.row_bias = a->row_bias;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.ld_row_bias = a->ld_row_bias > 0 ? a->ld_row_bias : a->N;
+  if (a->row_bias && (p.ld_row_bias & 3)) return CD360_ERR_ALIGN;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
   p.ldr = a->ldr;
   p.out = a->out;

@@ -17,7 +17,15 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 
 
+class LaunchStats:
+    """Count of libcd360 kernel launches issued from this process (every wrapper below obtains
+    the stream exactly once per C-ABI call; GroupNorm is two launches)."""
+    launches = 0
+    hook = None  # optional callable(name:str, flops:float) -> context manager, set by bench.py
+
+
 def _stream() -> int:
+    LaunchStats.launches += 1
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -56,11 +64,19 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out
     args = GemmArgs(
         a0=_ptr(a), lda0=lda, k0=k0, a1=_ptr(a1), lda1=lda1, k1=k1, w=_ptr(w),
         bias=_ptr(bias), row_bias=_ptr(row_bias), rows_per_group=rows_per_group,
+        ld_row_bias=(row_bias.stride(0) if row_bias is not None else 0),
         residual=_ptr(residual), ldr=(residual.stride(0) if residual is not None else 0),
         out=_ptr(out), ldo=out.stride(0), out_fp32=int(out.dtype == f32), M=M, N=N,
         conv=0, B=0, H=0, W=0, C=0, act=act, geglu=int(geglu), block_n=block_n, max_ctas=max_ctas)
-    check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16")
+    _run("gemm", 2.0 * M * N * (k0 + k1),
+         lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16"))
     return out
+
+
+def _run(name, flops, fn):
+    """Launch through the optional profiling hook (bench.py brackets launches with CUDA events)."""
+    h = LaunchStats.hook
+    return fn() if h is None else h(name, flops, fn)
 
 
 def conv3x3(x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None, out_fp32=False,
@@ -77,11 +93,13 @@ def conv3x3(x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None,
         out = torch.empty((M, N), device=x.device, dtype=f32 if out_fp32 else bf16)
     args = GemmArgs(
         a0=_ptr(x), lda0=Cin, k0=9 * Cin, a1=0, lda1=0, k1=0, w=_ptr(w), bias=_ptr(bias),
-        row_bias=_ptr(row_bias), rows_per_group=H * W, residual=_ptr(residual),
+        row_bias=_ptr(row_bias), rows_per_group=H * W,
+        ld_row_bias=(row_bias.stride(0) if row_bias is not None else 0), residual=_ptr(residual),
         ldr=(residual.stride(0) if residual is not None else 0), out=_ptr(out), ldo=out.stride(0),
         out_fp32=int(out.dtype == f32), M=M, N=N, conv=1, B=B, H=H, W=W, C=Cin, act=ACT_NONE,
         geglu=0, block_n=block_n, max_ctas=max_ctas)
-    check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(conv)")
+    _run("gemm", 2.0 * M * N * 9 * Cin,
+         lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(conv)"))
     return out
 
 
@@ -101,9 +119,10 @@ def attention(q, k, v, batch, heads, nq, nkv, *, out=None, ldq=None, ldk=None, l
     ldv = v.stride(0) if ldv is None else ldv
     if out is None:
         out = torch.empty((batch * nq, heads * 64), device=q.device, dtype=bf16)
-    check(lib.cd360_attention_bf16(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out),
-                                   out.stride(0), batch, heads, nq, nkv, _stream()),
-          "cd360_attention_bf16")
+    _run("attention", 4.0 * batch * heads * nq * nkv * 64,
+         lambda: check(lib.cd360_attention_bf16(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(out),
+                                                out.stride(0), batch, heads, nq, nkv, _stream()),
+                       "cd360_attention_bf16"))
     return out
 
 
@@ -131,6 +150,7 @@ def groupnorm(x0, gamma, beta, batch, hw, *, x1=None, eps=1e-5, silu=True, out=N
         out = torch.empty((batch * hw, c0 + c1), device=x0.device, dtype=bf16)
     if workspace is None:
         workspace = groupnorm_workspace(batch, hw, x0.device)
+    LaunchStats.launches += 1  # stats + apply
     check(lib.cd360_groupnorm_silu_bf16(_ptr(x0), c0, _ptr(x1), c1, _ptr(gamma), _ptr(beta),
                                         _ptr(out), _ptr(workspace), batch, hw, eps, int(silu),
                                         _stream()), "cd360_groupnorm_silu_bf16")
@@ -172,13 +192,15 @@ def timestep_embedding(t, dim, *, out=None):
     return out
 
 
-def im2col3x3_nchw(x, kpad, *, scale=None, out=None):
+def im2col3x3_nchw(x, kpad, *, scale=None, out=None, batch=None):
+    """batch > x.shape[0] replicates the images cyclically (CFG rows) while loading."""
     lib = _lib.load()
     _req(x, f32, "x")
-    b, cin, h, w = x.shape
+    src_b, cin, h, w = x.shape
+    b = src_b if batch is None else batch
     if out is None:
         out = torch.empty((b * h * w, kpad), device=x.device, dtype=bf16)
-    check(lib.cd360_im2col3x3_nchw_f32(_ptr(x), _ptr(scale), _ptr(out), b, cin, h, w, kpad,
+    check(lib.cd360_im2col3x3_nchw_f32(_ptr(x), _ptr(scale), _ptr(out), b, src_b, cin, h, w, kpad,
                                        _stream()), "cd360_im2col3x3_nchw_f32")
     return out
 
@@ -217,6 +239,18 @@ def cfg_euler_step(x, eps, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next,
     return x
 
 
+def cfg_euler_step_dev(x, eps, n_img, guidance_rows, hw, sigmas3, scale, scale_im, *,
+                       denoised_out=None):
+    lib = _lib.load()
+    _req(x, f32, "x")
+    _req(eps, f32, "eps")
+    _req(sigmas3, f32, "sigmas3")
+    check(lib.cd360_cfg_euler_step_dev(_ptr(x), _ptr(eps), _ptr(denoised_out), n_img, guidance_rows,
+                                       hw, _ptr(sigmas3), float(scale), float(scale_im), _stream()),
+          "cd360_cfg_euler_step_dev")
+    return x
+
+
 def cast_bf16(x, *, out=None):
     lib = _lib.load()
     _req(x, f32, "x")
@@ -243,6 +277,19 @@ def nhwc_to_nchw_f32(x, batch, hw, c, *, out=None):
         out = torch.empty((batch, c, hw), device=x.device, dtype=f32)
     check(lib.cd360_nhwc_to_nchw_f32(_ptr(x), int(x.dtype == f32), _ptr(out), batch, hw, c,
                                      _stream()), "cd360_nhwc_to_nchw_f32")
+    return out
+
+
+def nchw_to_nhwc_bf16(x, *, out=None):
+    """fp32 [B, C, ...spatial] -> bf16 tokens [B*hw, C]."""
+    lib = _lib.load()
+    _req(x, f32, "x")
+    b, c = x.shape[:2]
+    hw = x.numel() // (b * c)
+    if out is None:
+        out = torch.empty((b * hw, c), device=x.device, dtype=bf16)
+    check(lib.cd360_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), b, hw, c, _stream()),
+          "cd360_nchw_f32_to_nhwc_bf16")
     return out
 
 

@@ -1,0 +1,422 @@
+"""Transformer / attention surface of the reference (sgm/modules/attention.py) on the sm_100a
+kernels: GEGLU, FeedForward, MemoryEfficientCrossAttention, BasicTransformerBlock (with the
+FeatureNeRF injection) and SpatialTransformer.
+
+Drop-in contract: class names, constructor kwargs, attribute names
+(`attn1/attn2/ff/norm1-3/pose_emb_layers/pose_featurenerf/renderer/rendered_feat/references`,
+`norm/proj_in/transformer_blocks/proj_out/use_linear/image_cross/poscontrol_interval`) and
+state-dict keys equal the reference's.  Two call paths exist per module:
+
+  * `forward(...)` — the reference's tensor contract ([B, N, c] / [B, c, H, W] fp32 in and out),
+    for callers that address sub-modules directly (sample.py's patched forwards do);
+  * `tokens(...)`   — bf16 token layout [B*N, c] straight between kernels, what UNetModel uses.
+
+Inference semantics built in (what sample.py:33-136 monkey-patches onto the reference): pose
+blocks read their reference tokens from the `references` buffer + `choices`, and cache
+`rendered_feat` after the first step until `clear_rendered_feat()`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._lib import ACT_NONE
+from ..prepack import pack_geglu
+from .nerfsd_pytorch3d import NerfSDModule, VolRender
+from .utils_cameraray import pack_pose
+
+bf16 = torch.bfloat16
+
+
+def to_tokens(x: torch.Tensor) -> torch.Tensor:
+    """[..., c] float tensor -> contiguous bf16 [rows, c]."""
+    t = x.reshape(-1, x.shape[-1])
+    if t.dtype == bf16:
+        return t.contiguous()
+    return ops.cast_bf16(t.float().contiguous())
+
+
+class _Packed:
+    """Lazily built bf16 / re-laid-out copies of a module's parameters (kernel operand layout)."""
+
+    def packed(self):
+        dev = next(self.parameters()).device
+        p = self.__dict__.get("_pk")
+        if p is None or p["dev"] != dev:
+            p = self._pack(dev)
+            p["dev"] = dev
+            self.__dict__["_pk"] = p
+        return p
+
+    def invalidate_packed(self):
+        self.__dict__["_pk"] = None
+
+
+def invalidate_all_packed(root: nn.Module):
+    for m in root.modules():
+        if isinstance(m, _Packed):
+            m.invalidate_packed()
+        if hasattr(m, "_packed"):
+            m._packed = None
+
+
+class Linear(nn.Linear, _Packed):
+    """nn.Linear whose forward is the tcgen05 GEMM (any leading dims)."""
+
+    def _pack(self, dev):
+        return dict(w=self.weight.detach().to(bf16).contiguous(),
+                    b=None if self.bias is None else self.bias.detach().float().contiguous())
+
+    def tokens(self, x, **kw):
+        p = self.packed()
+        return ops.gemm(x, p["w"], bias=p["b"], **kw)
+
+    def forward(self, x):
+        y = self.tokens(to_tokens(x))
+        return ops.cast_f32(y).view(*x.shape[:-1], self.out_features)
+
+
+class LayerNorm(nn.LayerNorm, _Packed):
+    def _pack(self, dev):
+        return dict(g=self.weight.detach().float().contiguous(), b=self.bias.detach().float().contiguous())
+
+    def tokens(self, x, out=None):
+        p = self.packed()
+        return ops.layernorm(x, p["g"], p["b"], eps=self.eps, out=out)
+
+    def forward(self, x):
+        return ops.cast_f32(self.tokens(to_tokens(x))).view(x.shape)
+
+
+class GEGLU(nn.Module, _Packed):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def _pack(self, dev):
+        w, b = pack_geglu(self.proj.weight.detach(), self.proj.bias.detach())
+        return dict(w=w, b=b)
+
+    def tokens(self, x):
+        p = self.packed()
+        return ops.gemm(x, p["w"], bias=p["b"], geglu=True)
+
+    def forward(self, x):
+        return ops.cast_f32(self.tokens(to_tokens(x))).view(*x.shape[:-1], self.proj.out_features // 2)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.0):
+        super().__init__()
+        if not glu:
+            raise NotImplementedError("only the gated (GEGLU) feed-forward of the SDXL config is built")
+        inner = int(dim * mult)
+        self.net = nn.Sequential(GEGLU(dim, inner), nn.Dropout(dropout), Linear(inner, dim_out or dim))
+
+    def tokens(self, xn, residual=None, out=None):
+        return self.net[2].tokens(self.net[0].tokens(xn), residual=residual, out=out)
+
+    def forward(self, x):
+        return ops.cast_f32(self.tokens(to_tokens(x))).view(x.shape)
+
+
+def Normalize(in_channels):
+    return nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class MemoryEfficientCrossAttention(nn.Module, _Packed):
+    """softmax(QK^T/8)V with to_q/to_k/to_v/to_out projections (reference :305-425).  Heads are
+    addressed in place by the attention kernel — no permute / contiguous copies."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.0,
+                 add_lora=False, **kwargs):
+        super().__init__()
+        if dim_head != 64:
+            raise NotImplementedError("attention kernel is specialised for head dim 64")
+        if add_lora:
+            raise NotImplementedError("add_lora=True is not built (shipped config: add_lora: False)")
+        inner = dim_head * heads
+        self.self_attention = context_dim is None
+        context_dim = context_dim or query_dim
+        self.heads = heads
+        self.dim_head = dim_head
+        self.add_lora = add_lora
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(dropout))
+
+    def _pack(self, dev):
+        q, k, v = (m.weight.detach().to(bf16) for m in (self.to_q, self.to_k, self.to_v))
+        p = dict(wo=self.to_out[0].weight.detach().to(bf16).contiguous(),
+                 bo=self.to_out[0].bias.detach().float().contiguous(), wq=q.contiguous(),
+                 wkv=torch.cat([k, v], 0).contiguous())
+        if self.self_attention:
+            p["wqkv"] = torch.cat([q, k, v], 0).contiguous()
+        return p
+
+    def project_context(self, ctx_tok):
+        """K|V of the context tokens, [B*nctx, 2*inner]."""
+        return ops.gemm(ctx_tok, self.packed()["wkv"])
+
+    def tokens(self, xn, batch, n, *, kv=None, nkv=None, residual=None, out=None):
+        """xn bf16 [batch*n, c] (already normalised).  kv: None -> self-attention on xn; else the
+        projected context [batch*nkv, 2*inner].  Returns to_out(attn) (+ residual)."""
+        p = self.packed()
+        inner = self.heads * self.dim_head
+        if kv is None:
+            qkv = ops.gemm(xn, p["wqkv"])
+            a = ops.attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], batch,
+                              self.heads, n, n, ldq=3 * inner, ldk=3 * inner, ldv=3 * inner)
+        else:
+            q = ops.gemm(xn, p["wq"])
+            a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, self.heads, n, nkv,
+                              ldq=inner, ldk=2 * inner, ldv=2 * inner)
+        return ops.gemm(a, p["wo"], bias=p["bo"], residual=residual, out=out)
+
+    def forward(self, x, context=None, mask=None, additional_tokens=None,
+                n_times_crossframe_attn_in_self=0):
+        if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
+            raise NotImplementedError("mask / additional_tokens / crossframe attention are unused on this path")
+        b, n, _ = x.shape
+        xt = to_tokens(x)
+        if context is None and self.self_attention:
+            y = self.tokens(xt, b, n)
+        else:
+            ctx = x if context is None else context
+            kv = self.project_context(to_tokens(ctx))
+            y = self.tokens(xt, b, n, kv=kv, nkv=ctx.shape[1])
+        return ops.cast_f32(y).view(b, n, -1)
+
+
+class BasicTransformerBlock(nn.Module):
+    ATTENTION_MODES = {
+        "softmax": MemoryEfficientCrossAttention,       # the reference's "softmax" class cannot be
+        "softmax-xformers": MemoryEfficientCrossAttention,  # constructed; same kernel
+    }
+
+    def __init__(self, dim, n_heads, d_head, dropout=0.0, context_dim=None, gated_ff=True,
+                 checkpoint=True, disable_self_attn=False, attn_mode="softmax", sdp_backend=None,
+                 image_cross=False, far=2, num_samples=32, add_lora=False, rgb_predict=False,
+                 mode="pixel-nerf", average=False, num_freqs=16, use_prev_weights_imp_sample=False,
+                 imp_sample_next_step=False, stratified=False, imp_sampling_percent=0.9,
+                 near_plane=0.0):
+        super().__init__()
+        assert attn_mode in self.ATTENTION_MODES
+        if disable_self_attn:
+            raise NotImplementedError("disable_self_attn is unused by the SDXL config")
+        attn_cls = self.ATTENTION_MODES[attn_mode]
+        self.add_lora = add_lora
+        self.image_cross = image_cross
+        self.rgb_predict = rgb_predict
+        self.use_prev_weights_imp_sample = use_prev_weights_imp_sample
+        self.imp_sample_next_step = imp_sample_next_step
+        self.disable_self_attn = disable_self_attn
+        self.rendered_feat = None
+        self.choices: Optional[Sequence[int]] = None
+        self.attn1 = attn_cls(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
+                              add_lora=add_lora, context_dim=None)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = attn_cls(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                              dropout=dropout, add_lora=add_lora)
+        if image_cross:
+            self.pose_emb_layers = Linear(2 * dim, dim, bias=False)
+            nn.init.eye_(self.pose_emb_layers.weight)
+            self.pose_featurenerf = NerfSDModule(
+                mode=mode, out_channels=dim, far_plane=far, num_samples=num_samples,
+                rgb_predict=rgb_predict, average=average, num_freqs=num_freqs, stratified=stratified,
+                imp_sampling_percent=imp_sampling_percent, near_plane=near_plane)
+            self.renderer = VolRender()
+        self.norm1 = LayerNorm(dim)
+        self.norm2 = LayerNorm(dim)
+        self.norm3 = LayerNorm(dim)
+        self.checkpoint = checkpoint
+        self._ctxref_cache = None
+
+    # ---- FeatureNeRF -------------------------------------------------------------------------
+    def context_ref_tokens(self, batch: int) -> torch.Tensor:
+        """Reference tokens per CFG row from the stored `references` buffer (sample.py:85-96):
+        row group 0 -> the 'null' reference (last row) repeated n times, other groups -> the chosen
+        real references.  bf16 [batch*n*hw, c]; cached (static across the sampling loop)."""
+        refs = self.references
+        choices = list(self.choices) if self.choices is not None else list(range(refs.shape[0] - 1))
+        key = (batch, tuple(choices), refs.data_ptr())
+        if self._ctxref_cache is not None and self._ctxref_cache[0] == key:
+            return self._ctxref_cache[1]
+        rows = 3 if batch % 3 == 0 else 2
+        bs = batch // rows
+        n = len(choices)
+        real = refs[:-1][choices]                          # [n, hw, c]
+        null = refs[-1:].expand(n, -1, -1)
+        per_group = [null] + [real] * (rows - 1)
+        full = torch.stack([g for g in per_group for _ in range(bs)])  # [batch, n, hw, c]
+        tok = to_tokens(full.contiguous())
+        self._ctxref_cache = (key, tok, n)
+        return tok
+
+    def reference_tokens(self, cams, xref_tok, n, kv, nkv, batch, hw):
+        """reference_attn (reference :571-598) in token layout -> (rendered bf16 [batch*hw, c],
+        fg [batch,hw], alphas [batch,hw,d], rgb [batch,hw,3])."""
+        nerf = self.pose_featurenerf
+        d = nerf.raymarcher.num_samples
+        feats, raw, dists, _ = nerf.encode_tokens(cams, xref_tok, batch, n, hw)
+        # feats += attn2(norm2(feats), context): the block's own norm2 / attn2 over every sample
+        fn = self.norm2.tokens(feats)
+        feats = self.attn2.tokens(fn, batch, hw * d, kv=kv, nkv=nkv, residual=feats, out=feats)
+        if raw.shape[-1] != 4:
+            raw4 = torch.zeros(raw.shape[0], 4, device=raw.device, dtype=torch.float32)
+            raw4[:, 3] = raw[:, -1]
+            raw = raw4
+        c = feats.shape[-1]
+        return ops.nerf_volrender(feats, raw, dists, batch, hw, d, c)
+
+    def reference_attn(self, x, context_ref, context, pose, prev_weights, mask_ref):
+        """Reference-signature variant: context_ref [b, n, hw, c], context [b, 77, ctx]."""
+        if mask_ref is not None:
+            raise NotImplementedError("mask_ref is not supported on the inference path")
+        b, n, hw, c = context_ref.shape
+        cams = pack_pose(pose, x.device)
+        kv = self.attn2.project_context(to_tokens(context))
+        rendered, fg, alphas, rgb = self.reference_tokens(cams, to_tokens(context_ref), n, kv,
+                                                          context.shape[1], b, hw)
+        d = alphas.shape[-1]
+        return (ops.cast_f32(rendered).view(b, hw, c), fg.view(b, hw, 1), None,
+                alphas.view(b, hw, d, 1), rgb if self.rgb_predict else None)
+
+    # ---- token fast path -----------------------------------------------------------------------
+    def tokens(self, x, batch, n, ctx_tok, nctx, cams=None):
+        """x bf16 [batch*n, c] (updated in place where possible) -> (x, aux | None)."""
+        aux = None
+        x = self.attn1.tokens(self.norm1.tokens(x), batch, n, residual=x, out=x)
+        kv = self.attn2.project_context(ctx_tok)
+        x = self.attn2.tokens(self.norm2.tokens(x), batch, n, kv=kv, nkv=nctx, residual=x, out=x)
+        if self.image_cross and cams is not None:
+            if self.rendered_feat is None:
+                xref_tok = self.context_ref_tokens(batch)
+                n_views = self._ctxref_cache[2]
+                rendered, fg, alphas, rgb = self.reference_tokens(cams, xref_tok, n_views, kv, nctx,
+                                                                  batch, n)
+                # persistent buffer: a captured CUDA graph keeps reading this address after
+                # clear_rendered_feat() and the next image's step 0
+                buf = self.__dict__.get("_rendered_buf")
+                if buf is None or buf.shape != rendered.shape or buf.device != rendered.device:
+                    buf = rendered
+                    self.__dict__["_rendered_buf"] = buf
+                else:
+                    buf.copy_(rendered)
+                self.rendered_feat = buf
+                aux = (fg, alphas, rgb)
+            x = self.pose_emb_layers.tokens(x, a1=self.rendered_feat)  # Linear(cat[x, xref]) w/o the cat
+        x = self.ff.tokens(self.norm3.tokens(x), residual=x, out=x)
+        return x, aux
+
+    # ---- reference-signature entry point ---------------------------------------------------------
+    def forward(self, x, context=None, context_ref=None, pose=None, mask_ref=None, prev_weights=None,
+                additional_tokens=None, n_times_crossframe_attn_in_self=0):
+        b, n, c = x.shape
+        xt = to_tokens(x).clone()
+        ctx_tok = to_tokens(context)
+        cams = pack_pose(pose, x.device) if (pose is not None and self.image_cross) else None
+        fg = alphas = rgb = None
+        if cams is not None and context_ref is not None and not hasattr(self, "references"):
+            # training-style call: explicit reference tokens [(b n), hw, c]
+            xt = self.attn1.tokens(self.norm1.tokens(xt), b, n, residual=xt, out=xt)
+            kv = self.attn2.project_context(ctx_tok)
+            xt = self.attn2.tokens(self.norm2.tokens(xt), b, n, kv=kv, nkv=context.shape[1],
+                                   residual=xt, out=xt)
+            nv = context_ref.shape[0] // b
+            rendered, fg, alphas, rgb = self.reference_tokens(cams, to_tokens(context_ref), nv, kv,
+                                                              context.shape[1], b, n)
+            xt = self.pose_emb_layers.tokens(xt, a1=rendered)
+            xt = self.ff.tokens(self.norm3.tokens(xt), residual=xt, out=xt)
+        else:
+            xt, aux = self.tokens(xt, b, n, ctx_tok, context.shape[1], cams)
+            if aux is not None:
+                fg, alphas, rgb = aux
+        if fg is not None:
+            d = alphas.shape[-1]
+            fg, alphas = fg.view(b, n, 1), alphas.view(b, n, d, 1)
+            rgb = rgb if self.rgb_predict else None
+        return ops.cast_f32(xt).view(b, n, c), fg, None, alphas, rgb
+
+
+class SpatialTransformer(nn.Module, _Packed):
+    """GroupNorm -> proj_in -> depth x BasicTransformerBlock -> proj_out -> + x (reference :684-886)."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None,
+                 disable_self_attn=False, use_linear=False, attn_type="softmax", use_checkpoint=True,
+                 sdp_backend=None, image_cross=True, rgb_predict=False, far=2, num_samples=32,
+                 add_lora=False, mode="feature-nerf", average=False, num_freqs=16,
+                 use_prev_weights_imp_sample=False, stratified=False, poscontrol_interval=4,
+                 imp_sampling_percent=0.9, near_plane=0.0):
+        super().__init__()
+        if not use_linear:
+            raise NotImplementedError("use_linear_in_transformer=False (1x1 conv projections) is not built")
+        if isinstance(context_dim, (list, tuple)) or type(context_dim).__name__ == "ListConfig":
+            context_dim = list(context_dim)
+            assert all(cd == context_dim[0] for cd in context_dim), "need homogeneous context_dim"
+            context_dim = context_dim[0]
+        self.in_channels = in_channels
+        inner = n_heads * d_head
+        assert inner == in_channels
+        self.norm = Normalize(in_channels)
+        self.image_cross = image_cross
+        self.poscontrol_interval = poscontrol_interval
+        self.proj_in = Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(
+                inner, n_heads, d_head, dropout=dropout, context_dim=context_dim,
+                disable_self_attn=disable_self_attn, attn_mode=attn_type, checkpoint=use_checkpoint,
+                sdp_backend=sdp_backend, image_cross=image_cross and (d % poscontrol_interval == 0),
+                far=far, num_samples=num_samples,
+                add_lora=add_lora and image_cross and (d % poscontrol_interval == 0),
+                rgb_predict=rgb_predict, mode=mode, average=average, num_freqs=num_freqs,
+                use_prev_weights_imp_sample=use_prev_weights_imp_sample,
+                imp_sample_next_step=False, stratified=stratified,
+                imp_sampling_percent=imp_sampling_percent, near_plane=near_plane)
+            for d in range(depth)])
+        self.proj_out = Linear(inner, in_channels)
+        nn.init.zeros_(self.proj_out.weight)  # zero_module (reference :795)
+        nn.init.zeros_(self.proj_out.bias)
+        self.use_linear = use_linear
+
+    def _pack(self, dev):
+        return dict(g=self.norm.weight.detach().float().contiguous(),
+                    b=self.norm.bias.detach().float().contiguous())
+
+    def tokens(self, x, batch, hw, ctx_tok, nctx, cams=None, aux_out=None):
+        """x bf16 [batch*hw, c] -> same shape (new tensor)."""
+        p = self.packed()
+        xn = ops.groupnorm(x, p["g"], p["b"], batch, hw, eps=self.norm.eps, silu=False)
+        h = self.proj_in.tokens(xn)
+        for i, block in enumerate(self.transformer_blocks):
+            use_pose = self.image_cross and (i % self.poscontrol_interval == 0)
+            h, aux = block.tokens(h, batch, hw, ctx_tok, nctx, cams if use_pose else None)
+            if aux is not None and aux_out is not None:
+                aux_out.append(aux)
+        return self.proj_out.tokens(h, residual=x)
+
+    def forward(self, x, xr=None, context=None, contextr=None, pose=None, mask_ref=None,
+                prev_weights=None):
+        """Reference contract: x [B, c, H, W] -> 6-tuple (x, xr, fg_masks, prev_weights, alphas, rgbs)."""
+        if xr is not None:
+            raise NotImplementedError("reference-image stream (training path) is a later row of SURVEY §8f")
+        if isinstance(context, list):
+            context = context[0]
+        b, c, h, w = x.shape
+        aux: list = []
+        cams = pack_pose(pose, x.device) if pose is not None else None
+        y = self.tokens(ops.nchw_to_nhwc_bf16(x.float().contiguous()), b, h * w, to_tokens(context),
+                        context.shape[1], cams, aux)
+        out = ops.nhwc_to_nchw_f32(y, b, h * w, c).view(b, c, h, w)
+        if aux:
+            d = aux[0][1].shape[-1]
+            fg = [a[0].view(b, h * w, 1) for a in aux]
+            al = [a[1].view(b, h * w, d, 1) for a in aux]
+            rgb = [a[2] for a in aux]
+            return out, None, fg, None, al, rgb
+        return out, None, None, None, None, None

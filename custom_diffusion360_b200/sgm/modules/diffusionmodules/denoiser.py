@@ -1,0 +1,61 @@
+"""Denoiser preconditioning surface (reference: denoiser.py:7-79).
+
+`denoiser(network, input, sigma, cond, **kwargs)` -> (D(x), fg_masks, alphas, rgbs), with
+`.w(sigma)`, `.sigmas`, `sigma_to_idx`, `idx_to_sigma` as in the reference.  This generic entry
+point evaluates the handful of scalar coefficient ops with torch; the sampling loop does not go
+through it per step — it uses `FusedGuidedStep` (sampling.py), where c_in is folded into the input
+convolution's im2col and c_out / c_skip / CFG / Euler are one kernel (cd360_cfg_euler_step).
+"""
+import torch
+import torch.nn as nn
+
+from ...util import append_dims, instantiate_from_config
+
+
+class Denoiser(nn.Module):
+    def __init__(self, weighting_config, scaling_config):
+        super().__init__()
+        self.weighting = instantiate_from_config(weighting_config)
+        self.scaling = instantiate_from_config(scaling_config)
+
+    def possibly_quantize_sigma(self, sigma):
+        return sigma
+
+    def possibly_quantize_c_noise(self, c_noise):
+        return c_noise
+
+    def w(self, sigma):
+        return self.weighting(sigma)
+
+    def __call__(self, network, input, sigma, cond, sigmas_ref=None, **kwargs):
+        if sigmas_ref is not None or kwargs.get("input_ref") is not None:
+            raise NotImplementedError("reference-image noising (training path) is a later row of SURVEY §8f")
+        sigma = self.possibly_quantize_sigma(sigma)
+        sigma_shape = sigma.shape
+        sigma = append_dims(sigma, input.ndim)
+        c_skip, c_out, c_in, c_noise = self.scaling(sigma)
+        c_noise = self.possibly_quantize_c_noise(c_noise.reshape(sigma_shape))
+        predict, fg, alphas, rgbs = network(input * c_in, c_noise, cond, **kwargs)
+        return predict * c_out + input * c_skip, fg, alphas, rgbs
+
+
+class DiscreteDenoiser(Denoiser):
+    def __init__(self, weighting_config, scaling_config, num_idx, discretization_config,
+                 do_append_zero=False, quantize_c_noise=True, flip=True):
+        super().__init__(weighting_config, scaling_config)
+        sigmas = instantiate_from_config(discretization_config)(num_idx, do_append_zero=do_append_zero,
+                                                                flip=flip)
+        self.register_buffer("sigmas", sigmas)
+        self.quantize_c_noise = quantize_c_noise
+
+    def sigma_to_idx(self, sigma):
+        return (sigma - self.sigmas[:, None]).abs().argmin(dim=0).view(sigma.shape)
+
+    def idx_to_sigma(self, idx):
+        return self.sigmas[idx]
+
+    def possibly_quantize_sigma(self, sigma):
+        return self.idx_to_sigma(self.sigma_to_idx(sigma))
+
+    def possibly_quantize_c_noise(self, c_noise):
+        return self.sigma_to_idx(c_noise) if self.quantize_c_noise else c_noise

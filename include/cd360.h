@@ -76,6 +76,7 @@ typedef struct cd360_gemm_args {
   const float* bias;     /* [N] or NULL */
   const float* row_bias; /* [ceil(M / rows_per_group), N] or NULL */
   int32_t rows_per_group;
+  int64_t ld_row_bias; /* elements; 0 = N */
   const void* residual; /* bf16 [M, N_out] or NULL */
   int64_t ldr;
   void* out; /* bf16 (out_fp32 == 0) or fp32 [M, N_out] */
@@ -139,10 +140,11 @@ int cd360_timestep_embedding(const float* t, float* out, int32_t batch, int32_t 
 /* ---------------------------------------------------------------------------------------------
  * Layout / resampling helpers around the convolutions.
  * --------------------------------------------------------------------------------------------- */
-/* x fp32 NCHW [B, Cin, H, W] * scale[b] -> im2col bf16 [B*H*W, kpad] for the 3x3 pad-1 input conv
+/* x fp32 NCHW [src_batch, Cin, H, W] (row b reads image b % src_batch: the CFG replication
+ * torch.cat([x]*rows), guiders.py:133, folded into the load) * scale[b] -> im2col bf16 [B*H*W, kpad] for the 3x3 pad-1 input conv
  * (openaimodel.py:720); k = (ky*3+kx)*Cin + c, zero padded to kpad.  scale may be NULL. */
 int cd360_im2col3x3_nchw_f32(const float* x, const float* scale, void* out, int32_t batch,
-                             int32_t cin, int32_t h, int32_t w, int32_t kpad,
+                             int32_t src_batch, int32_t cin, int32_t h, int32_t w, int32_t kpad,
                              cd360_stream_t stream);
 /* NHWC bf16 [B,H,W,C] -> im2col bf16 [B*(H/2)*(W/2), 9*C] of a stride-2 pad-1 3x3 conv
  * (Downsample, openaimodel.py:215-222). */
@@ -166,6 +168,12 @@ int cd360_upsample_nearest2x_bf16(const void* x, void* out, int32_t batch, int32
 int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_out, int32_t n_img,
                          int32_t guidance_rows, int32_t hw, float sigma_q, float sigma,
                          float sigma_next, float scale, float scale_im, cd360_stream_t stream);
+
+/* Same, with (sigma_q, sigma, sigma_next) read from device memory (fp32 [3]) so that one captured
+ * CUDA graph replays for every step of the schedule. */
+int cd360_cfg_euler_step_dev(float* x, const float* eps, float* denoised_out, int32_t n_img,
+                             int32_t guidance_rows, int32_t hw, const float* sigmas3, float scale,
+                             float scale_im, cd360_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * FeatureNeRF (sgm/modules/nerfsd_pytorch3d.py, sgm/modules/utils_cameraray.py).
@@ -211,6 +219,10 @@ int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n, cd360_stream_t 
 /* NHWC bf16/fp32 [B, hw, C] -> NCHW fp32 [B, C, hw] (module outputs at the sgm boundary). */
 int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t batch,
                            int32_t hw, int32_t c, cd360_stream_t stream);
+
+/* NCHW fp32 [B, C, hw] -> NHWC bf16 [B, hw, C] (module inputs at the sgm boundary). */
+int cd360_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t batch, int32_t hw, int32_t c,
+                                cd360_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,119 @@
+"""Host-side logic on CPU: module tree / state-dict contract, topology, kernel-call sequence and
+operand shapes of a full forward (with shape-only stand-ins for the kernels, tests/fake_ops.py),
+the inference caching semantics, config factory, and that the real ops refuse CPU tensors."""
+import pytest
+import torch
+
+from oracle import sgm_oracle as O
+from tests.fake_ops import patched_ops
+
+P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+
+
+def _model(cfg):
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    return UNetModel(**cfg).eval()
+
+
+def test_state_dict_contract_tiny_and_pose_off():
+    for cfg in (dict(O.TINY_CFG), dict(O.TINY_CFG, image_cross_blocks=[])):
+        m = _model(cfg)
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if "raymarcher" not in k}
+        assert mine == O.param_shapes(cfg)
+        ray = [k for k in m.state_dict() if "raymarcher" in k]
+        assert len(ray) == 5 * len(O.pose_block_prefixes(cfg))  # u, lengths, lengths_{center,upper,lower}
+
+
+def test_class_and_attribute_names_sample_py_relies_on():
+    m = _model(dict(O.TINY_CFG))
+    sts = [x for x in m.modules() if x.__class__.__name__ == "SpatialTransformer"]
+    bts = [x for x in m.modules() if x.__class__.__name__ == "BasicTransformerBlock"]
+    assert len(sts) == 11 and len(bts) == 2 * 5 + 5 * 6
+    for st in sts:
+        for a in ("norm", "proj_in", "proj_out", "use_linear", "transformer_blocks", "image_cross", "poscontrol_interval"):
+            assert hasattr(st, a)
+    for bt in bts:
+        for a in ("attn1", "attn2", "norm1", "norm2", "norm3", "ff", "disable_self_attn", "rendered_feat"):
+            assert hasattr(bt, a)
+    names = [n for n, _ in m.pose_blocks()]
+    assert [n + "." for n in names] == [p for p, _, _ in O.pose_block_prefixes(O.TINY_CFG)]
+    pose_params = [n for n, _ in m.named_parameters() if "pose" in n]
+    assert len(pose_params) == 8 * len(names)  # pose_emb + plane_coefs(4) + nviews(2) + decoder
+
+
+def test_forward_call_sequence_and_shapes_with_fake_kernels():
+    cfg = dict(O.TINY_CFG)
+    L, nv = 16, 4
+    m = _model(cfg)
+    refs = {p[:-1]: torch.randn(nv + 1, (L // ds) ** 2, c) for p, c, ds in O.pose_block_prefixes(cfg)}
+    m.register_references(refs)
+    m.set_reference_choices(list(range(nv)))
+    x = torch.randn(3, 4, L, L)
+    ctx, y = torch.randn(3, 77, cfg["context_dim"]), torch.randn(3, cfg["adm_in_channels"])
+    cams = torch.randn(3, nv + 1, 16)
+    with patched_ops() as fake, torch.no_grad():
+        eps, fg, al, rgb = m(x, timesteps=torch.tensor([500, 500, 500]), context=ctx, y=y, pose=cams,
+                             mask_ref=None, drop_im=None)
+        n_first = len(fake.calls)
+        eps2, fg2, _, _ = m(x, timesteps=torch.tensor([400, 400, 400]), context=ctx, y=y, pose=cams)
+        n_second = len(fake.calls) - n_first
+    assert eps.shape == (3, 4, L, L) and eps.dtype == torch.float32
+    npose = len(O.pose_block_prefixes(cfg))
+    assert len(fg) == len(al) == len(rgb) == npose and fg2 == []
+    assert fg[0].shape == (3, (L // 2) ** 2, 1) and al[0].shape == (3, (L // 2) ** 2, cfg["num_samples"], 1)
+    assert n_second < n_first  # cached rendered features: no FeatureNeRF kernels on later steps
+    kinds = [c[0] for c in fake.calls[:n_first]]
+    assert kinds.count("volrender") == npose
+    assert kinds.count("conv3x3") == 2 * 17 + 2 + 1  # 17 ResBlocks x 2, 2 Upsample convs, out conv
+    assert kinds.count("attention") == 2 * 40 + npose  # attn1+attn2 per block, + attn2 over samples
+    m.clear_rendered_feat()
+    assert all(b.rendered_feat is None for _, b in m.pose_blocks())
+
+
+def test_sdxl_topology_counts_on_meta_device():
+    with torch.device("meta"):
+        m = _model(dict(O.SDXL_CFG))
+    assert sum(p.numel() for n, p in m.named_parameters() if "pose" not in n) == 2567463684
+    assert len(list(m.pose_blocks())) == 12
+    assert len(m.resblocks()) == 17
+
+
+def test_engine_factory_and_generic_sampler_control_flow():
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    from custom_diffusion360_b200.sgm.util import instantiate_from_config
+    cfg = dict(O.TINY_CFG, image_cross_blocks=[])
+    engine = instantiate_from_config({"target": "custom_diffusion360_b200.sgm.models.diffusion.DiffusionEngine", "params": dict(
+        network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+        denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+            "num_idx": 1000, "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+            "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"},
+            "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"}}},
+        sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+            "num_steps": 3, "device": "cpu",
+            "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"},
+            "guider_config": {"target": P + "guiders.VanillaCFGImgRef", "params": {"scale": 7.5}}}})})
+    assert isinstance(engine, DiffusionEngine)
+    assert torch.equal(engine.denoiser.sigmas, O.legacy_ddpm_sigmas(1000, do_append_zero=False, flip=True))
+    assert not any(p.requires_grad for _, p in engine.model.diffusion_model.named_parameters())
+    c = {"crossattn": torch.randn(1, 77, cfg["context_dim"]), "vector": torch.randn(1, cfg["adm_in_channels"])}
+    with patched_ops() as fake:
+        out = engine.sample(c, uc=c, batch_size=1, num_steps=3, noise=torch.randn(1, 4, 16, 16), fused=False)
+    assert out.shape == (1, 4, 16, 16)
+    assert sum(1 for k, _ in fake.calls if k == "conv3x3") == 3 * (2 * 17 + 2 + 1)  # 3 steps
+
+
+def test_unsupported_options_raise():
+    from custom_diffusion360_b200.sgm.modules import attention as A
+    with pytest.raises(NotImplementedError):
+        A.MemoryEfficientCrossAttention(128, heads=4, dim_head=32)
+    with pytest.raises(NotImplementedError):
+        A.MemoryEfficientCrossAttention(128, heads=2, dim_head=64, add_lora=True)
+    with pytest.raises(NotImplementedError):
+        _model(dict(O.TINY_CFG, use_linear_in_transformer=False))
+
+
+def test_real_ops_refuse_cpu_tensors():
+    from custom_diffusion360_b200._lib import Cd360Error
+    m = _model(dict(O.TINY_CFG, image_cross_blocks=[]))
+    with pytest.raises(Cd360Error):
+        m(torch.randn(1, 4, 16, 16), timesteps=torch.tensor([1]), context=torch.randn(1, 77, 128), y=torch.randn(1, 96))
