@@ -18,15 +18,14 @@ class Discretization:
 
 class LegacyDDPMDiscretization(Discretization):
     """Linear-in-sqrt(beta) DDPM schedule, float64 table; σ_t = sqrt((1 - ᾱ_t) / ᾱ_t).
-    Sub-sampling picks `linspace(T-1, 0, n, endpoint=False).astype(int)[::-1]` like the reference."""
+    Sub-sampling picks `linspace(T-1, 0, n, endpoint=False).astype(int)[::-1]` like the reference.
+    The table is always built on the host (float64 torch.linspace, as the reference does), whatever
+    default device is active."""
 
     def __init__(self, linear_start=0.00085, linear_end=0.0120, num_timesteps=1000):
         self.num_timesteps = num_timesteps
-        betas = np.linspace(linear_start ** 0.5, linear_end ** 0.5, num_timesteps, dtype=np.float64) ** 2
-        # torch.linspace(float64) and np.linspace agree to the last bit except possibly at a few
-        # interior points; the reference uses torch, so do we
         betas = (torch.linspace(linear_start ** 0.5, linear_end ** 0.5, num_timesteps,
-                                dtype=torch.float64) ** 2).numpy()
+                                dtype=torch.float64, device="cpu") ** 2).numpy()
         self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
 
     def get_sigmas(self, n, device="cpu"):
@@ -37,5 +36,5 @@ class LegacyDDPMDiscretization(Discretization):
             ac = self.alphas_cumprod
         else:
             raise ValueError(f"n={n} exceeds the {self.num_timesteps}-entry table")
-        sigmas = torch.tensor((1 - ac) / ac, dtype=torch.float32, device=device) ** 0.5
-        return torch.flip(sigmas, (0,))
+        sigmas = torch.tensor((1 - ac) / ac, dtype=torch.float32, device="cpu") ** 0.5
+        return torch.flip(sigmas, (0,)).to(device)

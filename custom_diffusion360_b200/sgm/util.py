@@ -44,6 +44,35 @@ def append_dims(x, target_dims: int):
     return x[(...,) + (None,) * extra]
 
 
+def load_checkpoints(engine, base_sd: dict, delta_sd: dict = None, verbose: bool = False):
+    """Checkpoint key contract of the reference (sgm/util.py:202-251, main.py:611-625):
+    `base_sd` uses `model.diffusion_model.<name>` keys (sd_xl_base_1.0.safetensors; conditioner /
+    first-stage keys are ignored here), `delta_sd` = checkpoint['delta_state_dict'] with the pose
+    weights, the per-block `references` buffers and `embed` (token rows, not ours to load).
+    Returns (missing, unexpected) for the UNet part."""
+    prefix = "model.diffusion_model."
+    unet = engine.model.diffusion_model
+    sd = {k[len(prefix):]: v for k, v in base_sd.items() if k.startswith(prefix)}
+    refs = {}
+    if delta_sd is not None:
+        for k, v in delta_sd.items():
+            if not k.startswith(prefix):
+                continue
+            name = k[len(prefix):]
+            if name.endswith(".references"):
+                refs[name] = v
+            else:
+                sd[name] = v
+    missing, unexpected = unet.load_state_dict(sd, strict=False)
+    missing = [m for m in missing if "raymarcher" not in m]
+    if refs:
+        dev = next(unet.parameters()).device
+        unet.register_references({k: v.to(dev) for k, v in refs.items()})
+    if verbose:
+        print(f"missing: {missing}\nunexpected: {unexpected}")
+    return missing, unexpected
+
+
 def append_zero(x):
     import torch
 
