@@ -112,8 +112,13 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, latent: int = 128):
             sd[name] = (torch.ones(shape) if name.endswith("weight") else torch.zeros(shape))
         else:
             sd[name] = torch.randn(shape, generator=g) / math.sqrt(float(torch.tensor(shape[1:]).prod()))
-    t32 = _oracle_forward_seconds(O, sd, cfg, 32, True, threads)   # thread-pool / allocator warm-up
-    t32 = _oracle_forward_seconds(O, sd, cfg, 32, True, threads)
+    _oracle_forward_seconds(O, sd, cfg, 32, True, threads)   # thread-pool / allocator warm-up
+    # torch's CPU kernels stop scaling (and can regress) far below the core count of a big host:
+    # keep the thread count that is actually fastest on a small calibration run
+    cand = sorted({threads, min(threads, 64), min(threads, 32), min(threads, 16)}, reverse=True)
+    timing = {c: _oracle_forward_seconds(O, sd, cfg, 32, True, c) for c in cand}
+    threads = min(timing, key=timing.get)
+    t32 = timing[threads]
     n = max(1, steps + warmup)
     est128 = t32 * 17.0
     use = 128 if (latent == 128 and est128 * n <= budget_s) else 64

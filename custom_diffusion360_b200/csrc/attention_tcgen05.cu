@@ -70,6 +70,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   const int batch = blockIdx.z;
   const int num_kv_tiles = (p.nkv + ATT_BKV - 1) / ATT_BKV;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
       printf("cd360 attention: dynamic smem base not 1024-aligned\n");
@@ -98,6 +99,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // Q/K/V come from the preceding projection GEMM
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
@@ -317,7 +319,7 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   p.heads = heads;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((nq + ATT_BQ - 1) / ATT_BQ, heads, batch);
-  attention_bf16_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  launch_ex(attention_bf16_tcgen05_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, tq, tk, tv, p);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }

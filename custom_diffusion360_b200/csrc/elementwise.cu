@@ -9,6 +9,8 @@ namespace cd360 {
 // timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230): [cos(t f_k) | sin(t f_k)]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out,
                                           int batch, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ add,
                     float* __restrict__ out, int batch, int n, int k, int act_in, int act_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_x[];  // [SL_BCHUNK][k]
   const int b0 = blockIdx.y * SL_BCHUNK;
   const int nb = min(SL_BCHUNK, batch - b0);
@@ -87,6 +91,8 @@ small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ out, int batch, int src_batch,
                                       int cin, int h, int w, int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batch) * h * w * kpad;
   if (i >= total) return;
@@ -114,6 +120,8 @@ __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* 
 __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x,
                                     __nv_bfloat16* __restrict__ out, int batch, int h, int w,
                                     int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ho = h / 2, wo = w / 2, cv = c / 8;
   const long long total = static_cast<long long>(batch) * ho * wo * 9 * cv;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -136,6 +144,8 @@ __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x,
 // nearest x2 (Upsample.forward, openaimodel.py:161), NHWC, 8 channels per thread
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
                                   __nv_bfloat16* __restrict__ out, int batch, int h, int w, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = c / 8;
   const long long total = static_cast<long long>(batch) * (2 * h) * (2 * w) * cv;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -152,11 +162,15 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                      long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16_rn(x[i]);
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                      long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(x[i]);
 }
@@ -164,6 +178,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
 // [B, hw, C] (bf16 or fp32) -> NCHW fp32 [B, C, hw]
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
                                     float* __restrict__ out, int batch, int hw, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batch) * hw * c;
   if (i >= total) return;
@@ -178,6 +194,8 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
 // NCHW fp32 [B, C, hw] -> [B, hw, C] bf16 (module inputs at the sgm boundary)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                     int batch, int hw, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(batch) * hw * c;
   if (i >= total) return;
@@ -192,6 +210,8 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
                                  float* __restrict__ denoised_out, int n_img, int g, int hw,
                                  float sigma_q, float sigma, float sigma_next, float scale,
                                  float scale_im, const float* __restrict__ sig_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (sig_dev != nullptr) {  // (sigma_q, sigma, sigma_next) live in device memory: graph-replayable
     sigma_q = sig_dev[0];
     sigma = sig_dev[1];
@@ -233,7 +253,7 @@ extern "C" int cd360_timestep_embedding(const float* t, float* out, int32_t batc
   if (!t || !out) return CD360_ERR_NULL;
   if (batch <= 0 || dim < 2) return CD360_ERR_SHAPE;
   const int n = batch * (dim / 2);
-  timestep_embedding_kernel<<<blocks_for(n, 128), 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(timestep_embedding_kernel, dim3(blocks_for(n, 128)), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       t, out, batch, dim);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -250,7 +270,7 @@ extern "C" int cd360_small_linear(const float* x, const void* w, const float* bi
   if (smem > 48 * 1024) return CD360_ERR_SHAPE;
   dim3 grid((n + 8 * SL_OUT_PER_WARP - 1) / (8 * SL_OUT_PER_WARP),
             (batch + SL_BCHUNK - 1) / SL_BCHUNK);
-  small_linear_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(small_linear_kernel, dim3(grid), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, reinterpret_cast<const __nv_bfloat16*>(w), bias, add, out, batch, n, k, act_in, act_out);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -264,8 +284,7 @@ extern "C" int cd360_im2col3x3_nchw_f32(const float* x, const float* scale, void
   if (batch <= 0 || cin <= 0 || h <= 0 || w <= 0 || kpad < 9 * cin || (kpad & 7))
     return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * h * w * kpad;
-  im2col3x3_nchw_kernel<<<blocks_for(total, 256), 256, 0,
-                          reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(im2col3x3_nchw_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, scale, reinterpret_cast<__nv_bfloat16*>(out), batch, src_batch, cin, h, w, kpad);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -277,7 +296,7 @@ extern "C" int cd360_im2col3x3_s2_bf16(const void* x, void* out, int32_t batch, 
   if (batch <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || c <= 0 || (c & 7))
     return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * (h / 2) * (w / 2) * 9 * (c / 8);
-  im2col3x3_s2_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(im2col3x3_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w,
       c);
   CD360_CHECK_LAUNCH();
@@ -289,7 +308,7 @@ extern "C" int cd360_upsample_nearest2x_bf16(const void* x, void* out, int32_t b
   if (!x || !out) return CD360_ERR_NULL;
   if (batch <= 0 || h <= 0 || w <= 0 || c <= 0 || (c & 7)) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(upsample2x_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(out), batch, h, w,
       c);
   CD360_CHECK_LAUNCH();
@@ -300,7 +319,7 @@ extern "C" int cd360_cast_f32_to_bf16(const float* x, void* out, int64_t n,
                                       cd360_stream_t stream_) {
   if (!x || !out) return CD360_ERR_NULL;
   if (n <= 0) return CD360_ERR_SHAPE;
-  cast_f32_bf16_kernel<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(cast_f32_bf16_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, reinterpret_cast<__nv_bfloat16*>(out), n);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -310,7 +329,7 @@ extern "C" int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n,
                                       cd360_stream_t stream_) {
   if (!x || !out) return CD360_ERR_NULL;
   if (n <= 0) return CD360_ERR_SHAPE;
-  cast_bf16_f32_kernel<<<blocks_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(cast_bf16_f32_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       reinterpret_cast<const __nv_bfloat16*>(x), out, n);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -321,7 +340,7 @@ extern "C" int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* o
   if (!x || !out) return CD360_ERR_NULL;
   if (batch <= 0 || hw <= 0 || c <= 0) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * hw * c;
-  nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(nhwc_to_nchw_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, x_is_fp32, out, batch, hw, c);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -332,7 +351,7 @@ extern "C" int cd360_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t ba
   if (!x || !out) return CD360_ERR_NULL;
   if (batch <= 0 || hw <= 0 || c <= 0) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(batch) * hw * c;
-  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(nchw_to_nhwc_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, reinterpret_cast<__nv_bfloat16*>(out), batch, hw, c);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
@@ -346,7 +365,7 @@ extern "C" int cd360_cfg_euler_step(float* x, const float* eps, float* denoised_
   if (n_img <= 0 || hw <= 0 || guidance_rows < 1 || guidance_rows > 3) return CD360_ERR_SHAPE;
   if (!(sigma > 0.f)) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(n_img) * 4 * hw;
-  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(cfg_euler_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, eps, denoised_out, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next, scale, scale_im,
       nullptr);
   CD360_CHECK_LAUNCH();
@@ -360,7 +379,7 @@ extern "C" int cd360_cfg_euler_step_dev(float* x, const float* eps, float* denoi
   if (!x || !eps || !sigmas3) return CD360_ERR_NULL;
   if (n_img <= 0 || hw <= 0 || guidance_rows < 1 || guidance_rows > 3) return CD360_ERR_SHAPE;
   const long long total = static_cast<long long>(n_img) * 4 * hw;
-  cfg_euler_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(cfg_euler_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       x, eps, denoised_out, n_img, guidance_rows, hw, 0.f, 1.f, 0.f, scale, scale_im, sigmas3);
   CD360_CHECK_LAUNCH();
   return CD360_OK;

@@ -1,24 +1,39 @@
 // gemm_tcgen05.cu — persistent, warp-specialised bf16 GEMM / implicit-GEMM 3x3 convolution for
-// sm_100a.  One CTA per SM; roles:
+// sm_100a.  One CTA per SM (or one CTA PAIR per two SMs, cta_group::2); roles per CTA:
 //   warp 0 (1 thread)  TMA producer: A and W tiles -> 128B-swizzled smem ring (mbarrier full/empty)
-//   warp 1 (1 thread)  tcgen05.mma issuer: 128 x BN x 16 UMMAs accumulate into TMEM
+//   warp 1 (1 thread)  tcgen05.mma issuer (leader CTA only in pair mode)
 //   warp 2             TMEM allocator / deallocator
-//   warps 4-7          epilogue: tcgen05.ld -> bias / emb-add / activation / GEGLU / residual -> HBM
+//   warps 4-11         epilogue: tcgen05.ld -> bias / emb-add / activation / GEGLU / residual -> HBM
+//                      (two warps per TMEM lane quarter, each taking half of the tile's columns)
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
+//
+// Pair mode (CG == 2): a cluster of two CTAs computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA loads its own 128 rows of A and HALF of the
+// W tile (BN/2 rows), so per-SM operand traffic from L2 drops by a third and a 192 KB smem ring
+// buffers twice as many MMA cycles.  Both CTAs' TMA loads complete on the leader's `full`
+// barrier; the leader's MMA thread releases smem slots / publishes accumulators to both CTAs with
+// multicast tcgen05.commit; the peer's epilogue warps hand TMEM back with remote mbarrier arrives.
 //
 // Convolution mode feeds the SAME main loop from a 4-D NHWC tensor map: the A tile of K-block
 // (tap, c-chunk) is the box [64 ch, tw, th, tb] at pixel offset (dx-1, dy-1); out-of-image
 // coordinates are zero-filled by TMA, which implements the pad-1 border without a halo copy.
 //
+// Every kernel in this library is launched with programmatic dependent launch: the prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail, and
+// griddepcontrol.wait orders all global-memory traffic after the previous grid's completion.
+//
 // Reference arithmetic replaced: see include/cd360.h (cd360_gemm_bf16).
+#include <stdlib.h>
+
 #include "cd360_common.cuh"
 
 namespace cd360 {
 
-constexpr int BM = 128;
-constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int BM = 128;  // rows per CTA
+constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
 
 struct GemmKParams {
@@ -42,14 +57,16 @@ struct GemmKParams {
   int geglu;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 struct GemmSmem {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int BNC = BN / CG;  // W rows this CTA stages
+  static constexpr int B_TILE_BYTES = BNC * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+  static_assert(DYN_BYTES <= 227 * 1024, "smem ring too large");
 };
 
 // ---- epilogue helpers --------------------------------------------------------------------------
@@ -126,12 +143,12 @@ __device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams&
 }
 
 // ---- kernel ------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                          const __grid_constant__ CUtensorMap tmA1,
                          const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -143,10 +160,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = blockIdx.x / CG;         // CTA (CG=1) or cluster (CG=2) index
+  const int num_units = gridDim.x / CG;
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int nkb = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -154,33 +176,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);  // pair: leader's expect_tx arrive + peer's remote arrive
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[b], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // nothing above touches global memory written by earlier kernels
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
-      const int m0 = m_blk * BM;
-      const int n0 = n_blk * BN;
+      const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
+      const int n0 = n_blk * BN + static_cast<int>(rank) * L::BNC;
       int cb = 0, cy = 0, cx = 0;
       if (p.conv) {
         const int hw = p.H * p.W;
@@ -193,31 +221,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + A_TILE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        uint64_t* fb = &full_bar[stage];
+        if (CG == 1) {
+          mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
+        } else if (leader) {
+          mbar_arrive_expect_tx(fb, 2 * L::STAGE_BYTES);
+        } else {
+          mbar_arrive_remote(fb, 0);
+        }
         if (p.conv) {
           const int tap = kb / p.cblocks;
           const int kc = kb - tap * p.cblocks;
           const int dy = tap / 3, dx = tap - dy * 3;
-          tma_load_4d(sa, &tmA0, &full_bar[stage], kc * BK, cx + dx - 1, cy + dy - 1, cb);
-        } else if (kb < p.kb0) {
-          tma_load_2d(sa, &tmA0, &full_bar[stage], kb * BK, m0);
+          if (CG == 2) tma_load_4d_2sm(sa, &tmA0, fb, kc * BK, cx + dx - 1, cy + dy - 1, cb);
+          else tma_load_4d(sa, &tmA0, fb, kc * BK, cx + dx - 1, cy + dy - 1, cb);
         } else {
-          tma_load_2d(sa, &tmA1, &full_bar[stage], (kb - p.kb0) * BK, m0);
+          const CUtensorMap* tm = kb < p.kb0 ? &tmA0 : &tmA1;
+          const int kk = (kb < p.kb0 ? kb : kb - p.kb0) * BK;
+          if (CG == 2) tma_load_2d_2sm(sa, tm, fb, kk, m0);
+          else tma_load_2d(sa, tm, fb, kk, m0);
         }
-        tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+        if (CG == 2) tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0);
+        else tma_load_2d(sb, &tmB, fb, kb * BK, n0);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1 && lane == 0 && leader) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
@@ -232,10 +270,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
           const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
-          umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (kb == nkb - 1) umma_commit(&tmem_full[buf]);
+        // free the smem slot (in both CTAs) once these MMAs retire
+        if (CG == 2) umma_commit_2sm(&empty_bar[stage], 0x3);
+        else umma_commit(&empty_bar[stage]);
+        if (kb == nkb - 1) {
+          if (CG == 2) umma_commit_2sm(&tmem_full[buf], 0x3);
+          else umma_commit(&tmem_full[buf]);
+        }
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -244,15 +288,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int q = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+    const int q = warp & 3;               // TMEM lane quarter this warp may access (warp % 4)
+    const int half = (warp - 4) >> 2;     // which half of the tile's columns
     const int row_in_tile = q * 32 + lane;
     int t = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
-      const long long row = static_cast<long long>(m_blk) * BM + row_in_tile;
+      const long long row =
+          static_cast<long long>(m_blk * CG + static_cast<int>(rank)) * BM + row_in_tile;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
       mbar_wait(&tmem_full[buf], acc_phase);
@@ -260,12 +306,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       const float* rb = nullptr;
-      if (p.row_bias != nullptr && row_ok)
-        rb = p.row_bias + (row / p.rows_per_group) * p.ld_row_bias;
+      if (p.row_bias != nullptr && row_ok) rb = p.row_bias + (row / p.rows_per_group) * p.ld_row_bias;
 
       if (!p.geglu) {
+        constexpr int CH = BN / 64;  // 32-column chunks per half
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int ci = 0; ci < CH; ++ci) {
+          const int c = half * CH + ci;
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;  // warp-uniform
           uint32_t r[32];
@@ -287,8 +334,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       } else {
         // tile columns [0, BN/2) hold x, [BN/2, BN) hold the matching gates (pre-interleaved W)
+        constexpr int CH = BN / 128;  // (x, gate) chunk pairs per half
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int ci = 0; ci < CH; ++ci) {
+          const int c = half * CH + ci;
           uint32_t rx[32], rg[32];
           tmem_ld_32x32b_x32(taddr + c * 32, rx);
           tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
@@ -312,16 +361,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -378,12 +431,12 @@ int num_sms() {
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                        const GemmKParams& p, int max_ctas, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, CG>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, CG>;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
         cudaSuccess)
@@ -391,18 +444,29 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  int grid = num_sms();
-  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (tiles < grid) grid = tiles;
-  kern<<<grid, kGemmThreads, L::DYN_BYTES, stream>>>(a0, a1, b, p);
+  int units = num_sms() / CG;
+  if (max_ctas > 0 && max_ctas / CG >= 1 && max_ctas / CG < units) units = max_ctas / CG;
+  if (tiles < units) units = tiles;
+  if (launch_ex(kern, dim3(units * CG), dim3(kGemmThreads), L::DYN_BYTES, stream, CG, a0, a1, b,
+                p) != cudaSuccess)
+    return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
 
-static int pick_block_n(int M, int N, int geglu, int requested) {
-  if (requested == 128 || requested == 256) return requested;
-  if (geglu) return (N % 256 == 0) ? 256 : 128;
+// tile configuration: block_n = 128 / 256 selects the single-CTA kernels, 512 (= "256 wide,
+// CTA pair") the cta_group::2 kernel; 0 = heuristic.
+static int pick_config(int M, int N, int geglu, int requested) {
+  if (requested == 128 || requested == 256 || requested == 512) return requested;
+  static int pair_ok = -1;
+  if (pair_ok < 0) {
+    const char* e = getenv("CD360_GEMM_PAIR");
+    pair_ok = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (geglu && (N % 256) != 0) return 128;
   if (N <= 128) return 128;
+  if (pair_ok && M > 128 && N >= 256) return 512;
+  if (geglu) return 256;
   const long long t256 = static_cast<long long>((M + BM - 1) / BM) * ((N + 255) / 256);
   return t256 >= 100 ? 256 : 128;
 }
@@ -422,7 +486,9 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     return CD360_ERR_NULL;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (a->M <= 0 || a->N <= 0) return CD360_ERR_SHAPE;
-  const int BN = pick_block_n(a->M, a->N, a->geglu, a->block_n);
+  const int cfgsel = pick_config(a->M, a->N, a->geglu, a->block_n);
+  const int CGsel = cfgsel == 512 ? 2 : 1;
+  const int BN = cfgsel == 512 ? 256 : cfgsel;
   if (a->geglu && (a->N % BN != 0 || (a->N & 1))) return CD360_ERR_SHAPE;
   if (a->geglu && a->act != CD360_ACT_NONE) return CD360_ERR_UNSUPPORTED;
 
@@ -430,7 +496,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   p.M = a->M;
   p.N = a->N;
   p.N_out = a->geglu ? a->N / 2 : a->N;
-  p.num_m_blocks = (a->M + BM - 1) / BM;
+  p.num_m_blocks = (a->M + BM * CGsel - 1) / (BM * CGsel);
   p.num_n_blocks = (a->N + BN - 1) / BN;
   p.bias = a->bias;
   p.row_bias = a->row_bias;
@@ -516,10 +582,11 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(BN / CGsel)};
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, true);
     if (rc != CD360_OK) return rc;
   }
-  if (BN == 256) return launch_gemm<256, 4>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
-  return launch_gemm<128, 6>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+  if (cfgsel == 512) return launch_gemm<256, 6, 2>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+  if (cfgsel == 256) return launch_gemm<256, 4, 1>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+  return launch_gemm<128, 6, 1>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
 }

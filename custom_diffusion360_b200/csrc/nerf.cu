@@ -89,6 +89,8 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
                    float b_nv, __nv_bfloat16* __restrict__ pe, int* __restrict__ gidx,
                    float* __restrict__ gwgt, float* __restrict__ vlogit, int nb, int n, int res,
                    int d, int kpe) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];  // w_nv_geo[198] | per-view origin logit [n]
   float* s_ol = s_w + 200;
   const int hw = res * res;
@@ -203,6 +205,8 @@ nerf_combine_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
                     const float* __restrict__ gwgt, const float* __restrict__ vlogit,
                     __nv_bfloat16* __restrict__ s_out, float* __restrict__ view_softmax, int nb,
                     int n, int hw, int d, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long npts = static_cast<long long>(nb) * hw * d;
@@ -284,6 +288,8 @@ nerf_volrender_kernel(const __nv_bfloat16* __restrict__ feats, const float* __re
                       const float* __restrict__ dists, __nv_bfloat16* __restrict__ rendered,
                       float* __restrict__ fg, float* __restrict__ alphas, float* __restrict__ rgb,
                       int nb, int hw, int d, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= static_cast<long long>(nb) * hw) return;
@@ -362,7 +368,7 @@ extern "C" int cd360_nerf_points(const float* cams, const float* xy, const float
   const int pts = res * res * d;
   dim3 grid((pts + 127) / 128, b);
   const size_t smem = (200 + NERF_MAX_VIEWS) * sizeof(float);
-  nerf_points_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(nerf_points_kernel, dim3(grid), dim3(128), smem, reinterpret_cast<cudaStream_t>(stream_), 1, 
       cams, xy, depths, w_nv_geo, b_nv, reinterpret_cast<__nv_bfloat16*>(pe), gidx, gwgt, vlogit, b,
       n, res, d, kpe);
   CD360_CHECK_LAUNCH();
@@ -379,8 +385,7 @@ extern "C" int cd360_nerf_combine(const void* g, int64_t ldg, const void* hpre,
     return CD360_ERR_SHAPE;
   const long long warps = static_cast<long long>(b) * hw * d;
   const long long blocks = (warps + 7) / 8;
-  nerf_combine_kernel<<<static_cast<unsigned>(blocks), 256, 0,
-                        reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(nerf_combine_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       reinterpret_cast<const __nv_bfloat16*>(g), ldg, reinterpret_cast<const __nv_bfloat16*>(hpre),
       gidx, gwgt, vlogit, reinterpret_cast<__nv_bfloat16*>(s), view_softmax, b, n, hw, d, c);
   CD360_CHECK_LAUNCH();
@@ -395,8 +400,7 @@ extern "C" int cd360_nerf_volrender(const void* feats, const float* raw, const f
   if (b <= 0 || hw <= 0 || d <= 0 || d > 32 || c <= 0 || (c & 7)) return CD360_ERR_SHAPE;
   const long long warps = static_cast<long long>(b) * hw;
   const long long blocks = (warps + 7) / 8;
-  nerf_volrender_kernel<<<static_cast<unsigned>(blocks), 256, 0,
-                          reinterpret_cast<cudaStream_t>(stream_)>>>(
+  launch_ex(nerf_volrender_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1, 
       reinterpret_cast<const __nv_bfloat16*>(feats), raw, dists,
       reinterpret_cast<__nv_bfloat16*>(rendered), fg, alphas, rgb, b, hw, d, c);
   CD360_CHECK_LAUNCH();

@@ -26,12 +26,14 @@ __global__ void __launch_bounds__(1024)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
                        const __nv_bfloat16* __restrict__ x1, int c1, float* __restrict__ partial,
                        int hw, int rows_per_chunk, int nvec, int rlanes) {
-  __shared__ float s_acc[GN_GROUPS * 2];
+  pdl_launch_dependents();
+  pdl_wait();
+  // per-(row lane, channel) partial sums, reduced in a FIXED order below: results are bit-exact
+  // run to run (no floating-point atomics anywhere on the path)
+  extern __shared__ float s_part[];  // [2][rlanes][ctot]
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int ctot = c0 + c1;
   const int cg = ctot / GN_GROUPS;
-  if (threadIdx.x < GN_GROUPS * 2) s_acc[threadIdx.x] = 0.f;
-  __syncthreads();
   const int vec = threadIdx.x % nvec;
   const int rl = threadIdx.x / nvec;
   if (rl < rlanes) {
@@ -53,26 +55,20 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
     }
-    // fold the 8 channels into their groups (<= 8 distinct groups), then one smem atomic each
-    int g_prev = ch0 / cg;
-    float as = 0.f, ass = 0.f;
+    float* ps = s_part + static_cast<size_t>(rl) * ctot + ch0;
+    float* pss = s_part + static_cast<size_t>(rlanes + rl) * ctot + ch0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (ch0 + i) / cg;
-      if (g != g_prev) {
-        atomicAdd(&s_acc[g_prev * 2], as);
-        atomicAdd(&s_acc[g_prev * 2 + 1], ass);
-        as = 0.f; ass = 0.f; g_prev = g;
-      }
-      as += s[i]; ass += ss[i];
-    }
-    atomicAdd(&s_acc[g_prev * 2], as);
-    atomicAdd(&s_acc[g_prev * 2 + 1], ass);
+    for (int i = 0; i < 8; ++i) { ps[i] = s[i]; pss[i] = ss[i]; }
   }
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2)
-    partial[(static_cast<long long>(b) * gridDim.x + chunk) * GN_GROUPS * 2 + threadIdx.x] =
-        s_acc[threadIdx.x];
+  if (threadIdx.x < GN_GROUPS * 2) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const float* base = s_part + static_cast<size_t>(which) * rlanes * ctot + g * cg;
+    float acc = 0.f;
+    for (int r = 0; r < rlanes; ++r)
+      for (int c = 0; c < cg; ++c) acc += base[static_cast<size_t>(r) * ctot + c];
+    partial[(static_cast<long long>(b) * gridDim.x + chunk) * GN_GROUPS * 2 + threadIdx.x] = acc;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -82,6 +78,8 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        __nv_bfloat16* __restrict__ out, int hw, int rows_per_block, float eps,
                        int apply_silu) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_dyn[];  // scale[ctot] | shift[ctot]
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
   const int b = blockIdx.y;
@@ -143,6 +141,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, int c,
                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -240,7 +240,8 @@ extern "C" int cd360_groupnorm_silu_bf16(const void* x0, int32_t c0, const void*
   int rlanes = nvec <= 256 ? 256 / nvec : 1;
   if (rlanes < 1) rlanes = 1;
   const int threads = ((nvec * rlanes + 31) / 32) * 32;
-  groupnorm_stats_kernel<<<dim3(chunks, batch), threads, 0, stream>>>(
+  const size_t stats_smem = static_cast<size_t>(2) * rlanes * ctot * sizeof(float);  // <= 20 KiB
+  launch_ex(groupnorm_stats_kernel, dim3(chunks, batch), dim3(threads), stats_smem, stream, 1,
       reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1),
       c1, workspace, hw, rows_per_chunk, nvec, rlanes);
   CD360_CHECK_LAUNCH();
@@ -249,7 +250,7 @@ extern "C" int cd360_groupnorm_silu_bf16(const void* x0, int32_t c0, const void*
   const int rows_per_block = (hw + row_blocks - 1) / row_blocks;
   row_blocks = (hw + rows_per_block - 1) / rows_per_block;
   const size_t smem = static_cast<size_t>(ctot) * 2 * sizeof(float);
-  groupnorm_apply_kernel<<<dim3(row_blocks, batch), 256, smem, stream>>>(
+  launch_ex(groupnorm_apply_kernel, dim3(row_blocks, batch), dim3(256), smem, stream, 1, 
       reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1),
       c1, workspace, chunks, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), hw,
       rows_per_block, eps, apply_silu);
@@ -267,7 +268,7 @@ extern "C" int cd360_layernorm_bf16(const void* x, const float* gamma, const flo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int warps_per_block = 8;
   const int blocks = (rows + warps_per_block - 1) / warps_per_block;
-  layernorm_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(
+  launch_ex(layernorm_kernel, dim3(blocks), dim3(warps_per_block * 32), 0, stream, 1, 
       reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(out),
       rows, c, eps);
   CD360_CHECK_LAUNCH();

@@ -79,6 +79,17 @@ def _run(name, flops, fn):
     return fn() if h is None else h(name, flops, fn)
 
 
+def _op(name):
+    """Route a whole wrapper through the profiling hook (non-tensor-core kernels: no FLOP count)."""
+    def deco(fn):
+        def wrapped(*a, **kw):
+            h = LaunchStats.hook
+            return fn(*a, **kw) if h is None else h(name, 0.0, lambda: fn(*a, **kw))
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 def conv3x3(x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None, out_fp32=False,
             block_n=0, max_ctas=0):
     """Stride-1 pad-1 3x3 convolution as implicit GEMM.  x: bf16 [B*H*W, C] (NHWC);
@@ -139,6 +150,7 @@ def groupnorm_workspace(batch: int, hw: int, device) -> torch.Tensor:
     return ws
 
 
+@_op("groupnorm")
 def groupnorm(x0, gamma, beta, batch, hw, *, x1=None, eps=1e-5, silu=True, out=None,
               workspace=None):
     """GroupNorm(32)+optional SiLU over NHWC bf16 [batch*hw, c0 (+c1)]."""
@@ -157,6 +169,7 @@ def groupnorm(x0, gamma, beta, batch, hw, *, x1=None, eps=1e-5, silu=True, out=N
     return out
 
 
+@_op("layernorm")
 def layernorm(x, gamma, beta, *, eps=1e-5, out=None):
     lib = _lib.load()
     _req(x, bf16, "x")
@@ -168,6 +181,7 @@ def layernorm(x, gamma, beta, *, eps=1e-5, out=None):
     return out
 
 
+@_op("small_linear")
 def small_linear(x, w, bias=None, *, add=None, act_in=ACT_NONE, act_out=ACT_NONE, out=None):
     lib = _lib.load()
     _req(x, f32, "x")
@@ -181,6 +195,7 @@ def small_linear(x, w, bias=None, *, add=None, act_in=ACT_NONE, act_out=ACT_NONE
     return out
 
 
+@_op("other")
 def timestep_embedding(t, dim, *, out=None):
     lib = _lib.load()
     _req(t, f32, "t")
@@ -192,6 +207,7 @@ def timestep_embedding(t, dim, *, out=None):
     return out
 
 
+@_op("other")
 def im2col3x3_nchw(x, kpad, *, scale=None, out=None, batch=None):
     """batch > x.shape[0] replicates the images cyclically (CFG rows) while loading."""
     lib = _lib.load()
@@ -205,6 +221,7 @@ def im2col3x3_nchw(x, kpad, *, scale=None, out=None, batch=None):
     return out
 
 
+@_op("im2col_s2")
 def im2col3x3_s2(x, batch, h, w, *, out=None):
     lib = _lib.load()
     _req(x, bf16, "x")
@@ -216,6 +233,7 @@ def im2col3x3_s2(x, batch, h, w, *, out=None):
     return out
 
 
+@_op("upsample")
 def upsample_nearest2x(x, batch, h, w, *, out=None):
     lib = _lib.load()
     _req(x, bf16, "x")
@@ -239,6 +257,7 @@ def cfg_euler_step(x, eps, n_img, guidance_rows, hw, sigma_q, sigma, sigma_next,
     return x
 
 
+@_op("cfg_euler")
 def cfg_euler_step_dev(x, eps, n_img, guidance_rows, hw, sigmas3, scale, scale_im, *,
                        denoised_out=None):
     lib = _lib.load()
@@ -251,6 +270,7 @@ def cfg_euler_step_dev(x, eps, n_img, guidance_rows, hw, sigmas3, scale, scale_i
     return x
 
 
+@_op("cast")
 def cast_bf16(x, *, out=None):
     lib = _lib.load()
     _req(x, f32, "x")
@@ -261,6 +281,7 @@ def cast_bf16(x, *, out=None):
     return out
 
 
+@_op("cast")
 def cast_f32(x, *, out=None):
     lib = _lib.load()
     _req(x, bf16, "x")
@@ -271,6 +292,7 @@ def cast_f32(x, *, out=None):
     return out
 
 
+@_op("other")
 def nhwc_to_nchw_f32(x, batch, hw, c, *, out=None):
     lib = _lib.load()
     if out is None:
@@ -280,6 +302,7 @@ def nhwc_to_nchw_f32(x, batch, hw, c, *, out=None):
     return out
 
 
+@_op("other")
 def nchw_to_nhwc_bf16(x, *, out=None):
     """fp32 [B, C, ...spatial] -> bf16 tokens [B*hw, C]."""
     lib = _lib.load()
@@ -293,6 +316,7 @@ def nchw_to_nhwc_bf16(x, *, out=None):
     return out
 
 
+@_op("nerf")
 def nerf_points(cams, xy, depths, w_nv_geo, b_nv, b, n, res, d, kpe):
     lib = _lib.load()
     dev = cams.device
@@ -307,6 +331,7 @@ def nerf_points(cams, xy, depths, w_nv_geo, b_nv, b, n, res, d, kpe):
     return pe, gidx, gwgt, vlogit
 
 
+@_op("nerf")
 def nerf_combine(g, hpre, gidx, gwgt, vlogit, b, n, hw, d, c):
     lib = _lib.load()
     s = torch.empty((b * hw * d, c), device=g.device, dtype=bf16)
@@ -317,6 +342,7 @@ def nerf_combine(g, hpre, gidx, gwgt, vlogit, b, n, hw, d, c):
     return s, vs
 
 
+@_op("nerf")
 def nerf_volrender(feats, raw, dists, b, hw, d, c):
     lib = _lib.load()
     dev = feats.device

@@ -58,6 +58,88 @@ def test_gemm_linear(M, N, K, bn):
 
 
 @gpu
+@pytest.mark.parametrize("M,N,K", [
+    (256, 256, 128),
+    (300, 384, 200),          # ragged M (second CTA of the pair partly / fully out of range), K tail
+    (3072, 1280, 1280),
+    (12288, 640, 640),
+    (640, 5120, 1280),
+    (129, 264, 64),           # peer CTA owns a single valid row; N tail inside the peer's W half
+])
+def test_gemm_cta_pair(M, N, K):
+    """cta_group::2 kernel (block_n=512): 256 x 256 tiles across a two-CTA cluster."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(12)
+    a, af = _rt(torch.randn(M, K, device=_dev()))
+    w, wf = _rt(torch.randn(N, K, device=_dev()) / math.sqrt(K))
+    bias = torch.randn(N, device=_dev()) if N % 4 == 0 else None
+    res, resf = _rt(torch.randn(M, N, device=_dev()))
+    out = ops.gemm(a, w, bias=bias, residual=res, block_n=512)
+    ref = af @ wf.t() + resf + (bias if bias is not None else 0)
+    _assert_close(out, ref, what="gemm cta pair")
+    for max_ctas in (2, 6):  # one / three clusters looping over all tiles: ring + TMEM wrap-around
+        out = ops.gemm(a, w, block_n=512, max_ctas=max_ctas)
+        _assert_close(out, af @ wf.t(), what=f"gemm cta pair max_ctas={max_ctas}")
+
+
+@gpu
+def test_cta_pair_conv_geglu_segments():
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200.sgm.prepack import pack_conv3x3, pack_geglu
+    torch.manual_seed(13)
+    B, H, W, Cin, Cout = 3, 32, 32, 320, 640
+    x, xf = _rt(torch.randn(B, Cin, H, W, device=_dev()))
+    w, wf = _rt(torch.randn(Cout, Cin, 3, 3, device=_dev()) / math.sqrt(9 * Cin))
+    bias = torch.randn(Cout, device=_dev())
+    emb = torch.randn(B, Cout, device=_dev())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cin)
+    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, bias=bias, row_bias=emb, block_n=512)
+    ref = torch.nn.functional.conv2d(xf, wf, bias, padding=1) + emb[:, :, None, None]
+    _assert_close(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), what="conv3x3 cta pair")
+    # small image: a 128-row tile spans two images, the pair spans four
+    B, H, W, Cin, Cout = 5, 8, 8, 128, 256
+    x, xf = _rt(torch.randn(B, Cin, H, W, device=_dev()))
+    w, wf = _rt(torch.randn(Cout, Cin, 3, 3, device=_dev()) / math.sqrt(9 * Cin))
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cin)
+    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, block_n=512)
+    ref = torch.nn.functional.conv2d(xf, wf, None, padding=1)
+    _assert_close(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), what="conv3x3 cta pair small")
+    # GEGLU + two K segments
+    c, M = 640, 1024
+    a, af = _rt(torch.randn(M, c, device=_dev()))
+    w, wf = _rt(torch.randn(8 * c, c, device=_dev()) / math.sqrt(c))
+    b8 = torch.randn(8 * c, device=_dev())
+    wp, bp = pack_geglu(w, b8)
+    out = ops.gemm(a, wp, bias=bp, geglu=True, block_n=512)
+    h = af @ wf.t() + b8
+    xx, gate = h.chunk(2, dim=-1)
+    _assert_close(out, xx * torch.nn.functional.gelu(gate), abs_=2e-3, what="geglu cta pair")
+    a0, a0f = _rt(torch.randn(M, 1280, device=_dev()))
+    a1, a1f = _rt(torch.randn(M, 640, device=_dev()))
+    w2, w2f = _rt(torch.randn(640, 1920, device=_dev()) / math.sqrt(1920))
+    out = ops.gemm(a0, w2, a1=a1, block_n=512)
+    _assert_close(out, torch.cat([a0f, a1f], 1) @ w2f.t(), what="two segments cta pair")
+
+
+@gpu
+def test_kernels_are_bit_deterministic():
+    """No floating-point atomics on the path: repeated launches give identical bits."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(14)
+    x, _ = _rt(torch.randn(3 * 1024, 640, device=_dev()))
+    g, b = torch.randn(640, device=_dev()), torch.randn(640, device=_dev())
+    o1 = ops.groupnorm(x, g, b, 3, 1024)
+    o2 = ops.groupnorm(x, g, b, 3, 1024)
+    assert torch.equal(o1, o2)
+    w, _ = _rt(torch.randn(1280, 640, device=_dev()) / 25)
+    assert torch.equal(ops.gemm(x, w), ops.gemm(x, w))
+    q, _ = _rt(torch.randn(3 * 1024, 640, device=_dev()))
+    a1 = ops.attention(q, x, x, 3, 10, 1024, 1024)
+    a2 = ops.attention(q, x, x, 3, 10, 1024, 1024)
+    assert torch.equal(a1, a2)
+
+
+@gpu
 def test_gemm_persistent_many_tiles():
     """More tiles than CTAs: exercises the smem ring wrap-around and TMEM double buffering."""
     from custom_diffusion360_b200 import ops

@@ -219,5 +219,45 @@ def test_fused_guided_sampler_vs_golden(gold):
     # a second image through the same engine re-uses the captured graph's buffers
     out3 = engine.sample(c, uc=uc, batch_size=1, num_steps=steps, noise=inp["x"].clone(),
                          pose=[cams] * 3)
-    # GroupNorm partial sums use shared-memory atomics (order not fixed) -> last-bit differences
-    _check("fused_repeat", out3, out, rel_tol=2e-2, max_frac=0.1)
+    # every kernel reduces in a fixed order (no floating-point atomics): the repeat is bit-exact,
+    # which also guards against races between the graph-replayed kernels
+    _record("fused_repeat", out3, out)
+    assert torch.equal(out3, out)
+
+
+@gpu
+def test_sdxl_unet_config1_vs_oracle():
+    """BASELINE.json configs[0]: the full SDXL UNet (2.57 B params), one forward, 64x64 latent,
+    batch 1, FeatureNeRF off — CUDA path vs the fp32 CPU oracle on the same seeded weights.
+    ~300 sequential bf16 roundings of the residual stream: tolerance rel_rms <= 6e-2."""
+    import math
+    dev = torch.device("cuda:0")
+    cfg = dict(O.SDXL_CFG, image_cross_blocks=[])
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for name, shape in O.param_shapes(cfg).items():
+        if name.endswith("bias"):
+            sd[name] = 0.02 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[name] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            std = 1.0 / math.sqrt(float(torch.tensor(shape[1:]).prod()))
+            if name.endswith("proj_out.weight") or name.endswith("out_layers.3.weight"):
+                std *= 0.5
+            sd[name] = std * torch.randn(shape, generator=g)
+    x = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(1, 77, 2048, generator=g)
+    y = torch.randn(1, 2816, generator=g)
+    t = torch.tensor([500])
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    with torch.device("meta"):
+        model = UNetModel(**cfg)
+    model = model.to_empty(device=dev)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        eps, *_ = model(x.to(dev), timesteps=t.to(dev), context=ctx.to(dev), y=y.to(dev))
+        torch.cuda.synchronize()
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref, _ = O.unet_forward(sd, cfg, x, t, ctx, y)
+    _check("sdxl_config1_L64_B1_pose_off", eps, ref, rel_tol=6e-2, max_frac=0.25)
