@@ -1,13 +1,18 @@
 // attention_tcgen05.cu — flash attention (head dim 64) on tcgen05 for sm_100a.
 //
 // One CTA = 128 queries of one (batch, head); two CTAs are resident per SM so that one CTA's
-// tensor-core work (S = Q K^T, O_j = P V) overlaps the other's softmax.  Roles inside a CTA:
+// tensor-core work (S = Q K^T, O += P V) overlaps the other's softmax.  Roles inside a CTA:
 //   warp 0 (1 thread)  TMA producer: Q once, then a 2-stage ring of (K_j, V_j) tiles of 128 keys
 //   warp 1 (1 thread)  tcgen05.mma issuer
-//   warp 2             TMEM allocator (128 columns S + 64 columns O_j -> 256 allocated)
-//   warps 4-7          softmax: one thread per query row (TMEM lane == row), online softmax in
-//                      base 2 with fp32 running max / sum, P written as bf16 into 128B-swizzled
-//                      smem (A operand of the second MMA), O accumulated in registers.
+//   warp 2             TMEM allocator (128 columns S + 64 columns O -> 256 allocated)
+//   warps 4-7          softmax: one thread per query row (TMEM lane == row), base-2 softmax with
+//                      fp32 running sum, P written as bf16 into 128B-swizzled smem (A operand of
+//                      the second MMA).
+// O is accumulated IN TMEM by the P·V MMAs (accumulate flag) and is only touched by the softmax
+// threads when the running row maximum has grown by more than 2^8 since the reference maximum was
+// last fixed ("lazy rescaling": exp2 arguments stay <= 8, so bf16 P and the fp32 sums cannot
+// overflow; the final division by the row sum makes the result independent of the reference).
+// That removes the per-tile TMEM->register round trip of O from the critical path.
 // V is consumed in place as an MN-major B operand, so no transpose of V is ever materialised, and
 // Q/K/V/O are addressed in the [B, n, heads*64] layout the projections produce — the reference's
 // head split/merge permute+contiguous copies (sgm/modules/attention.py:393-401,413-418) vanish.
@@ -34,6 +39,7 @@ constexpr int ATT_SMEM_BYTES = ATT_BAR + 128;
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
+constexpr float ATT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row max grew by > 2^8
 
 struct AttnParams {
   __nv_bfloat16* o;
@@ -47,6 +53,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -125,35 +136,43 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, true);  // V is MN-major
     const uint32_t q_addr = smem_u32(smem + ATT_SQ);
     const uint32_t p_addr = smem_u32(smem + ATT_SP);
-    mbar_wait(q_full, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      mbar_wait(&kv_full[stage], phase);
-      tc_fence_after();
+    auto issue_s = [&](int stage) {  // S = Q K^T : 4 k-steps of 16 over d = 64
       const uint32_t k_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES);
-      const uint32_t v_addr = k_addr + ATT_TILE_BYTES;
-      // S = Q K^T : 4 k-steps of 16 over d = 64
 #pragma unroll
       for (int k = 0; k < ATT_D / 16; ++k)
         umma_bf16(tmem_base + ATT_TMEM_S, make_smem_desc_sw128(q_addr + k * 32),
                   make_smem_desc_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
       umma_commit(s_full);
-      // O_j = P V : 8 k-steps of 16 over the 128 keys of this tile
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      // O (+)= P V : 8 k-steps of 16 over the 128 keys of this tile
       mbar_wait(p_full, j & 1);
       tc_fence_after();
+      const uint32_t v_addr =
+          smem_u32(smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
 #pragma unroll
       for (int k = 0; k < ATT_BKV / 16; ++k) {
         const uint32_t a = p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32;
         const uint32_t b = v_addr + k * 16 * 128;
         umma_bf16(tmem_base + ATT_TMEM_O, make_smem_desc_sw128(a), make_smem_desc_sw128(b),
-                  idesc_o, k != 0 ? 1u : 0u);
+                  idesc_o, (j | k) != 0 ? 1u : 0u);
       }
       umma_commit(o_full);
       umma_commit(&kv_empty[stage]);
       if (++stage == ATT_STAGES) {
         stage = 0;
         phase ^= 1;
+      }
+      if (j + 1 < num_kv_tiles) {  // S of the next tile runs right behind P V on the tensor pipe
+        mbar_wait(&kv_full[stage], phase);
+        tc_fence_after();
+        issue_s(stage);
       }
     }
   } else if (warp >= 4) {
@@ -164,16 +183,14 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_O;
     uint8_t* sp_row = smem + ATT_SP + row * 128;
     const int sw = row & 7;
-    float m = -INFINITY, l = 0.f;
-    float o[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
+    float m_ref = -INFINITY;  // reference maximum (raw score units) the exponentials are taken against
+    float l = 0.f;
 
     for (int j = 0; j < num_kv_tiles; ++j) {
       const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // pass 1: row max of this tile
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -182,16 +199,40 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_ld_wait();
         if (c * 32 + 32 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 2)
+            mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      const float m_new = fmaxf(m, mx);  // finite: every tile has >= 1 valid key
-      const float alpha = ex2_approx((m - m_new) * p.scale_log2);
-      const float mb = m_new * p.scale_log2;
+      // P V of the previous tile must have retired before P is overwritten / O is rescaled
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // lazy rescale (every tile has >= 1 valid key, so mx is finite)
+      const bool grow = (mx - m_ref) * p.scale_log2 > ATT_RESCALE_LOG2;  // true on the first tile
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_ref;
+        if (j > 0) {
+          const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_o + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, r);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+        m_ref = m_new;
+      }
+      const float mb = m_ref * p.scale_log2;
       // pass 2: exponentiate, row sum, write bf16 P into the swizzled A-operand buffer
       float sum = 0.f;
 #pragma unroll 1
@@ -200,12 +241,20 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_ld_32x32b_x32(t_s + c * 32, r);
         tmem_ld_wait();
         float pv[32];
+        if (c * 32 + 32 <= valid) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-          if (c * 32 + i >= valid) e = 0.f;
-          pv[i] = e;
-          sum += e;
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            sum += pv[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+            if (c * 32 + i >= valid) e = 0.f;
+            pv[i] = e;
+            sum += e;
+          }
         }
         uint8_t* half_base = sp_row + (c >> 1) * ATT_TILE_BYTES;
 #pragma unroll
@@ -219,41 +268,37 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
           *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
         }
       }
-      l = l * alpha + sum;
-      m = m_new;
+      l += sum;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // accumulate O_j
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_o + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
-      tc_fence_before();
     }
+    // epilogue: O / l
+    mbar_wait(o_full, (num_kv_tiles - 1) & 1);
+    tc_fence_after();
     const int qrow = q_tile * ATT_BQ + row;
-    if (qrow < p.nq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst =
-          p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
-      uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16x2(o[8 * g + 0] * inv, o[8 * g + 1] * inv);
-        u.y = pack_bf16x2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-        u.z = pack_bf16x2(o[8 * g + 4] * inv, o[8 * g + 5] * inv);
-        u.w = pack_bf16x2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-        d4[g] = u;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_o + c * 32, r);
+      tmem_ld_wait();
+      if (qrow < p.nq) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+          d4[g] = u;
+        }
       }
     }
+    tc_fence_before();
   }
 
   tc_fence_before();
@@ -319,7 +364,9 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   p.heads = heads;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((nq + ATT_BQ - 1) / ATT_BQ, heads, batch);
-  launch_ex(attention_bf16_tcgen05_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, tq, tk, tv, p);
+  if (launch_ex(attention_bf16_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1,
+                tq, tk, tv, p) != cudaSuccess)
+    return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }

@@ -174,8 +174,9 @@ class MemoryEfficientCrossAttention(nn.Module, _Packed):
                               self.heads, n, n, ldq=3 * inner, ldk=3 * inner, ldv=3 * inner)
         else:
             q = ops.gemm(xn, p["wq"])
-            a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, self.heads, n, nkv,
-                              ldq=inner, ldk=2 * inner, ldv=2 * inner)
+            # kv may be a column slice of the all-blocks context projection: row stride from the view
+            a = ops.attention(q, kv[:, :inner], kv[:, inner:2 * inner], batch, self.heads, n, nkv,
+                              ldq=inner, ldk=kv.stride(0), ldv=kv.stride(0))
         return ops.gemm(a, p["wo"], bias=p["bo"], residual=residual, out=out)
 
     def forward(self, x, context=None, mask=None, additional_tokens=None,
@@ -288,11 +289,14 @@ class BasicTransformerBlock(nn.Module):
                 alphas.view(b, hw, d, 1), rgb if self.rgb_predict else None)
 
     # ---- token fast path -----------------------------------------------------------------------
-    def tokens(self, x, batch, n, ctx_tok, nctx, cams=None):
-        """x bf16 [batch*n, c] (updated in place where possible) -> (x, aux | None)."""
+    def tokens(self, x, batch, n, ctx_tok, nctx, cams=None, kv=None):
+        """x bf16 [batch*n, c] (updated in place where possible) -> (x, aux | None).
+        kv: this block's K|V projection of the context if the caller already computed it
+        (UNetModel projects the context for ALL blocks in one GEMM per step)."""
         aux = None
         x = self.attn1.tokens(self.norm1.tokens(x), batch, n, residual=x, out=x)
-        kv = self.attn2.project_context(ctx_tok)
+        if kv is None:
+            kv = self.attn2.project_context(ctx_tok)
         x = self.attn2.tokens(self.norm2.tokens(x), batch, n, kv=kv, nkv=nctx, residual=x, out=x)
         if self.image_cross and cams is not None:
             if self.rendered_feat is None:
@@ -388,14 +392,19 @@ class SpatialTransformer(nn.Module, _Packed):
         return dict(g=self.norm.weight.detach().float().contiguous(),
                     b=self.norm.bias.detach().float().contiguous())
 
-    def tokens(self, x, batch, hw, ctx_tok, nctx, cams=None, aux_out=None):
-        """x bf16 [batch*hw, c] -> same shape (new tensor)."""
+    def tokens(self, x, batch, hw, ctx_tok, nctx, cams=None, aux_out=None, kv_all=None):
+        """x bf16 [batch*hw, c] -> same shape (new tensor).  kv_all: optional [batch*nctx, sum 2c]
+        context projection of every block of the network (blocks know their column slice)."""
         p = self.packed()
         xn = ops.groupnorm(x, p["g"], p["b"], batch, hw, eps=self.norm.eps, silu=False)
         h = self.proj_in.tokens(xn)
         for i, block in enumerate(self.transformer_blocks):
             use_pose = self.image_cross and (i % self.poscontrol_interval == 0)
-            h, aux = block.tokens(h, batch, hw, ctx_tok, nctx, cams if use_pose else None)
+            kv = None
+            sl = block.__dict__.get("_kv_slice")
+            if kv_all is not None and sl is not None:
+                kv = kv_all[:, sl[0]:sl[0] + sl[1]]
+            h, aux = block.tokens(h, batch, hw, ctx_tok, nctx, cams if use_pose else None, kv=kv)
             if aux is not None and aux_out is not None:
                 aux_out.append(aux)
         return self.proj_out.tokens(h, residual=x)

@@ -301,6 +301,22 @@ class UNetModel(nn.Module, _Packed):
             og=f(self.out[0].weight), ob=f(self.out[0].bias),
             cout_w=pack_conv3x3(self.out[2].weight.detach()), cout_b=f(self.out[2].bias))
         assert 9 * self.in_channels <= 64
+        # context K|V projection weights of every transformer block, concatenated: one GEMM per
+        # step instead of one small-M GEMM (M = 77*B rows) per block; the per-block packed copies
+        # become views of this buffer
+        from ..attention import BasicTransformerBlock
+        blocks = [m for m in self.modules() if isinstance(m, BasicTransformerBlock)]
+        if blocks:
+            parts, off = [], 0
+            for blk in blocks:
+                wkv = blk.attn2.packed()["wkv"]
+                blk.__dict__["_kv_slice"] = (off, wkv.shape[0])
+                parts.append(wkv)
+                off += wkv.shape[0]
+            p["kvw"] = torch.cat(parts, 0).contiguous()
+            for blk in blocks:
+                o, n = blk.__dict__["_kv_slice"]
+                blk.attn2.packed()["wkv"] = p["kvw"][o:o + n]
         return p
 
     # ---- forward -------------------------------------------------------------------------------
@@ -311,7 +327,7 @@ class UNetModel(nn.Module, _Packed):
                 h = layer.tokens(h, batch, hh, ww, emb_all[:, off:off + n], skip=skip)
                 skip = None
             elif isinstance(layer, SpatialTransformer):
-                h = layer.tokens(h, batch, hh * ww, ctx_tok, nctx, cams, aux)
+                h = layer.tokens(h, batch, hh * ww, ctx_tok, nctx, cams, aux, kv_all=p.get("kv_all"))
             elif isinstance(layer, Downsample):
                 h = layer.tokens(h, batch, hh, ww)
                 hh, ww = hh // 2, ww // 2
@@ -365,6 +381,7 @@ class UNetModel(nn.Module, _Packed):
             ctx_tok, nctx = context, context.shape[0] // b
         cams = pack_pose(pose, dev) if pose is not None else None
         aux: list = []
+        p["kv_all"] = ops.gemm(ctx_tok, p["kvw"]) if "kvw" in p else None
         # input conv: Cin=4 -> im2col (K=36 padded to 64) + GEMM
         col = ops.im2col3x3_nchw(x.float().contiguous(), 64, scale=in_scale, batch=b)
         h = ops.gemm(col, p["cin_w"], bias=p["cin_b"])
