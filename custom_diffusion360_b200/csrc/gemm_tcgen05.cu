@@ -3,25 +3,29 @@
 //   warp 0 (1 thread)  TMA producer: A and W tiles -> 128B-swizzled smem ring (mbarrier full/empty)
 //   warp 1 (1 thread)  tcgen05.mma issuer (leader CTA only in pair mode)
 //   warp 2             TMEM allocator / deallocator
-//   warps 4-11         epilogue: tcgen05.ld -> bias / emb-add / activation / GEGLU / residual -> HBM
-//                      (two warps per TMEM lane quarter, each taking half of the tile's columns)
+//   warps 4-11         epilogue: two warps per TMEM lane quarter, each taking half of the tile's
+//                      columns, 64 columns ("slab") at a time:
+//                        tcgen05.ld -> +bias / +per-image emb bias / SiLU / GEGLU (fp32 registers)
+//                        + residual slab (TMA-loaded into 128B-swizzled smem, prefetched a slab
+//                          ahead, i.e. during the next tile's main loop)
+//                        -> bf16 slab in swizzled smem -> ONE TMA store per slab.
+//                      Row-per-thread global loads/stores (32 sectors per warp instruction) made
+//                      the epilogue slower than a K<=1280 main loop; the TMA path is fully
+//                      coalesced and clips M/N tails by itself.  fp32 outputs and odd leading
+//                      dimensions take the direct path.
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 //
 // Pair mode (CG == 2): a cluster of two CTAs computes a 256 x BN tile with
 // tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA loads its own 128 rows of A and HALF of the
-// W tile (BN/2 rows), so per-SM operand traffic from L2 drops by a third and a 192 KB smem ring
-// buffers twice as many MMA cycles.  Both CTAs' TMA loads complete on the leader's `full`
-// barrier; the leader's MMA thread releases smem slots / publishes accumulators to both CTAs with
-// multicast tcgen05.commit; the peer's epilogue warps hand TMEM back with remote mbarrier arrives.
+// W tile (BN/2 rows), so per-SM operand traffic from L2 drops by a third.  Both CTAs' TMA loads
+// complete on the leader's `full` barrier; the leader's MMA thread releases smem slots /
+// publishes accumulators to both CTAs with multicast tcgen05.commit; the peer's epilogue warps
+// hand TMEM back with remote mbarrier arrives.
 //
 // Convolution mode feeds the SAME main loop from a 4-D NHWC tensor map: the A tile of K-block
 // (tap, c-chunk) is the box [64 ch, tw, th, tb] at pixel offset (dx-1, dy-1); out-of-image
 // coordinates are zero-filled by TMA, which implements the pad-1 border without a halo copy.
-//
-// Every kernel in this library is launched with programmatic dependent launch: the prologue
-// (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail, and
-// griddepcontrol.wait orders all global-memory traffic after the previous grid's completion.
 //
 // Reference arithmetic replaced: see include/cd360.h (cd360_gemm_bf16).
 #include <stdlib.h>
@@ -34,7 +38,8 @@ constexpr int BM = 128;  // rows per CTA
 constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
-constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int SLAB_BYTES = BM * 64 * 2;     // 128 rows x 64 bf16 = 16 KiB epilogue staging tile
 
 struct GemmKParams {
   int M, N, N_out;
@@ -55,6 +60,7 @@ struct GemmKParams {
   int out_fp32;
   int act;
   int geglu;
+  int epi_tma;  // 1: slab epilogue through smem + TMA (bf16 out, 16-byte aligned rows)
 };
 
 template <int BN, int STAGES, int CG>
@@ -62,11 +68,13 @@ struct GemmSmem {
   static constexpr int BNC = BN / CG;  // W rows this CTA stages
   static constexpr int B_TILE_BYTES = BNC * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] + tmem ptr
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;       // out[2] | res[2] slabs
+  static constexpr int BAR_OFFSET = EPI_OFFSET + 4 * SLAB_BYTES;
+  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] res_full[2] + tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 6) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
-  static_assert(DYN_BYTES <= 227 * 1024, "smem ring too large");
+  static_assert(DYN_BYTES <= 227 * 1024, "smem budget exceeded");
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024 B alignment");
 };
 
 // ---- epilogue helpers --------------------------------------------------------------------------
@@ -89,6 +97,7 @@ __device__ __forceinline__ void load_bias32(float (&v)[32], const float* __restr
   }
 }
 
+// direct (row-per-thread) store path: fp32 outputs, odd leading dimensions, N tails < 8
 __device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams& p, long long row,
                                               int ocol0, int nvalid) {
   if (p.residual != nullptr) {
@@ -147,7 +156,9 @@ template <int BN, int STAGES, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                          const __grid_constant__ CUtensorMap tmA1,
-                         const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+                         const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmOut,
+                         const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
   using L = GemmSmem<BN, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -156,7 +167,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,6 +185,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    if (p.epi_tma) {
+      tma_prefetch_desc(&tmOut);
+      if (p.residual != nullptr) tma_prefetch_desc(&tmRes);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -182,6 +198,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&res_full[b], 1);
     }
     fence_barrier_init();
   }
@@ -291,14 +308,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int q = warp & 3;               // TMEM lane quarter this warp may access (warp % 4)
     const int half = (warp - 4) >> 2;     // which half of the tile's columns
     const int row_in_tile = q * 32 + lane;
+    const bool half_leader = (q == 0) && (lane == 0);
+    uint8_t* out_buf = smem + L::EPI_OFFSET + half * SLAB_BYTES;
+    uint8_t* res_buf = smem + L::EPI_OFFSET + (2 + half) * SLAB_BYTES;
+    const uint32_t bar_id = 1 + 2 * half;  // named barriers (1,2) / (3,4) for the two halves
+    const int sw = row_in_tile & 7;
+    const bool use_res = p.epi_tma && p.residual != nullptr;
+    // out slabs this half produces per tile, and the slab's first OUTPUT column inside the tile
+    constexpr int SLABS = BN / 128;                 // plain: 64-col slabs per half
+    const int n_slabs = p.geglu ? (BN / 256 > 0 ? BN / 256 : 1) : SLABS;
+    const int out_tile_cols = p.geglu ? BN / 2 : BN;
+    auto slab_col = [&](int n_blk, int s) {         // first output column of slab s of this half
+      return n_blk * out_tile_cols + (half * n_slabs + s) * 64;
+    };
+    uint32_t res_cnt = 0;  // residual slabs consumed so far (parity of res_full[half])
+    if (use_res && half_leader && unit < num_tiles) {
+      const int m_blk = unit % p.num_m_blocks, n_blk = unit / p.num_m_blocks;
+      mbar_arrive_expect_tx(&res_full[half], SLAB_BYTES);
+      tma_load_2d(res_buf, &tmRes, &res_full[half], slab_col(n_blk, 0),
+                  (m_blk * CG + static_cast<int>(rank)) * BM);
+    }
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
-      const long long row =
-          static_cast<long long>(m_blk * CG + static_cast<int>(rank)) * BM + row_in_tile;
+      const int row0 = (m_blk * CG + static_cast<int>(rank)) * BM;
+      const long long row = static_cast<long long>(row0) + row_in_tile;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
       mbar_wait(&tmem_full[buf], acc_phase);
@@ -308,64 +345,170 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const float* rb = nullptr;
       if (p.row_bias != nullptr && row_ok) rb = p.row_bias + (row / p.rows_per_group) * p.ld_row_bias;
 
-      if (!p.geglu) {
-        constexpr int CH = BN / 64;  // 32-column chunks per half
-#pragma unroll 1
-        for (int ci = 0; ci < CH; ++ci) {
-          const int c = half * CH + ci;
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (row_ok) {
-            const int nvalid = min(32, p.N - col0);
-            float v[32];
+      if (p.epi_tma) {
+        // ---------------- slab path: registers -> swizzled smem -> TMA store ----------------
+        for (int s = 0; s < n_slabs; ++s) {
+          float v[64];
+          if (!p.geglu) {
+            const int c0 = (half * SLABS + s) * 2;  // first 32-col chunk of this slab
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias != nullptr) load_bias32(v, p.bias, col0, nvalid);
-            if (rb != nullptr) load_bias32(v, rb, col0, nvalid);
-            if (p.act == CD360_ACT_SILU) {
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr + (c0 + h) * 32, r);
+              tmem_ld_wait();
+              float vv[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+              for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]);
+              const int col0 = n0 + (c0 + h) * 32;
+              const int nvalid = max(0, min(32, p.N - col0));
+              if (nvalid > 0) {
+                if (p.bias != nullptr) load_bias32(vv, p.bias, col0, nvalid);
+                if (rb != nullptr) load_bias32(vv, rb, col0, nvalid);
+              }
+              if (p.act == CD360_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) vv[j] = silu_f(vv[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[h * 32 + j] = vv[j];
             }
-            store_chunk32(v, p, row, col0, nvalid);
+          } else {
+            // x columns [c*32..] and their gates [BN/2 + c*32..] of the pre-interleaved W tile
+            const int c0 = (half * n_slabs + s) * 2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t rx[32], rg[32];
+              tmem_ld_32x32b_x32(taddr + (c0 + h) * 32, rx);
+              tmem_ld_32x32b_x32(taddr + BN / 2 + (c0 + h) * 32, rg);
+              tmem_ld_wait();
+              float xv[32], gv[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                xv[j] = __uint_as_float(rx[j]);
+                gv[j] = __uint_as_float(rg[j]);
+              }
+              if (p.bias != nullptr) {
+                load_bias32(xv, p.bias, n0 + (c0 + h) * 32, 32);
+                load_bias32(gv, p.bias, n0 + BN / 2 + (c0 + h) * 32, 32);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[h * 32 + j] = xv[j] * gelu_erf_f(gv[j]);
+            }
+          }
+          if (s == n_slabs - 1) {  // all TMEM reads of this tile done: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
+              else mbar_arrive(&tmem_empty[buf]);
+            }
+          }
+          if (use_res) {
+            mbar_wait(&res_full[half], res_cnt & 1);
+            ++res_cnt;
+            const uint8_t* rrow = res_buf + row_in_tile * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((c ^ sw) << 4));
+              float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                     f3 = unpack_bf16x2(u.w);
+              v[8 * c + 0] += f0.x; v[8 * c + 1] += f0.y; v[8 * c + 2] += f1.x;
+              v[8 * c + 3] += f1.y; v[8 * c + 4] += f2.x; v[8 * c + 5] += f2.y;
+              v[8 * c + 6] += f3.x; v[8 * c + 7] += f3.y;
+            }
+          }
+          // the previous TMA store of this half must have finished reading out_buf
+          if (half_leader) tma_store_wait_read();
+          named_bar_sync(bar_id, 128);  // res_buf fully consumed, out_buf reusable
+          if (use_res && half_leader) {  // prefetch the next residual slab (this or next tile)
+            int nt = tile, ns = s + 1;
+            if (ns == n_slabs) { nt = tile + num_units; ns = 0; }
+            if (nt < num_tiles) {
+              const int nm = nt % p.num_m_blocks, nn = nt / p.num_m_blocks;
+              mbar_arrive_expect_tx(&res_full[half], SLAB_BYTES);
+              tma_load_2d(res_buf, &tmRes, &res_full[half], slab_col(nn, ns),
+                          (nm * CG + static_cast<int>(rank)) * BM);
+            }
+          }
+          uint8_t* orow = out_buf + row_in_tile * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 u;
+            u.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+            u.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            u.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+            u.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id + 1, 128);  // slab complete in smem
+          if (half_leader) {
+            tma_store_2d(&tmOut, out_buf, slab_col(n_blk, s), row0);
+            tma_store_commit();
           }
         }
       } else {
-        // tile columns [0, BN/2) hold x, [BN/2, BN) hold the matching gates (pre-interleaved W)
-        constexpr int CH = BN / 128;  // (x, gate) chunk pairs per half
+        // ---------------- direct path ----------------
+        if (!p.geglu) {
+          constexpr int CH = BN / 64;  // 32-column chunks per half
 #pragma unroll 1
-        for (int ci = 0; ci < CH; ++ci) {
-          const int c = half * CH + ci;
-          uint32_t rx[32], rg[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, rx);
-          tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
-          tmem_ld_wait();
-          if (row_ok) {
-            float v[32], g[32];
+          for (int ci = 0; ci < CH; ++ci) {
+            const int c = half * CH + ci;
+            const int col0 = n0 + c * 32;
+            if (col0 >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if (row_ok) {
+              const int nvalid = min(32, p.N - col0);
+              float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(rx[j]);
-              g[j] = __uint_as_float(rg[j]);
-            }
-            if (p.bias != nullptr) {
-              load_bias32(v, p.bias, n0 + c * 32, 32);
-              load_bias32(g, p.bias, n0 + BN / 2 + c * 32, 32);
-            }
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if (p.bias != nullptr) load_bias32(v, p.bias, col0, nvalid);
+              if (rb != nullptr) load_bias32(v, rb, col0, nvalid);
+              if (p.act == CD360_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
-            store_chunk32(v, p, row, n_blk * (BN / 2) + c * 32, 32);
+                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+              }
+              store_chunk32(v, p, row, col0, nvalid);
+            }
+          }
+        } else {
+          constexpr int CH = BN / 128;  // (x, gate) chunk pairs per half
+#pragma unroll 1
+          for (int ci = 0; ci < (CH > 0 ? CH : 1); ++ci) {
+            const int c = half * CH + ci;
+            if (CH == 0 && half == 1) break;
+            uint32_t rx[32], rg[32];
+            tmem_ld_32x32b_x32(taddr + c * 32, rx);
+            tmem_ld_32x32b_x32(taddr + BN / 2 + c * 32, rg);
+            tmem_ld_wait();
+            if (row_ok) {
+              float v[32], g[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                v[j] = __uint_as_float(rx[j]);
+                g[j] = __uint_as_float(rg[j]);
+              }
+              if (p.bias != nullptr) {
+                load_bias32(v, p.bias, n0 + c * 32, 32);
+                load_bias32(g, p.bias, n0 + BN / 2 + c * 32, 32);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
+              store_chunk32(v, p, row, n_blk * (BN / 2) + c * 32, 32);
+            }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
-        else mbar_arrive(&tmem_empty[buf]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
+          else mbar_arrive(&tmem_empty[buf]);
+        }
       }
     }
+    if (p.epi_tma && half_leader) tma_store_wait_all();  // smem must outlive the bulk stores
   }
 
   // ---- teardown ----
@@ -433,7 +576,8 @@ static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 template <int BN, int STAGES, int CG>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                       const GemmKParams& p, int max_ctas, cudaStream_t stream) {
+                       const CUtensorMap& o, const CUtensorMap& r, const GemmKParams& p,
+                       int max_ctas, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, CG>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, CG>;
@@ -447,28 +591,26 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
   int units = num_sms() / CG;
   if (max_ctas > 0 && max_ctas / CG >= 1 && max_ctas / CG < units) units = max_ctas / CG;
   if (tiles < units) units = tiles;
-  if (launch_ex(kern, dim3(units * CG), dim3(kGemmThreads), L::DYN_BYTES, stream, CG, a0, a1, b,
-                p) != cudaSuccess)
+  if (launch_ex(kern, dim3(units * CG), dim3(kGemmThreads), L::DYN_BYTES, stream, CG, a0, a1, b, o,
+                r, p) != cudaSuccess)
     return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
 
-// tile configuration: block_n = 128 / 256 selects the single-CTA kernels, 512 (= "256 wide,
-// CTA pair") the cta_group::2 kernel; 0 = heuristic.
+// tile configuration: block_n = 128 selects the single-CTA 128x128 kernel, 256 / 512 the
+// 256x256 CTA-pair (cta_group::2) kernel; 0 = heuristic (pair whenever M spans two CTAs).
 static int pick_config(int M, int N, int geglu, int requested) {
-  if (requested == 128 || requested == 256 || requested == 512) return requested;
   static int pair_ok = -1;
   if (pair_ok < 0) {
     const char* e = getenv("CD360_GEMM_PAIR");
     pair_ok = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
+  if (requested == 128) return 128;
+  if (requested == 256 || requested == 512) return (geglu && (N % 256) != 0) ? 128 : 512;
   if (geglu && (N % 256) != 0) return 128;
-  if (N <= 128) return 128;
-  if (pair_ok && M > 128 && N >= 256) return 512;
-  if (geglu) return 256;
-  const long long t256 = static_cast<long long>((M + BM - 1) / BM) * ((N + 255) / 256);
-  return t256 >= 100 ? 256 : 128;
+  if (N <= 128 || M <= 128 || !pair_ok) return (geglu && (N % 256) == 0) ? 512 : 128;
+  return 512;
 }
 
 }  // namespace cd360
@@ -488,7 +630,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   if (a->M <= 0 || a->N <= 0) return CD360_ERR_SHAPE;
   const int cfgsel = pick_config(a->M, a->N, a->geglu, a->block_n);
   const int CGsel = cfgsel == 512 ? 2 : 1;
-  const int BN = cfgsel == 512 ? 256 : cfgsel;
+  const int BN = cfgsel == 512 ? 256 : 128;
   if (a->geglu && (a->N % BN != 0 || (a->N & 1))) return CD360_ERR_SHAPE;
   if (a->geglu && a->act != CD360_ACT_NONE) return CD360_ERR_UNSUPPORTED;
 
@@ -520,8 +662,15 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   if (a->residual && (a->ldr & 7)) return CD360_ERR_ALIGN;
   if (a->ldo < p.N_out) return CD360_ERR_SHAPE;
   if ((a->bias || a->row_bias) && (a->N & 3)) return CD360_ERR_ALIGN;
+  // slab/TMA epilogue: bf16 output with 16-byte aligned rows (TMA clips the M / N tails)
+  p.epi_tma = (!a->out_fp32 && (a->ldo & 7) == 0 && (p.N_out & 7) == 0) ? 1 : 0;
+  if (a->geglu && BN == 128) p.epi_tma = 0;  // 64 output columns per tile: one slab, direct path
+  {
+    const char* e = getenv("CD360_GEMM_EPI_TMA");
+    if (e != nullptr && e[0] == '0') p.epi_tma = 0;
+  }
 
-  CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;
   int ktot;
   int rc;
   if (a->conv) {
@@ -586,7 +735,21 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, true);
     if (rc != CD360_OK) return rc;
   }
-  if (cfgsel == 512) return launch_gemm<256, 6, 2>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
-  if (cfgsel == 256) return launch_gemm<256, 4, 1>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
-  return launch_gemm<128, 6, 1>(tmA0, tmA1, tmB, p, a->max_ctas, stream);
+  tmOut = tmB;
+  tmRes = tmB;
+  if (p.epi_tma) {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.N_out), static_cast<uint64_t>(a->M)};
+    uint32_t box[2] = {64, BM};
+    uint64_t so[1] = {static_cast<uint64_t>(a->ldo) * 2};
+    rc = encode_tmap_bf16(&tmOut, a->out, 2, dims, so, box, false);
+    if (rc != CD360_OK) return rc;
+    if (a->residual != nullptr) {
+      uint64_t sr[1] = {static_cast<uint64_t>(a->ldr) * 2};
+      rc = encode_tmap_bf16(&tmRes, a->residual, 2, dims, sr, box, false);
+      if (rc != CD360_OK) return rc;
+    }
+  }
+  if (cfgsel == 512)
+    return launch_gemm<256, 5, 2>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
+  return launch_gemm<128, 5, 1>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
 }
