@@ -35,10 +35,12 @@ constexpr int ATT_SQ = 0;
 constexpr int ATT_SKV = ATT_TILE_BYTES;                               // stages x (K, V)
 constexpr int ATT_SP = ATT_SKV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 16 KiB halves
 constexpr int ATT_BAR = ATT_SP + 2 * ATT_TILE_BYTES;
-constexpr int ATT_SMEM_BYTES = ATT_BAR + 128;
+constexpr int ATT_ONES = ATT_BAR + 128;   // 512 B of bf16 1.0: B operand of the row-sum MMA
+constexpr int ATT_SMEM_BYTES = ATT_ONES + 512;
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
+constexpr uint32_t ATT_TMEM_L = ATT_TMEM_O + 64;  // 16 columns, each = sum_j P[row, j]
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row max grew by > 2^8
 
 struct AttnParams {
@@ -53,6 +55,26 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// packed fp32 pair FMA (Blackwell FFMA2): halves the FMA-pipe instruction count of the softmax
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+// smem descriptor of an un-swizzled MN-major operand made of 8x8 core matrices (128 B each) that
+// are LBO / SBO = 128 B apart.  Only used for the all-ones tile, whose content is layout-invariant.
+__device__ __forceinline__ uint64_t make_smem_desc_ones(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(128 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version; layout type 0 = no swizzle
+  return d;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -106,6 +128,11 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
     tmem_relinquish();
   }
+  if (warp == 3) {  // 512 B of bf16 ones (0x3F80)
+    reinterpret_cast<uint4*>(smem + ATT_ONES)[lane] =
+        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -134,6 +161,8 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, true);  // V is MN-major
+    constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BQ, 16, true);     // P x ones -> row sums
+    const uint64_t ones_desc = make_smem_desc_ones(smem_u32(smem + ATT_ONES));
     const uint32_t q_addr = smem_u32(smem + ATT_SQ);
     const uint32_t p_addr = smem_u32(smem + ATT_SP);
     auto issue_s = [&](int stage) {  // S = Q K^T : 4 k-steps of 16 over d = 64
@@ -162,6 +191,9 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         const uint32_t b = v_addr + k * 16 * 128;
         umma_bf16(tmem_base + ATT_TMEM_O, make_smem_desc_sw128(a), make_smem_desc_sw128(b),
                   idesc_o, (j | k) != 0 ? 1u : 0u);
+        // row sums of the bf16 P the product actually uses: 16 identical columns of l
+        umma_bf16(tmem_base + ATT_TMEM_L, make_smem_desc_sw128(a), ones_desc, idesc_l,
+                  (j | k) != 0 ? 1u : 0u);
       }
       umma_commit(o_full);
       umma_commit(&kv_empty[stage]);
@@ -184,7 +216,6 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     uint8_t* sp_row = smem + ATT_SP + row * 128;
     const int sw = row & 7;
     float m_ref = -INFINITY;  // reference maximum (raw score units) the exponentials are taken against
-    float l = 0.f;
 
     for (int j = 0; j < num_kv_tiles; ++j) {
       const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV);
@@ -219,7 +250,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         if (j > 0) {
           const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < 3; ++c) {  // 64 columns of O, then the chunk holding the row sums
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_o + c * 32, r);
             tmem_ld_wait();
@@ -228,13 +259,13 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
             tmem_st_32x32b_x32(t_o + c * 32, r);
           }
           tmem_st_wait();
-          l *= alpha;
         }
         m_ref = m_new;
       }
       const float mb = m_ref * p.scale_log2;
-      // pass 2: exponentiate, row sum, write bf16 P into the swizzled A-operand buffer
-      float sum = 0.f;
+      // pass 2: exponentiate, write bf16 P into the swizzled A-operand buffer
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nmb2 = make_float2(-mb, -mb);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
@@ -243,9 +274,11 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         float pv[32];
         if (c * 32 + 32 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-            sum += pv[i];
+          for (int i = 0; i < 32; i += 2) {
+            const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                   sc2, nmb2);
+            pv[i] = ex2_approx(a.x);
+            pv[i + 1] = ex2_approx(a.y);
           }
         } else {
 #pragma unroll
@@ -253,7 +286,6 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
             float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
             if (c * 32 + i >= valid) e = 0.f;
             pv[i] = e;
-            sum += e;
           }
         }
         uint8_t* half_base = sp_row + (c >> 1) * ATT_TILE_BYTES;
@@ -268,7 +300,6 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
           *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
         }
       }
-      l += sum;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -278,7 +309,13 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     mbar_wait(o_full, (num_kv_tiles - 1) & 1);
     tc_fence_after();
     const int qrow = q_tile * ATT_BQ + row;
-    const float inv = 1.f / l;
+    float inv;
+    {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_o + 64, r);  // columns [64, 80) all hold the row sum
+      tmem_ld_wait();
+      inv = 1.f / __uint_as_float(r[0]);
+    }
     __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
