@@ -29,14 +29,16 @@ constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_D = 64;
 constexpr int ATT_STAGES = 2;
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM / ones, warps 4-11: softmax
 constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 128 B
 constexpr int ATT_SQ = 0;
 constexpr int ATT_SKV = ATT_TILE_BYTES;                               // stages x (K, V)
 constexpr int ATT_SP = ATT_SKV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 16 KiB halves
 constexpr int ATT_BAR = ATT_SP + 2 * ATT_TILE_BYTES;
-constexpr int ATT_ONES = ATT_BAR + 128;   // 512 B of bf16 1.0: B operand of the row-sum MMA
-constexpr int ATT_SMEM_BYTES = ATT_ONES + 512;
+constexpr int ATT_ONES = ATT_BAR + 128;   // 256 B of bf16 1.0: B operand of the row-sum MMA
+constexpr int ATT_EXCH = ATT_ONES + 256;  // [2][128] bf16: per-half row maxima of the current tile
+constexpr int ATT_SMEM_BYTES = ATT_EXCH + 512;
+static_assert(2 * (ATT_SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr uint32_t ATT_TMEM_COLS = 256;
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
@@ -67,13 +69,12 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&d);
 }
 // smem descriptor of an un-swizzled MN-major operand made of 8x8 core matrices (128 B each) that
-// are LBO / SBO = 128 B apart.  Only used for the all-ones tile, whose content is layout-invariant.
+// aliased onto a 256-byte region.  Only used for the all-ones tile, whose content is layout-invariant.
 __device__ __forceinline__ uint64_t make_smem_desc_ones(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(128 >> 4) << 16;
-  d |= static_cast<uint64_t>(128 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version; layout type 0 = no swizzle
+  d |= static_cast<uint64_t>(128 >> 4) << 16;  // LBO = 128 B, SBO = 0: every access stays inside
+  d |= static_cast<uint64_t>(1) << 46;         // the 256-byte ones region; layout type 0 = no swizzle
   return d;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -120,7 +121,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -128,9 +129,10 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
     tmem_relinquish();
   }
-  if (warp == 3) {  // 512 B of bf16 ones (0x3F80)
-    reinterpret_cast<uint4*>(smem + ATT_ONES)[lane] =
-        make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  if (warp == 3) {  // 256 B of bf16 ones (0x3F80)
+    if (lane < 16)
+      reinterpret_cast<uint4*>(smem + ATT_ONES)[lane] =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -209,22 +211,27 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
   } else if (warp >= 4) {
     // ================================ softmax / output ================================
-    const int q = warp - 4;
+    // two threads per query row: warps 4-7 own key columns [0,64) of the tile, warps 8-11 own
+    // [64,128) (same TMEM lane quarters) -> 4 softmax warps per scheduler with two resident CTAs,
+    // which is what hides the TMEM / MUFU latencies of the per-row chains.
+    const int q = warp & 3;
+    const int h = (warp - 4) >> 2;  // column half
     const int row = q * 32 + lane;  // row inside the Q tile == TMEM lane
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_S;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_S + h * 64;
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_O;
-    uint8_t* sp_row = smem + ATT_SP + row * 128;
+    uint8_t* sp_row = smem + ATT_SP + h * ATT_TILE_BYTES + row * 128;
+    uint16_t* exch = reinterpret_cast<uint16_t*>(smem + ATT_EXCH);  // [2][128] bf16 partial maxima
     const int sw = row & 7;
     float m_ref = -INFINITY;  // reference maximum (raw score units) the exponentials are taken against
 
     for (int j = 0; j < num_kv_tiles; ++j) {
-      const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV);
+      const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV) - h * 64;  // valid keys in my half
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max of this tile
+      // pass 1: max over my 64 columns
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_s + c * 32, r);
         tmem_ld_wait();
@@ -238,19 +245,33 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
             if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
+      // exchange with the partner thread of this row.  Both partners use the SAME value
+      // max(bf16_up(mx_0), bf16_up(mx_1)) (>= the true row max, within 2^-8 relative): the
+      // reference maximum only has to be consistent and close, not exact (lazy rescaling).
+      {
+        uint32_t u = __float_as_uint(mx);
+        if (mx > 0.f && (u & 0xFFFFu)) u += 0x10000u;  // round up (negative: truncation rounds up)
+        exch[h * 128 + row] = static_cast<uint16_t>(u >> 16);
+      }
+      named_bar_sync(1, 256);
+      const float m_tile = fmaxf(__uint_as_float(static_cast<uint32_t>(exch[row]) << 16),
+                                 __uint_as_float(static_cast<uint32_t>(exch[128 + row]) << 16));
       // P V of the previous tile must have retired before P is overwritten / O is rescaled
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
-      // lazy rescale (every tile has >= 1 valid key, so mx is finite)
-      const bool grow = (mx - m_ref) * p.scale_log2 > ATT_RESCALE_LOG2;  // true on the first tile
+      // lazy rescale (every tile has >= 1 valid key, so m_tile is finite)
+      const bool grow = (m_tile - m_ref) * p.scale_log2 > ATT_RESCALE_LOG2;  // true on the first tile
       if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = grow ? mx : m_ref;
+        const float m_new = grow ? m_tile : m_ref;
         if (j > 0) {
           const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
+          // half 0 rescales O[:, 0:32) and the row-sum chunk, half 1 rescales O[:, 32:64)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {  // 64 columns of O, then the chunk holding the row sums
+          for (int cc = 0; cc < 2; ++cc) {
+            if (h == 1 && cc == 1) break;
+            const int c = (h == 0) ? (cc == 0 ? 0 : 2) : 1;
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_o + c * 32, r);
             tmem_ld_wait();
@@ -263,11 +284,11 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         m_ref = m_new;
       }
       const float mb = m_ref * p.scale_log2;
-      // pass 2: exponentiate, write bf16 P into the swizzled A-operand buffer
+      // pass 2: exponentiate my 64 columns, write bf16 P (one 128-byte row of P half h)
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
       const float2 nmb2 = make_float2(-mb, -mb);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_s + c * 32, r);
         tmem_ld_wait();
@@ -288,7 +309,6 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
             pv[i] = e;
           }
         }
-        uint8_t* half_base = sp_row + (c >> 1) * ATT_TILE_BYTES;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
@@ -296,8 +316,8 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
           u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
           u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
           u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          const int chunk = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
-          *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
+          const int chunk = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
+          *reinterpret_cast<uint4*>(sp_row + ((chunk ^ sw) << 4)) = u;
         }
       }
       fence_proxy_async_smem();
@@ -305,7 +325,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // epilogue: O / l
+    // epilogue: O / l — each partner stores 32 of the row's 64 output channels
     mbar_wait(o_full, (num_kv_tiles - 1) & 1);
     tc_fence_after();
     const int qrow = q_tile * ATT_BQ + row;
@@ -316,14 +336,14 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       tmem_ld_wait();
       inv = 1.f / __uint_as_float(r[0]);
     }
-    __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    __nv_bfloat16* dst =
+        p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D + h * 32;
+    {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(t_o + c * 32, r);
+      tmem_ld_32x32b_x32(t_o + h * 32, r);
       tmem_ld_wait();
       if (qrow < p.nq) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
