@@ -36,6 +36,8 @@ class GemmArgs(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32),
         ("conv", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
         ("act", C.c_int32), ("geglu", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_slabs", C.c_int32), ("ln_eps", C.c_float),
+        ("ln_colsum", C.c_void_p), ("stats_out", C.c_void_p),
     ]
 
 

@@ -61,6 +61,13 @@ struct GemmKParams {
   int act;
   int geglu;
   int epi_tma;  // 1: slab epilogue through smem + TMA (bf16 out, 16-byte aligned rows)
+  // LayerNorm folded into the GEMM (gamma in W, beta in bias): out = rstd*(acc - mu*colsum) + bias
+  const float* ln_stats;   // [M, ln_slabs, 2] partial (sum, sumsq) of every A row, or NULL
+  int ln_slabs;
+  float ln_inv_c, ln_eps;
+  const float* ln_colsum;  // [N]
+  float* stats_out;        // [M, N_out/64, 2] partial (sum, sumsq) of the bf16 output rows, or NULL
+  int stats_slabs;
 };
 
 template <int BN, int STAGES, int CG>
@@ -338,6 +345,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const long long row = static_cast<long long>(row0) + row_in_tile;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr && row_ok) {  // finalise this row's LayerNorm statistics
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + row * p.ln_slabs;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_slabs; ++i) {
+          const float2 t2 = __ldg(st + i);
+          s1 += t2.x;
+          s2 += t2.y;
+        }
+        ln_mu = s1 * p.ln_inv_c;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr =
@@ -362,6 +381,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               const int col0 = n0 + (c0 + h) * 32;
               const int nvalid = max(0, min(32, p.N - col0));
               if (nvalid > 0) {
+                if (p.ln_stats != nullptr) {
+                  float cs[32];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) cs[j] = 0.f;
+                  load_bias32(cs, p.ln_colsum, col0, nvalid);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) vv[j] = fmaf(-ln_mu, cs[j], vv[j]) * ln_rstd;
+                }
                 if (p.bias != nullptr) load_bias32(vv, p.bias, col0, nvalid);
                 if (rb != nullptr) load_bias32(vv, rb, col0, nvalid);
               }
@@ -386,6 +413,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               for (int j = 0; j < 32; ++j) {
                 xv[j] = __uint_as_float(rx[j]);
                 gv[j] = __uint_as_float(rg[j]);
+              }
+              if (p.ln_stats != nullptr) {
+                float cx[32], cgt[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { cx[j] = 0.f; cgt[j] = 0.f; }
+                load_bias32(cx, p.ln_colsum, n0 + (c0 + h) * 32, 32);
+                load_bias32(cgt, p.ln_colsum, n0 + BN / 2 + (c0 + h) * 32, 32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  xv[j] = fmaf(-ln_mu, cx[j], xv[j]) * ln_rstd;
+                  gv[j] = fmaf(-ln_mu, cgt[j], gv[j]) * ln_rstd;
+                }
               }
               if (p.bias != nullptr) {
                 load_bias32(xv, p.bias, n0 + (c0 + h) * 32, 32);
@@ -431,6 +470,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
           }
           uint8_t* orow = out_buf + row_in_tile * 128;
+          float so1 = 0.f, so2 = 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 u;
@@ -439,7 +479,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             u.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
             u.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
             *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = u;
+            if (p.stats_out != nullptr) {  // moments of the ROUNDED values a LayerNorm would read
+              const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
+                           f3 = unpack_bf16x2(u.w);
+              so1 += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+              so2 = fmaf(f0.x, f0.x, so2); so2 = fmaf(f0.y, f0.y, so2);
+              so2 = fmaf(f1.x, f1.x, so2); so2 = fmaf(f1.y, f1.y, so2);
+              so2 = fmaf(f2.x, f2.x, so2); so2 = fmaf(f2.y, f2.y, so2);
+              so2 = fmaf(f3.x, f3.x, so2); so2 = fmaf(f3.y, f3.y, so2);
+            }
           }
+          if (p.stats_out != nullptr && row_ok)
+            reinterpret_cast<float2*>(p.stats_out)[row * p.stats_slabs + slab_col(n_blk, s) / 64] =
+                make_float2(so1, so2);
           fence_proxy_async_smem();
           named_bar_sync(bar_id + 1, 128);  // slab complete in smem
           if (half_leader) {
@@ -668,6 +720,27 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   {
     const char* e = getenv("CD360_GEMM_EPI_TMA");
     if (e != nullptr && e[0] == '0') p.epi_tma = 0;
+  }
+  if (a->ln_stats != nullptr || a->stats_out != nullptr) {
+    if (!p.epi_tma || a->conv) return CD360_ERR_UNSUPPORTED;
+    if (a->ln_stats != nullptr) {
+      if (a->k1 != 0) return CD360_ERR_UNSUPPORTED;  // the folded LayerNorm spans one K segment
+      if (a->ln_colsum == nullptr) return CD360_ERR_NULL;
+      if (a->ln_slabs <= 0 || (reinterpret_cast<uintptr_t>(a->ln_stats) & 7) ||
+          (reinterpret_cast<uintptr_t>(a->ln_colsum) & 15))
+        return CD360_ERR_ALIGN;
+      p.ln_stats = a->ln_stats;
+      p.ln_slabs = a->ln_slabs;
+      p.ln_inv_c = 1.0f / static_cast<float>(a->k0);
+      p.ln_eps = a->ln_eps;
+      p.ln_colsum = a->ln_colsum;
+    }
+    if (a->stats_out != nullptr) {
+      if ((p.N_out % 64) != 0 || (reinterpret_cast<uintptr_t>(a->stats_out) & 7))
+        return CD360_ERR_SHAPE;
+      p.stats_out = a->stats_out;
+      p.stats_slabs = p.N_out / 64;
+    }
   }
 
   CUtensorMap tmA0, tmA1, tmB, tmOut, tmRes;

@@ -44,9 +44,13 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out=None,
          out_fp32=False, act=ACT_NONE, geglu=False, a1=None, block_n=0, max_ctas=0,
-         lda=None, lda1=None, k0=None, k1=None, M=None):
+         lda=None, lda1=None, k0=None, k1=None, M=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5,
+         stats_out=None):
     """out = epilogue(A @ W^T).  a: bf16 [M, K0] (row stride `lda` if given), optional second
-    K-segment a1 [M, K1]; w: bf16 [N, K0+K1]."""
+    K-segment a1 [M, K1]; w: bf16 [N, K0+K1].
+    ln_stats / ln_colsum: LayerNorm of the A rows folded into the epilogue (w, bias pre-folded with
+    gamma / beta, see include/cd360.h); stats_out: fp32 [M, N_out/64, 2] receives the per-slab
+    (sum, sumsq) of the output rows for the next folded LayerNorm."""
     lib = _lib.load()
     _req(w, bf16, "w")
     M = a.shape[0] if M is None else M
@@ -67,7 +71,9 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out
         ld_row_bias=(row_bias.stride(0) if row_bias is not None else 0),
         residual=_ptr(residual), ldr=(residual.stride(0) if residual is not None else 0),
         out=_ptr(out), ldo=out.stride(0), out_fp32=int(out.dtype == f32), M=M, N=N,
-        conv=0, B=0, H=0, W=0, C=0, act=act, geglu=int(geglu), block_n=block_n, max_ctas=max_ctas)
+        conv=0, B=0, H=0, W=0, C=0, act=act, geglu=int(geglu), block_n=block_n, max_ctas=max_ctas,
+        ln_stats=_ptr(ln_stats), ln_slabs=(ln_stats.shape[1] if ln_stats is not None else 0),
+        ln_eps=float(ln_eps), ln_colsum=_ptr(ln_colsum), stats_out=_ptr(stats_out))
     _run("gemm", 2.0 * M * N * (k0 + k1),
          lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16"))
     return out

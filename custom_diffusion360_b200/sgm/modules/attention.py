@@ -30,6 +30,10 @@ from .nerfsd_pytorch3d import NerfSDModule, VolRender
 from .utils_cameraray import pack_pose
 
 bf16 = torch.bfloat16
+# LayerNorms folded into the neighbouring GEMM epilogues on the token fast path (CD360_LN_FUSED=0
+# falls back to the stand-alone LayerNorm kernel, for A/B measurements)
+import os as _os
+LN_FUSED = _os.environ.get("CD360_LN_FUSED", "1") != "0"
 
 
 def to_tokens(x: torch.Tensor) -> torch.Tensor:
@@ -62,6 +66,7 @@ def invalidate_all_packed(root: nn.Module):
             m.invalidate_packed()
         if hasattr(m, "_packed"):
             m._packed = None
+        m.__dict__.pop("_lnpk", None)
 
 
 class Linear(nn.Linear, _Packed):
@@ -318,6 +323,88 @@ class BasicTransformerBlock(nn.Module):
         x = self.ff.tokens(self.norm3.tokens(x), residual=x, out=x)
         return x, aux
 
+    # ---- token fast path with the three LayerNorms folded into the GEMMs -------------------------
+    def ln_packed(self):
+        """gamma folded into the consuming weights (W' = W diag(gamma), bf16), beta into the bias
+        (b' = b + W beta), plus the column sums of W' the epilogue needs: LN(x) W^T + b ==
+        rstd (x W'^T - mu colsum(W')) + b'.  The statistics (mu, rstd) come from the (sum, sumsq)
+        partials the PRODUCING GEMM's epilogue wrote, so no LayerNorm kernel and no normalised
+        copy of x exist on this path."""
+        dev = self.norm1.weight.device
+        p = self.__dict__.get("_lnpk")
+        if p is not None and p["dev"] == dev:
+            return p
+        f = lambda t: t.detach().float()
+
+        def fold(w, b, norm):
+            g, beta = f(norm.weight), f(norm.bias)
+            wf = f(w)
+            wq = (wf * g[None, :]).to(bf16).contiguous()
+            bias = wf @ beta + (f(b) if b is not None else 0.0)
+            return wq, bias.contiguous()
+
+        a1, a2 = self.attn1, self.attn2
+        wqkv, bqkv = fold(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, self.norm1)
+        wq2, bq2 = fold(a2.to_q.weight, None, self.norm2)
+        proj = self.ff.net[0].proj
+        wff, bff = fold(proj.weight, proj.bias, self.norm3)
+        wff, bff = pack_geglu(wff, bff)  # interleave AFTER folding; column sums follow the packed rows
+        p = dict(dev=dev, wqkv=wqkv, bqkv=bqkv, cqkv=wqkv.float().sum(1).contiguous(),
+                 wq2=wq2, bq2=bq2, cq2=wq2.float().sum(1).contiguous(),
+                 wff=wff, bff=bff, cff=wff.float().sum(1).contiguous())
+        self.__dict__["_lnpk"] = p
+        return p
+
+    def tokens_fused(self, x, stats, batch, n, ctx_tok, nctx, cams=None, kv=None):
+        """Like `tokens`, with stats = fp32 [batch*n, c/64, 2] row moments of x (from the GEMM that
+        produced x).  Returns (x, stats_of_new_x, aux)."""
+        aux = None
+        lp = self.ln_packed()
+        M, c = x.shape
+        S = c // 64
+        dev = x.device
+        a1, a2 = self.attn1, self.attn2
+        p1, p2 = a1.packed(), a2.packed()
+        inner = a1.heads * a1.dim_head
+        eps = self.norm1.eps
+        new_stats = lambda: torch.empty((M, S, 2), device=dev, dtype=torch.float32)
+        # self-attention: LN1 folded into the QKV projection
+        qkv = ops.gemm(x, lp["wqkv"], bias=lp["bqkv"], ln_stats=stats, ln_colsum=lp["cqkv"], ln_eps=eps)
+        a = ops.attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], batch, a1.heads,
+                          n, n, ldq=3 * inner, ldk=3 * inner, ldv=3 * inner)
+        st = new_stats()
+        x = ops.gemm(a, p1["wo"], bias=p1["bo"], residual=x, out=x, stats_out=st)
+        # text cross-attention: LN2 folded into the query projection
+        if kv is None:
+            kv = a2.project_context(ctx_tok)
+        q = ops.gemm(x, lp["wq2"], bias=lp["bq2"], ln_stats=st, ln_colsum=lp["cq2"], ln_eps=eps)
+        a = ops.attention(q, kv[:, :inner], kv[:, inner:2 * inner], batch, a2.heads, n, nctx,
+                          ldq=inner, ldk=kv.stride(0), ldv=kv.stride(0))
+        st = new_stats()
+        x = ops.gemm(a, p2["wo"], bias=p2["bo"], residual=x, out=x, stats_out=st)
+        if self.image_cross and cams is not None:
+            if self.rendered_feat is None:
+                xref_tok = self.context_ref_tokens(batch)
+                n_views = self._ctxref_cache[2]
+                rendered, fg, alphas, rgb = self.reference_tokens(cams, xref_tok, n_views, kv, nctx,
+                                                                  batch, n)
+                buf = self.__dict__.get("_rendered_buf")
+                if buf is None or buf.shape != rendered.shape or buf.device != rendered.device:
+                    buf = rendered
+                    self.__dict__["_rendered_buf"] = buf
+                else:
+                    buf.copy_(rendered)
+                self.rendered_feat = buf
+                aux = (fg, alphas, rgb)
+            st = new_stats()
+            x = self.pose_emb_layers.tokens(x, a1=self.rendered_feat, stats_out=st)
+        # feed-forward: LN3 folded into the GEGLU projection
+        h = ops.gemm(x, lp["wff"], bias=lp["bff"], geglu=True, ln_stats=st, ln_colsum=lp["cff"],
+                     ln_eps=eps)
+        st = new_stats()
+        x = self.ff.net[2].tokens(h, residual=x, out=x, stats_out=st)
+        return x, st, aux
+
     # ---- reference-signature entry point ---------------------------------------------------------
     def forward(self, x, context=None, context_ref=None, pose=None, mask_ref=None, prev_weights=None,
                 additional_tokens=None, n_times_crossframe_attn_in_self=0):
@@ -397,14 +484,25 @@ class SpatialTransformer(nn.Module, _Packed):
         context projection of every block of the network (blocks know their column slice)."""
         p = self.packed()
         xn = ops.groupnorm(x, p["g"], p["b"], batch, hw, eps=self.norm.eps, silu=False)
-        h = self.proj_in.tokens(xn)
+        fused = LN_FUSED and (self.in_channels % 64 == 0)
+        stats = None
+        if fused:  # proj_in's epilogue emits the row moments the first block's LayerNorm needs
+            stats = torch.empty((xn.shape[0], self.in_channels // 64, 2), device=xn.device,
+                                dtype=torch.float32)
+            h = self.proj_in.tokens(xn, stats_out=stats)
+        else:
+            h = self.proj_in.tokens(xn)
         for i, block in enumerate(self.transformer_blocks):
             use_pose = self.image_cross and (i % self.poscontrol_interval == 0)
             kv = None
             sl = block.__dict__.get("_kv_slice")
             if kv_all is not None and sl is not None:
                 kv = kv_all[:, sl[0]:sl[0] + sl[1]]
-            h, aux = block.tokens(h, batch, hw, ctx_tok, nctx, cams if use_pose else None, kv=kv)
+            if fused:
+                h, stats, aux = block.tokens_fused(h, stats, batch, hw, ctx_tok, nctx,
+                                                   cams if use_pose else None, kv=kv)
+            else:
+                h, aux = block.tokens(h, batch, hw, ctx_tok, nctx, cams if use_pose else None, kv=kv)
             if aux is not None and aux_out is not None:
                 aux_out.append(aux)
         return self.proj_out.tokens(h, residual=x)

@@ -87,8 +87,20 @@ typedef struct cd360_gemm_args {
   int32_t B, H, W, C;
   int32_t act;   /* CD360_ACT_* */
   int32_t geglu; /* 0 / 1 */
-  int32_t block_n; /* 0 = auto, else 128 or 256 */
+  int32_t block_n; /* 0 = auto, 128 = single-CTA 128x128 tiles, 256/512 = CTA-pair 256x256 tiles */
   int32_t max_ctas; /* 0 = one per SM */
+  /* LayerNorm folded into the contraction (linear mode, bf16 output).  With W' = W diag(gamma)
+   * and bias' = bias + W beta supplied as `w` / `bias`:
+   *     out[m, n] = rstd[m] * (acc[m, n] - mu[m] * ln_colsum[n]) + bias'[n]
+   * where mu / rstd come from `ln_stats` = per-row partial (sum, sumsq) over 64-column slabs,
+   * fp32 [M, ln_slabs, 2], written by the GEMM that produced A through `stats_out`
+   * (fp32 [M, N_out/64, 2], moments of the bf16-rounded output rows; N_out % 64 == 0).
+   * Replaces the three nn.LayerNorm of BasicTransformerBlock (attention.py:531-533, 609-636). */
+  const float* ln_stats;
+  int32_t ln_slabs;
+  float ln_eps;
+  const float* ln_colsum; /* [N] fp32: sum_k w[n, k] of the bf16 weight actually multiplied */
+  float* stats_out;
 } cd360_gemm_args;
 
 int cd360_gemm_bf16(const cd360_gemm_args* args, cd360_stream_t stream);

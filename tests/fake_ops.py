@@ -18,7 +18,7 @@ class Fake:
 
     def gemm(self, a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out=None,
              out_fp32=False, act=0, geglu=False, a1=None, block_n=0, max_ctas=0, lda=None, lda1=None,
-             k0=None, k1=None, M=None):
+             k0=None, k1=None, M=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5, stats_out=None):
         assert a.dtype == bf16 and w.dtype == bf16
         M = a.shape[0]
         K = a.shape[1] + (a1.shape[1] if a1 is not None else 0)
@@ -33,7 +33,11 @@ class Fake:
             assert residual.shape == (M, n_out) and residual.dtype == bf16
         if row_bias is not None:
             assert row_bias.shape[1] == N and rows_per_group > 0
-        self._log("gemm", M=M, N=N, K=K, geglu=geglu)
+        if ln_stats is not None:
+            assert ln_stats.shape == (M, K // 64, 2) and ln_colsum.shape == (N,) and a1 is None
+        if stats_out is not None:
+            assert stats_out.shape == (M, n_out // 64, 2) and n_out % 64 == 0
+        self._log("gemm", M=M, N=N, K=K, geglu=geglu, ln=ln_stats is not None, stats=stats_out is not None)
         if out is not None:
             assert out.shape == (M, n_out)
             return out

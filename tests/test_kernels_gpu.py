@@ -122,6 +122,43 @@ def test_cta_pair_conv_geglu_segments():
 
 
 @gpu
+@pytest.mark.parametrize("M,c,N,geglu", [(384, 640, 1920, False), (3072, 1280, 1280, False),
+                                          (1000, 128, 1024, True), (3072, 1280, 10240, True)])
+def test_gemm_layernorm_folding(M, c, N, geglu):
+    """stats_out of a producing GEMM + LayerNorm folded into the consuming GEMM (gamma in W, beta in
+    the bias, mean / rstd applied in the epilogue) vs explicit LayerNorm -> Linear."""
+    from custom_diffusion360_b200 import ops
+    from custom_diffusion360_b200.sgm.prepack import pack_geglu
+    torch.manual_seed(15)
+    a, af = _rt(torch.randn(M, 256, device=_dev()))
+    w0, w0f = _rt(torch.randn(c, 256, device=_dev()) / 16)
+    res, resf = _rt(torch.randn(M, c, device=_dev()) * 2 + 0.7)   # non-zero row means
+    stats = torch.empty(M, c // 64, 2, device=_dev())
+    x = ops.gemm(a, w0, residual=res, stats_out=stats)
+    xf = x.float()
+    s_ref = torch.stack([xf.view(M, c // 64, 64).sum(-1), (xf * xf).view(M, c // 64, 64).sum(-1)], -1)
+    assert (stats - s_ref).abs().max() <= 1e-3 * s_ref.abs().max()
+    gamma = 1 + 0.2 * torch.randn(c, device=_dev())
+    beta = 0.3 * torch.randn(c, device=_dev())
+    w = torch.randn(N, c, device=_dev()) / math.sqrt(c)
+    b = torch.randn(N, device=_dev())
+    wfold = (w * gamma[None]).to(torch.bfloat16)
+    bfold = (w @ beta + b).contiguous()
+    if geglu:
+        wfold, bfold = pack_geglu(wfold, bfold)
+    colsum = wfold.float().sum(1).contiguous()
+    out = ops.gemm(x, wfold, bias=bfold, geglu=geglu, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-5)
+    xn = torch.nn.functional.layer_norm(xf, (c,), gamma, beta, 1e-5)
+    h = xn @ w.to(torch.bfloat16).float().t() + b
+    if geglu:
+        u, g = h.chunk(2, dim=-1)
+        h = u * torch.nn.functional.gelu(g)
+    # extra error sources vs the unfolded path: gamma folded before the bf16 rounding of W, x not
+    # re-rounded after normalisation, fp32 cancellation in acc - mu*colsum: all ~2^-9 relative
+    _assert_close(out, h, rel=2.0 ** -6, abs_=2e-2, what="layernorm folded gemm")
+
+
+@gpu
 def test_kernels_are_bit_deterministic():
     """No floating-point atomics on the path: repeated launches give identical bits."""
     from custom_diffusion360_b200 import ops
