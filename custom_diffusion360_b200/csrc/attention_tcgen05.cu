@@ -1,19 +1,21 @@
 // attention_tcgen05.cu — flash attention (head dim 64) on tcgen05 for sm_100a.
 //
-// One CTA = 128 queries of one (batch, head); two CTAs are resident per SM so that one CTA's
-// tensor-core work (S = Q K^T, O += P V) overlaps the other's softmax.  Roles inside a CTA:
-//   warp 0 (1 thread)  TMA producer: Q once, then a 2-stage ring of (K_j, V_j) tiles of 128 keys
-//   warp 1 (1 thread)  tcgen05.mma issuer
-//   warp 2             TMEM allocator (128 columns S + 64 columns O -> 256 allocated)
-//   warps 4-7          softmax: one thread per query row (TMEM lane == row), base-2 softmax with
-//                      fp32 running sum, P written as bf16 into 128B-swizzled smem (A operand of
-//                      the second MMA).
-// O is accumulated IN TMEM by the P·V MMAs (accumulate flag) and is only touched by the softmax
+// One CTA = 128 queries of one (batch, head); two CTAs are resident per SM.  Key tiles are 64
+// wide and BOTH the score tile S (TMEM) and the probability tile P (smem) are double buffered, so
+// the tensor pipe computes S(j+1) and P(j-1)·V while the softmax warps work on tile j — the
+// softmax threads never wait for an MMA round trip in steady state.  Roles inside a CTA:
+//   warp 0 (1 thread)  TMA producer: Q once, then a 4-stage ring of (K_j, V_j) tiles of 64 keys
+//   warp 1 (1 thread)  tcgen05.mma issuer: S(j+2) <- Q K^T, O += P(j) V(j), l += P(j) 1
+//   warp 2             TMEM allocator (2 x 64 columns S, 64 columns O, 16 columns row sums)
+//   warp 3             writes the all-ones B operand of the row-sum MMA
+//   warps 4-7          softmax: one thread per query row (TMEM lane == row): base-2 exponentials
+//                      against a lazily updated reference maximum, bf16 P into 128B-swizzled smem.
+// O and the row sums l are accumulated IN TMEM by the MMAs and only touched by the softmax
 // threads when the running row maximum has grown by more than 2^8 since the reference maximum was
-// last fixed ("lazy rescaling": exp2 arguments stay <= 8, so bf16 P and the fp32 sums cannot
-// overflow; the final division by the row sum makes the result independent of the reference).
-// That removes the per-tile TMEM->register round trip of O from the critical path.
-// V is consumed in place as an MN-major B operand, so no transpose of V is ever materialised, and
+// fixed ("lazy rescaling": exp2 arguments stay <= 8, so bf16 P and the fp32 sums cannot overflow;
+// the final division by l makes the result independent of the reference).  l comes from a second
+// tiny MMA (P x ones), i.e. it is the sum of exactly the bf16 weights the P·V product uses.
+// V is consumed in place as an MN-major B operand (no transpose is ever materialised) and
 // Q/K/V/O are addressed in the [B, n, heads*64] layout the projections produce — the reference's
 // head split/merge permute+contiguous copies (sgm/modules/attention.py:393-401,413-418) vanish.
 //
@@ -26,21 +28,22 @@
 namespace cd360 {
 
 constexpr int ATT_BQ = 128;
-constexpr int ATT_BKV = 128;
+constexpr int ATT_BKV = 64;
 constexpr int ATT_D = 64;
-constexpr int ATT_STAGES = 2;
-constexpr int ATT_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM / ones, warps 4-11: softmax
-constexpr int ATT_TILE_BYTES = 128 * 128;  // 128 rows x 128 B
+constexpr int ATT_STAGES = 4;
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_Q_BYTES = 128 * 128;   // 128 rows x 128 B
+constexpr int ATT_KV_BYTES = 64 * 128;   // 64 rows x 128 B (one of K / V)
+constexpr int ATT_P_BYTES = 128 * 128;   // 128 rows x 64 keys bf16
 constexpr int ATT_SQ = 0;
-constexpr int ATT_SKV = ATT_TILE_BYTES;                               // stages x (K, V)
-constexpr int ATT_SP = ATT_SKV + ATT_STAGES * 2 * ATT_TILE_BYTES;     // 2 x 16 KiB halves
-constexpr int ATT_BAR = ATT_SP + 2 * ATT_TILE_BYTES;
+constexpr int ATT_SKV = ATT_Q_BYTES;                              // stages x (K, V)
+constexpr int ATT_SP = ATT_SKV + ATT_STAGES * 2 * ATT_KV_BYTES;   // 2 P buffers
+constexpr int ATT_BAR = ATT_SP + 2 * ATT_P_BYTES;
 constexpr int ATT_ONES = ATT_BAR + 128;   // 256 B of bf16 1.0: B operand of the row-sum MMA
-constexpr int ATT_EXCH = ATT_ONES + 256;  // [2][128] bf16: per-half row maxima of the current tile
-constexpr int ATT_SMEM_BYTES = ATT_EXCH + 512;
+constexpr int ATT_SMEM_BYTES = ATT_ONES + 256;
 static_assert(2 * (ATT_SMEM_BYTES + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr uint32_t ATT_TMEM_COLS = 256;
-constexpr uint32_t ATT_TMEM_S = 0;
+constexpr uint32_t ATT_TMEM_S = 0;        // two buffers of 64 columns
 constexpr uint32_t ATT_TMEM_O = 128;
 constexpr uint32_t ATT_TMEM_L = ATT_TMEM_O + 64;  // 16 columns, each = sum_j P[row, j]
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // rescale O only when the row max grew by > 2^8
@@ -68,7 +71,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(*reinterpret_cast<unsigned long long*>(&c)));
   return *reinterpret_cast<float2*>(&d);
 }
-// smem descriptor of an un-swizzled MN-major operand made of 8x8 core matrices (128 B each) that
+// smem descriptor of an un-swizzled MN-major operand made of 8x8 core matrices (128 B each)
 // aliased onto a 256-byte region.  Only used for the all-ones tile, whose content is layout-invariant.
 __device__ __forceinline__ uint64_t make_smem_desc_ones(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -90,19 +93,19 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [ATT_STAGES]
-  uint64_t* kv_empty = bars + 3;  // [ATT_STAGES]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                 // [4]
+  uint64_t* kv_empty = bars + 1 + ATT_STAGES;   // [4]
+  uint64_t* s_full = bars + 1 + 2 * ATT_STAGES; // [2]
+  uint64_t* p_full = s_full + 2;                // [2]
+  uint64_t* o_full = p_full + 2;                // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
-  const int num_kv_tiles = (p.nkv + ATT_BKV - 1) / ATT_BKV;
+  const int nt = (p.nkv + ATT_BKV - 1) / ATT_BKV;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -120,9 +123,11 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 8);
-    mbar_init(o_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 4);  // one arrive per softmax warp
+      mbar_init(&o_full[b], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -143,15 +148,15 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
-    mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+    mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
     tma_load_4d(smem + ATT_SQ, &tmQ, q_full, 0, head, q_tile * ATT_BQ, batch);
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < num_kv_tiles; ++j) {
+    for (int j = 0; j < nt; ++j) {
       mbar_wait(&kv_empty[stage], phase ^ 1);
-      uint8_t* sk = smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES;
-      uint8_t* sv = sk + ATT_TILE_BYTES;
-      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+      uint8_t* sk = smem + ATT_SKV + stage * 2 * ATT_KV_BYTES;
+      uint8_t* sv = sk + ATT_KV_BYTES;
+      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
       tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * ATT_BKV, batch);
       tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * ATT_BKV, batch);
       if (++stage == ATT_STAGES) {
@@ -166,191 +171,149 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     constexpr uint32_t idesc_l = make_idesc_bf16(ATT_BQ, 16, true);     // P x ones -> row sums
     const uint64_t ones_desc = make_smem_desc_ones(smem_u32(smem + ATT_ONES));
     const uint32_t q_addr = smem_u32(smem + ATT_SQ);
-    const uint32_t p_addr = smem_u32(smem + ATT_SP);
-    auto issue_s = [&](int stage) {  // S = Q K^T : 4 k-steps of 16 over d = 64
-      const uint32_t k_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES);
+    auto issue_s = [&](int j) {  // S(j) = Q K_j^T into S buffer j & 1
+      const int stage = j % ATT_STAGES;
+      mbar_wait(&kv_full[stage], (j / ATT_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_KV_BYTES);
+      const uint32_t d = tmem_base + ATT_TMEM_S + (j & 1) * ATT_BKV;
 #pragma unroll
       for (int k = 0; k < ATT_D / 16; ++k)
-        umma_bf16(tmem_base + ATT_TMEM_S, make_smem_desc_sw128(q_addr + k * 32),
-                  make_smem_desc_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(s_full);
+        umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                  idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(&s_full[j & 1]);
     };
     mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
     issue_s(0);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      // O (+)= P V : 8 k-steps of 16 over the 128 keys of this tile
-      mbar_wait(p_full, j & 1);
+    if (nt > 1) issue_s(1);
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      const int stage = j % ATT_STAGES;
+      mbar_wait(&p_full[b], (j >> 1) & 1);  // P(j) written, S buffer b drained, O rescaled
       tc_fence_after();
-      const uint32_t v_addr =
-          smem_u32(smem + ATT_SKV + stage * 2 * ATT_TILE_BYTES) + ATT_TILE_BYTES;
+      const uint32_t p_addr = smem_u32(smem + ATT_SP + b * ATT_P_BYTES);
+      const uint32_t v_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_KV_BYTES) + ATT_KV_BYTES;
 #pragma unroll
       for (int k = 0; k < ATT_BKV / 16; ++k) {
-        const uint32_t a = p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32;
-        const uint32_t b = v_addr + k * 16 * 128;
-        umma_bf16(tmem_base + ATT_TMEM_O, make_smem_desc_sw128(a), make_smem_desc_sw128(b),
-                  idesc_o, (j | k) != 0 ? 1u : 0u);
-        // row sums of the bf16 P the product actually uses: 16 identical columns of l
-        umma_bf16(tmem_base + ATT_TMEM_L, make_smem_desc_sw128(a), ones_desc, idesc_l,
+        const uint64_t a = make_smem_desc_sw128(p_addr + k * 32);
+        umma_bf16(tmem_base + ATT_TMEM_O, a, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
                   (j | k) != 0 ? 1u : 0u);
+        // row sums of the bf16 P the product actually uses: 16 identical columns of l
+        umma_bf16(tmem_base + ATT_TMEM_L, a, ones_desc, idesc_l, (j | k) != 0 ? 1u : 0u);
       }
-      umma_commit(o_full);
+      umma_commit(&o_full[b]);
       umma_commit(&kv_empty[stage]);
-      if (++stage == ATT_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
-      if (j + 1 < num_kv_tiles) {  // S of the next tile runs right behind P V on the tensor pipe
-        mbar_wait(&kv_full[stage], phase);
-        tc_fence_after();
-        issue_s(stage);
-      }
+      if (j + 2 < nt) issue_s(j + 2);
     }
   } else if (warp >= 4) {
     // ================================ softmax / output ================================
-    // two threads per query row: warps 4-7 own key columns [0,64) of the tile, warps 8-11 own
-    // [64,128) (same TMEM lane quarters) -> 4 softmax warps per scheduler with two resident CTAs,
-    // which is what hides the TMEM / MUFU latencies of the per-row chains.
-    const int q = warp & 3;
-    const int h = (warp - 4) >> 2;  // column half
+    const int q = warp - 4;
     const int row = q * 32 + lane;  // row inside the Q tile == TMEM lane
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_S + h * 64;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ATT_TMEM_O;
-    uint8_t* sp_row = smem + ATT_SP + h * ATT_TILE_BYTES + row * 128;
-    uint16_t* exch = reinterpret_cast<uint16_t*>(smem + ATT_EXCH);  // [2][128] bf16 partial maxima
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_o = t_lane + ATT_TMEM_O;
     const int sw = row & 7;
     float m_ref = -INFINITY;  // reference maximum (raw score units) the exponentials are taken against
 
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV) - h * 64;  // valid keys in my half
-      mbar_wait(s_full, j & 1);
+    for (int j = 0; j < nt; ++j) {
+      const int b = j & 1;
+      const int valid = min(ATT_BKV, p.nkv - j * ATT_BKV);
+      mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: max over my 64 columns
+      uint32_t r[64];
+      tmem_ld_32x32b_x32(t_lane + ATT_TMEM_S + b * ATT_BKV, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld_32x32b_x32(t_lane + ATT_TMEM_S + b * ATT_BKV + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld_wait();
       float mx = -INFINITY;
+      if (valid == ATT_BKV) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
-        tmem_ld_wait();
-        if (c * 32 + 32 <= valid) {
+        for (int i = 0; i < 64; i += 2)
+          mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        } else {
+        for (int i = 0; i < 64; ++i)
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      // lazy rescale (every tile has >= 1 valid key, so mx is finite); true on the first tile
+      const bool grow = (mx - m_ref) * p.scale_log2 > ATT_RESCALE_LOG2;
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      const float m_new = grow ? mx : m_ref;
+      const float mb = m_new * p.scale_log2;
+      // exponentials (independent of the O state): MUFU work starts before any wait
+      uint32_t pk[32];
+      if (valid == ATT_BKV) {
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float2 nmb2 = make_float2(-mb, -mb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 64; i += 2) {
+          const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                 sc2, nmb2);
+          pk[i >> 1] = pack_bf16x2(ex2_approx(a.x), ex2_approx(a.y));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          float e0 = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
+          float e1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -mb));
+          if (i >= valid) e0 = 0.f;
+          if (i + 1 >= valid) e1 = 0.f;
+          pk[i >> 1] = pack_bf16x2(e0, e1);
         }
       }
-      // exchange with the partner thread of this row.  Both partners use the SAME value
-      // max(bf16_up(mx_0), bf16_up(mx_1)) (>= the true row max, within 2^-8 relative): the
-      // reference maximum only has to be consistent and close, not exact (lazy rescaling).
-      {
-        uint32_t u = __float_as_uint(mx);
-        if (mx > 0.f && (u & 0xFFFFu)) u += 0x10000u;  // round up (negative: truncation rounds up)
-        exch[h * 128 + row] = static_cast<uint16_t>(u >> 16);
-      }
-      named_bar_sync(1, 256);
-      const float m_tile = fmaxf(__uint_as_float(static_cast<uint32_t>(exch[row]) << 16),
-                                 __uint_as_float(static_cast<uint32_t>(exch[128 + row]) << 16));
-      // P V of the previous tile must have retired before P is overwritten / O is rescaled
+      // P V of tile j-1 must have retired: frees P buffer b (used by tile j-2) and fixes O
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+        mbar_wait(&o_full[b ^ 1], ((j - 1) >> 1) & 1);
         tc_fence_after();
       }
-      // lazy rescale (every tile has >= 1 valid key, so m_tile is finite)
-      const bool grow = (m_tile - m_ref) * p.scale_log2 > ATT_RESCALE_LOG2;  // true on the first tile
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = grow ? m_tile : m_ref;
-        if (j > 0) {
-          const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
-          // half 0 rescales O[:, 0:32) and the row-sum chunk, half 1 rescales O[:, 32:64)
+      if (any_grow && j > 0) {
+        const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            if (h == 1 && cc == 1) break;
-            const int c = (h == 0) ? (cc == 0 ? 0 : 2) : 1;
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_o + c * 32, r);
-            tmem_ld_wait();
+        for (int c = 0; c < 3; ++c) {  // 64 columns of O, then the chunk holding the row sums
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(t_o + c * 32, t);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(t_o + c * 32, r);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+          tmem_st_32x32b_x32(t_o + c * 32, t);
         }
-        m_ref = m_new;
+        tmem_st_wait();
       }
-      const float mb = m_ref * p.scale_log2;
-      // pass 2: exponentiate my 64 columns, write bf16 P (one 128-byte row of P half h)
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      const float2 nmb2 = make_float2(-mb, -mb);
+      m_ref = m_new;
+      uint8_t* prow = smem + ATT_SP + b * ATT_P_BYTES + row * 128;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_s + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-        if (c * 32 + 32 <= valid) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                   sc2, nmb2);
-            pv[i] = ex2_approx(a.x);
-            pv[i + 1] = ex2_approx(a.y);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = ex2_approx(fmaf(__uint_as_float(r[i]), p.scale_log2, -mb));
-            if (c * 32 + i >= valid) e = 0.f;
-            pv[i] = e;
-          }
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[8 * g + 0], pv[8 * g + 1]);
-          u.y = pack_bf16x2(pv[8 * g + 2], pv[8 * g + 3]);
-          u.z = pack_bf16x2(pv[8 * g + 4], pv[8 * g + 5]);
-          u.w = pack_bf16x2(pv[8 * g + 6], pv[8 * g + 7]);
-          const int chunk = c * 4 + g;  // 16-byte chunk index inside the 128-byte row
-          *reinterpret_cast<uint4*>(sp_row + ((chunk ^ sw) << 4)) = u;
-        }
-      }
+      for (int g = 0; g < 8; ++g)  // 16-byte chunk g of the 128-byte row, 128B-swizzled
+        *reinterpret_cast<uint4*>(prow + ((g ^ sw) << 4)) =
+            make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[b]);
     }
-    // epilogue: O / l — each partner stores 32 of the row's 64 output channels
-    mbar_wait(o_full, (num_kv_tiles - 1) & 1);
+    // epilogue: O / l
+    mbar_wait(&o_full[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
     tc_fence_after();
     const int qrow = q_tile * ATT_BQ + row;
     float inv;
     {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_o + 64, r);  // columns [64, 80) all hold the row sum
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(t_o + 64, t);  // columns [64, 80) all hold the row sum
       tmem_ld_wait();
-      inv = 1.f / __uint_as_float(r[0]);
+      inv = 1.f / __uint_as_float(t[0]);
     }
-    __nv_bfloat16* dst =
-        p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D + h * 32;
-    {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_o + h * 32, r);
+    __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(t_o + c * 32, t);
       tmem_ld_wait();
       if (qrow < p.nq) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+          u.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]) * inv, __uint_as_float(t[8 * g + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]) * inv, __uint_as_float(t[8 * g + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]) * inv, __uint_as_float(t[8 * g + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]) * inv, __uint_as_float(t[8 * g + 7]) * inv);
           d4[g] = u;
         }
       }
@@ -370,13 +333,13 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t
                      const uint64_t* strides_bytes, const uint32_t* box, bool l2_256);
 
 static int make_qkv_map(CUtensorMap* tm, const void* base, long long ld, int heads, int n,
-                        int batch) {
+                        int batch, int box_rows) {
   // element (b, n, h, d) at ((b*n_total + n)*ld + h*64 + d)
   uint64_t dims[4] = {ATT_D, static_cast<uint64_t>(heads), static_cast<uint64_t>(n),
                       static_cast<uint64_t>(batch)};
   uint64_t strides[3] = {ATT_D * 2, static_cast<uint64_t>(ld) * 2,
                          static_cast<uint64_t>(n) * static_cast<uint64_t>(ld) * 2};
-  uint32_t box[4] = {ATT_D, 1, 128, 1};
+  uint32_t box[4] = {ATT_D, 1, static_cast<uint32_t>(box_rows), 1};
   return encode_tmap_bf16(tm, base, 4, dims, strides, box, true);
 }
 
@@ -399,11 +362,11 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
     return CD360_ERR_ALIGN;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   CUtensorMap tq, tk, tv;
-  int rc = make_qkv_map(&tq, q, ldq, heads, nq, batch);
+  int rc = make_qkv_map(&tq, q, ldq, heads, nq, batch, ATT_BQ);
   if (rc != CD360_OK) return rc;
-  rc = make_qkv_map(&tk, k, ldk, heads, nkv, batch);
+  rc = make_qkv_map(&tk, k, ldk, heads, nkv, batch, ATT_BKV);
   if (rc != CD360_OK) return rc;
-  rc = make_qkv_map(&tv, v, ldv, heads, nkv, batch);
+  rc = make_qkv_map(&tv, v, ldv, heads, nkv, batch, ATT_BKV);
   if (rc != CD360_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {

@@ -349,10 +349,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       if (p.ln_stats != nullptr && row_ok) {  // finalise this row's LayerNorm statistics
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + row * p.ln_slabs;
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < p.ln_slabs; ++i) {
-          const float2 t2 = __ldg(st + i);
-          s1 += t2.x;
-          s2 += t2.y;
+        if ((p.ln_slabs & 1) == 0 && p.ln_slabs <= 32) {
+          // all loads in flight at once (a serial L2 round trip per slab would cost microseconds)
+          const float4* st4 = reinterpret_cast<const float4*>(st);
+          const int n4 = p.ln_slabs >> 1;
+          float4 t4[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            t4[i] = (i < n4) ? __ldg(st4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s1 += t4[i].x + t4[i].z;
+            s2 += t4[i].y + t4[i].w;
+          }
+        } else {
+          for (int i = 0; i < p.ln_slabs; ++i) {
+            const float2 t2 = __ldg(st + i);
+            s1 += t2.x;
+            s2 += t2.y;
+          }
         }
         ln_mu = s1 * p.ln_inv_c;
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
@@ -489,7 +504,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               so2 = fmaf(f3.x, f3.x, so2); so2 = fmaf(f3.y, f3.y, so2);
             }
           }
-          if (p.stats_out != nullptr && row_ok)
+          if (p.stats_out != nullptr && row_ok && slab_col(n_blk, s) < p.N_out)
             reinterpret_cast<float2*>(p.stats_out)[row * p.stats_slabs + slab_col(n_blk, s) / 64] =
                 make_float2(so1, so2);
           fence_proxy_async_smem();
