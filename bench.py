@@ -331,13 +331,13 @@ def main():
                      "launches_per_step": gk.get("launches"), "algorithmic_tflop_per_step": gk.get("algorithmic_tflop"),
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
         "roofline_step": {"bound": "tensor", "algorithmic_tflop_per_step": tflop_step,
-                          "achieved": step_tflops / world, "peak": peaks["sustained"], "unit": "TFLOP/s per GPU",
-                          "frac": step_tflops / world / peaks["sustained"],
+                          "achieved": step_tflops, "peak": peaks["sustained"], "unit": "TFLOP/s per GPU",
+                          "frac": step_tflops / peaks["sustained"],
                           "peak_source": peaks["source"] + " sustained (kernel inside a long step)"},
         "kernels": kern, "step0_featurenerf_ms": step0_ms,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": lat_bytes + 4 * (2 * 3 * args.n_img + 4),
                 "d2h_bytes_per_step": lat_bytes, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
         "cuda_graph": not args.no_graph, "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
