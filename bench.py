@@ -160,6 +160,51 @@ def workload_config(args):
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
 
+def make_step(latent, n_img, dev, rank=0, use_graph=True):
+    """The benchmark's workload: SDXL-shaped UNet with random weights, 8 reference views, the fused
+    guided Euler step.  Returns (engine, net, step, x_init, sigmas)."""
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    from custom_diffusion360_b200 import synthetic as S
+
+    cfg = dict(S.SDXL_CFG)
+    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+    with torch.device(dev):
+        engine = DiffusionEngine(
+            network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+            denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+                "num_idx": 1000,
+                "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+                "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"},
+                "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"}}},
+            sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+                "num_steps": 50, "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"},
+                "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef",
+                                  "params": {"scale": 7.5, "scale_im": 3.5}}}})
+    engine = engine.to(dev).eval()
+    net = engine.model.diffusion_model
+    S.init_random_weights_(net, seed=0)
+    net.register_references(S.make_references(net, latent, 8, dev, seed=rank))
+    engine.set_reference_choices(list(range(8)))
+    net.packed()
+    for m in net.modules():  # build the bf16 operand copies, then drop the fp32 masters' grads etc.
+        if hasattr(m, "packed") and m is not net:
+            try:
+                m.packed()
+            except StopIteration:
+                pass
+    cond, uc = S.make_conditioning(cfg, n_img, dev, seed=rank)
+    poses = [S.lookat_cameras(8, seed=rank * 100 + i, target_azimuth=0.35 + 0.5 * i) for i in range(n_img)]
+    shape = (4, latent, latent)
+    step = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, cond, uc, pose=poses, n_img=n_img,
+                           latent_shape=shape, use_graph=use_graph)
+    sigmas = engine.sampler.discretization(50, device="cpu")
+    g = torch.Generator(device=dev).manual_seed(30 + rank)  # sample.py seeds 30 (sample.py:213)
+    x_init = torch.randn(n_img, *shape, device=dev, generator=g) * float(torch.sqrt(1.0 + sigmas[0] ** 2))
+
+    return engine, net, step, x_init, sigmas
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -191,40 +236,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    cfg = dict(S.SDXL_CFG)
-    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
-    with torch.device(dev):
-        engine = DiffusionEngine(
-            network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
-            denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
-                "num_idx": 1000,
-                "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
-                "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"},
-                "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"}}},
-            sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
-                "num_steps": 50, "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"},
-                "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef",
-                                  "params": {"scale": 7.5, "scale_im": 3.5}}}})
-    engine = engine.to(dev).eval()
-    net = engine.model.diffusion_model
-    S.init_random_weights_(net, seed=0)
-    net.register_references(S.make_references(net, args.latent, 8, dev, seed=rank))
-    engine.set_reference_choices(list(range(8)))
-    net.packed()
-    for m in net.modules():  # build the bf16 operand copies, then drop the fp32 masters' grads etc.
-        if hasattr(m, "packed") and m is not net:
-            try:
-                m.packed()
-            except StopIteration:
-                pass
-    cond, uc = S.make_conditioning(cfg, args.n_img, dev, seed=rank)
-    poses = [S.lookat_cameras(8, seed=rank * 100 + i, target_azimuth=0.35 + 0.5 * i) for i in range(args.n_img)]
-    shape = (4, args.latent, args.latent)
-    step = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, cond, uc, pose=poses, n_img=args.n_img,
-                           latent_shape=shape, use_graph=not args.no_graph)
-    sigmas = engine.sampler.discretization(50, device="cpu")
-    g = torch.Generator(device=dev).manual_seed(30 + rank)  # sample.py seeds 30 (sample.py:213)
-    x_init = torch.randn(args.n_img, *shape, device=dev, generator=g) * float(torch.sqrt(1.0 + sigmas[0] ** 2))
+    engine, net, step, x_init, sigmas = make_step(args.latent, args.n_img, dev, rank, not args.no_graph)
     x = x_init.clone()
     nsig = len(sigmas) - 1
 

@@ -107,6 +107,7 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   const int batch = blockIdx.z;
   const int nt = (p.nkv + ATT_BKV - 1) / ATT_BKV;
 
+  CD360_TL(1);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {
@@ -390,3 +391,5 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
+
+CD360_TL_SETTER(attention)

@@ -398,4 +398,48 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
     if (e__ != cudaSuccess) return CD360_ERR_LAUNCH;           \
   } while (0)
 
+
+// ---- kernel timeline (tools/step_timeline.py) ---------------------------------------------------
+// Compiled only with -DCD360_TIMELINE into a private profiling library: every kernel records the
+// earliest CTA entry and the latest thread-0 exit (ns, %globaltimer) into a ring keyed by %gridid,
+// which gives per-kernel durations and inter-kernel gaps INSIDE a CUDA-graph replay (no nsys in
+// this image).  In the product build CD360_TL() expands to nothing.
+#ifdef CD360_TIMELINE
+struct TlRec {
+  unsigned long long start, end;
+  unsigned int kind, ctas;
+};
+constexpr unsigned int kTlRing = 8192;
+static __device__ TlRec* g_tl = nullptr;
+struct TlScope {
+  TlRec* r;
+  __device__ __forceinline__ explicit TlScope(int kind) : r(nullptr) {
+    if (g_tl != nullptr && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+      unsigned long long gid, now;
+      asm volatile("mov.u64 %0, %%gridid;" : "=l"(gid));
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      r = &g_tl[gid & (kTlRing - 1)];
+      atomicMin(&r->start, now);
+      r->kind = static_cast<unsigned int>(kind);
+      atomicAdd(&r->ctas, 1u);
+    }
+  }
+  __device__ __forceinline__ ~TlScope() {
+    if (r != nullptr) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      atomicMax(&r->end, now);
+    }
+  }
+};
+#define CD360_TL(kind) ::cd360::TlScope tl_scope_(kind)
+#define CD360_TL_SETTER(file)                                                          \
+  extern "C" int cd360_tl_set_##file(void* ring) {                                     \
+    return cudaMemcpyToSymbol(::cd360::g_tl, &ring, sizeof(ring)) == cudaSuccess ? 0 : -1; \
+  }
+#else
+#define CD360_TL(kind) do {} while (0)
+#define CD360_TL_SETTER(file)
+#endif
+
 }  // namespace cd360

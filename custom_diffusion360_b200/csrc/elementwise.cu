@@ -9,6 +9,7 @@ namespace cd360 {
 // timestep_embedding (sgm/modules/diffusionmodules/util.py:206-230): [cos(t f_k) | sin(t f_k)]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out,
                                           int batch, int dim) {
+  CD360_TL(6);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const int half = dim / 2;
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ add,
                     float* __restrict__ out, int batch, int n, int k, int act_in, int act_out) {
+  CD360_TL(5);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_x[];  // [SL_BCHUNK][k]
@@ -91,6 +93,7 @@ small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       __nv_bfloat16* __restrict__ out, int batch, int src_batch,
                                       int cin, int h, int w, int kpad) {
+  CD360_TL(7);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -120,6 +123,7 @@ __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, const float* 
 __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x,
                                     __nv_bfloat16* __restrict__ out, int batch, int h, int w,
                                     int c) {
+  CD360_TL(8);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const int ho = h / 2, wo = w / 2, cv = c / 8;
@@ -144,6 +148,7 @@ __global__ void im2col3x3_s2_kernel(const __nv_bfloat16* __restrict__ x,
 // nearest x2 (Upsample.forward, openaimodel.py:161), NHWC, 8 channels per thread
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
                                   __nv_bfloat16* __restrict__ out, int batch, int h, int w, int c) {
+  CD360_TL(9);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const int cv = c / 8;
@@ -162,6 +167,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x,
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                      long long n) {
+  CD360_TL(10);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -169,6 +175,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16*
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
                                      long long n) {
+  CD360_TL(11);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -178,6 +185,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float*
 // [B, hw, C] (bf16 or fp32) -> NCHW fp32 [B, C, hw]
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
                                     float* __restrict__ out, int batch, int hw, int c) {
+  CD360_TL(12);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -194,6 +202,7 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int x_is_fp32,
 // NCHW fp32 [B, C, hw] -> [B, hw, C] bf16 (module inputs at the sgm boundary)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                     int batch, int hw, int c) {
+  CD360_TL(13);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -210,6 +219,7 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const float* __restrict_
                                  float* __restrict__ denoised_out, int n_img, int g, int hw,
                                  float sigma_q, float sigma, float sigma_next, float scale,
                                  float scale_im, const float* __restrict__ sig_dev) {
+  CD360_TL(14);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   if (sig_dev != nullptr) {  // (sigma_q, sigma, sigma_next) live in device memory: graph-replayable
@@ -398,3 +408,5 @@ extern "C" const char* cd360_strerror(int code) {
     default: return "unknown error";
   }
 }
+
+CD360_TL_SETTER(elementwise)

@@ -32,6 +32,32 @@
 
 #include "cd360_common.cuh"
 
+// Phase tracing for tools/gemm_trace.py (never compiled into libcd360.so): per-CTA clock stamps.
+#ifdef CD360_GEMM_TRACE
+__device__ unsigned long long* g_cd360_trace = nullptr;
+__device__ __forceinline__ unsigned long long cd360_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CD360_TRACE(slot)                                                              \
+  do {                                                                                 \
+    if (g_cd360_trace != nullptr) g_cd360_trace[blockIdx.x * 32 + (slot)] = cd360_gtimer(); \
+  } while (0)
+// SM-clock stamps of epilogue warp 4 inside the LAST tile (slots 16..31)
+#define CD360_TRACE_CLK(cond, slot)                                                    \
+  do {                                                                                 \
+    if ((cond) && g_cd360_trace != nullptr)                                            \
+      g_cd360_trace[blockIdx.x * 32 + (slot)] = static_cast<unsigned long long>(clock64()); \
+  } while (0)
+extern "C" int cd360_gemm_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_cd360_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define CD360_TRACE(slot) do {} while (0)
+#define CD360_TRACE_CLK(cond, slot) do {} while (0)
+#endif
+
 namespace cd360 {
 
 constexpr int BM = 128;  // rows per CTA
@@ -76,10 +102,13 @@ struct GemmSmem {
   static constexpr int B_TILE_BYTES = BNC * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;       // out[2] | res[2] slabs
-  static constexpr int BAR_OFFSET = EPI_OFFSET + 4 * SLAB_BYTES;
+  static constexpr int BIAS_OFFSET = EPI_OFFSET + 4 * SLAB_BYTES;  // float[2][BN] tile bias
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * BN * 4;
   // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] res_full[2] + tmem ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 6) * 8 + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024 B alignment
+  // no static __shared__ in the kernel: the dynamic window starts at offset 0 of the CTA's shared
+  // memory and is 1024 B aligned (checked at kernel entry), so no alignment slack is reserved
+  static constexpr int DYN_BYTES = TOTAL;
   static_assert(DYN_BYTES <= 227 * 1024, "smem budget exceeded");
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep 1024 B alignment");
 };
@@ -101,6 +130,20 @@ __device__ __forceinline__ void load_bias32(float (&v)[32], const float* __restr
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < nvalid) v[j] += __ldg(p + col0 + j);
+  }
+}
+
+// tile bias staged in shared memory by the epilogue warps while the main loop runs (a global
+// load per 32-column chunk put an L2 round trip on the critical path of every tile)
+__device__ __forceinline__ void add_bias32_smem(float (&v)[32], const float* sb) {
+  const float4* p4 = reinterpret_cast<const float4*>(sb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 b = p4[j];
+    v[4 * j + 0] += b.x;
+    v[4 * j + 1] += b.y;
+    v[4 * j + 2] += b.z;
+    v[4 * j + 3] += b.w;
   }
 }
 
@@ -167,9 +210,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                          const __grid_constant__ CUtensorMap tmOut,
                          const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
   using L = GemmSmem<BN, STAGES, CG>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzled TMA / UMMA tiles need 1024 B alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -187,7 +229,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int nkb = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
+  CD360_TL(0);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
+  if (threadIdx.x == 0) CD360_TRACE(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
@@ -222,7 +266,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) CD360_TRACE(1);
   pdl_wait();  // nothing above touches global memory written by earlier kernels
+  if (threadIdx.x == 0) CD360_TRACE(2);
 
   if (warp == 0 && lane == 0) {
     // ================================ TMA producer ================================
@@ -267,6 +313,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
         if (CG == 2) tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0);
         else tma_load_2d(sb, &tmB, fb, kb * BK, n0);
+        if (tile == unit && kb == 0) CD360_TRACE(3);
+        if (tile + num_units >= num_tiles && kb == nkb - 1) CD360_TRACE(4);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -288,6 +336,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (t == 0 && kb == 0) CD360_TRACE(5);
+        if (t == 0 && kb == 1) CD360_TRACE(6);
         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
@@ -303,6 +353,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (kb == nkb - 1) {
           if (CG == 2) umma_commit_2sm(&tmem_full[buf], 0x3);
           else umma_commit(&tmem_full[buf]);
+          if (tile + num_units >= num_tiles) CD360_TRACE(7);
         }
         if (++stage == STAGES) {
           stage = 0;
@@ -372,8 +423,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         ln_mu = s1 * p.ln_inv_c;
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
+      const float* s_bias = reinterpret_cast<const float*>(smem + L::BIAS_OFFSET) + buf * BN;
+      if (p.bias != nullptr) {  // columns beyond N read as 0; double buffered by tile parity
+        for (int e = (warp - 4) * 32 + lane; e < BN; e += kEpiWarps * 32)
+          reinterpret_cast<float*>(smem + L::BIAS_OFFSET)[buf * BN + e] =
+              (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
+        named_bar_sync(5, kEpiWarps * 32);
+      }
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) {
+        if (t == 0) CD360_TRACE(8);
+        if (tile + num_units >= num_tiles) CD360_TRACE(9);
+      }
+      const bool trace_me = warp == 4 && lane == 0 && tile + num_units >= num_tiles;
+      (void)trace_me;
+      CD360_TRACE_CLK(trace_me, 16);
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       const float* rb = nullptr;
@@ -404,7 +469,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
                   for (int j = 0; j < 32; ++j) vv[j] = fmaf(-ln_mu, cs[j], vv[j]) * ln_rstd;
                 }
-                if (p.bias != nullptr) load_bias32(vv, p.bias, col0, nvalid);
+                if (p.bias != nullptr) add_bias32_smem(vv, s_bias + (c0 + h) * 32);
                 if (rb != nullptr) load_bias32(vv, rb, col0, nvalid);
               }
               if (p.act == CD360_ACT_SILU) {
@@ -442,13 +507,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                 }
               }
               if (p.bias != nullptr) {
-                load_bias32(xv, p.bias, n0 + (c0 + h) * 32, 32);
-                load_bias32(gv, p.bias, n0 + BN / 2 + (c0 + h) * 32, 32);
+                add_bias32_smem(xv, s_bias + (c0 + h) * 32);
+                add_bias32_smem(gv, s_bias + BN / 2 + (c0 + h) * 32);
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[h * 32 + j] = xv[j] * gelu_erf_f(gv[j]);
             }
           }
+          CD360_TRACE_CLK(trace_me && s < 2, 17 + 5 * s);
           if (s == n_slabs - 1) {  // all TMEM reads of this tile done: hand the buffer back
             tc_fence_before();
             __syncwarp();
@@ -471,9 +537,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               v[8 * c + 6] += f3.x; v[8 * c + 7] += f3.y;
             }
           }
+          CD360_TRACE_CLK(trace_me && s < 2, 18 + 5 * s);
           // the previous TMA store of this half must have finished reading out_buf
           if (half_leader) tma_store_wait_read();
+          CD360_TRACE_CLK(trace_me && s < 2, 19 + 5 * s);
           named_bar_sync(bar_id, 128);  // res_buf fully consumed, out_buf reusable
+          CD360_TRACE_CLK(trace_me && s < 2, 20 + 5 * s);
           if (use_res && half_leader) {  // prefetch the next residual slab (this or next tile)
             int nt = tile, ns = s + 1;
             if (ns == n_slabs) { nt = tile + num_units; ns = 0; }
@@ -513,6 +582,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             tma_store_2d(&tmOut, out_buf, slab_col(n_blk, s), row0);
             tma_store_commit();
           }
+          CD360_TRACE_CLK(trace_me && s < 2, 21 + 5 * s);
         }
       } else {
         // ---------------- direct path ----------------
@@ -531,7 +601,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              if (p.bias != nullptr) load_bias32(v, p.bias, col0, nvalid);
+              if (p.bias != nullptr) add_bias32_smem(v, s_bias + c * 32);
               if (rb != nullptr) load_bias32(v, rb, col0, nvalid);
               if (p.act == CD360_ACT_SILU) {
 #pragma unroll
@@ -558,8 +628,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                 g[j] = __uint_as_float(rg[j]);
               }
               if (p.bias != nullptr) {
-                load_bias32(v, p.bias, n0 + c * 32, 32);
-                load_bias32(g, p.bias, n0 + BN / 2 + c * 32, 32);
+                add_bias32_smem(v, s_bias + c * 32);
+                add_bias32_smem(g, s_bias + BN / 2 + c * 32);
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = v[j] * gelu_erf_f(g[j]);
@@ -575,7 +645,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
     }
-    if (p.epi_tma && half_leader) tma_store_wait_all();  // smem must outlive the bulk stores
+    if (warp == 4 && lane == 0) CD360_TRACE(10);
+    // smem must outlive the bulk stores' READS; the writes are complete at grid completion
+    if (p.epi_tma && half_leader) tma_store_wait_read();
+    if (warp == 4 && lane == 0) CD360_TRACE(11);
+    CD360_TRACE_CLK(warp == 4 && lane == 0, 27);
   }
 
   // ---- teardown ----
@@ -586,6 +660,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) CD360_TRACE(12);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -841,3 +916,5 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     return launch_gemm<256, 5, 2>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
   return launch_gemm<128, 5, 1>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
 }
+
+CD360_TL_SETTER(gemm)

@@ -89,6 +89,7 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
                    float b_nv, __nv_bfloat16* __restrict__ pe, int* __restrict__ gidx,
                    float* __restrict__ gwgt, float* __restrict__ vlogit, int nb, int n, int res,
                    int d, int kpe) {
+  CD360_TL(16);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_w[];  // w_nv_geo[198] | per-view origin logit [n]
@@ -205,6 +206,7 @@ nerf_combine_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
                     const float* __restrict__ gwgt, const float* __restrict__ vlogit,
                     __nv_bfloat16* __restrict__ s_out, float* __restrict__ view_softmax, int nb,
                     int n, int hw, int d, int c) {
+  CD360_TL(17);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -288,6 +290,7 @@ nerf_volrender_kernel(const __nv_bfloat16* __restrict__ feats, const float* __re
                       const float* __restrict__ dists, __nv_bfloat16* __restrict__ rendered,
                       float* __restrict__ fg, float* __restrict__ alphas, float* __restrict__ rgb,
                       int nb, int hw, int d, int c) {
+  CD360_TL(18);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const long long wid = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -406,3 +409,5 @@ extern "C" int cd360_nerf_volrender(const void* feats, const float* raw, const f
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
+
+CD360_TL_SETTER(nerf)

@@ -12,7 +12,7 @@
 
 namespace cd360 {
 
-constexpr int GN_MAX_CHUNKS = 32;
+constexpr int GN_MAX_CHUNKS = 128;
 constexpr int GN_GROUPS = 32;
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -21,11 +21,14 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's rows and the group's channels
-__global__ void __launch_bounds__(1024)
+// partial[b][chunk][g][2] = (sum, sumsq) over the chunk's rows and the group's channels.
+// Thread (rl, vec) walks rows rl, rl + rlanes, ... of the chunk with FOUR 16-byte loads in flight
+// (a single dependent load per thread left the kernel latency-bound at ~1.5 TB/s).
+__global__ void __launch_bounds__(512, 2)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
                        const __nv_bfloat16* __restrict__ x1, int c1, float* __restrict__ partial,
                        int hw, int rows_per_chunk, int nvec, int rlanes) {
+  CD360_TL(2);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   // per-(row lane, channel) partial sums, reduced in a FIXED order below: results are bit-exact
@@ -44,30 +47,49 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
     if (ch0 < c0) { src = x0; ld = c0; ch = ch0; } else { src = x1; ld = c1; ch = ch0 - c0; }
     const int r_begin = chunk * rows_per_chunk;
     const int r_end = min(hw, r_begin + rows_per_chunk);
+    src += static_cast<long long>(b) * hw * ld + ch;
     float s[8], ss[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-    for (int r = r_begin + rl; r < r_end; r += rlanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(
-          src + (static_cast<long long>(b) * hw + r) * ld + ch));
-      float f[8];
-      unpack8(u, f);
+    for (int r = r_begin + rl; r < r_end; r += 4 * rlanes) {
+      uint4 u[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+      for (int j = 0; j < 4; ++j) {
+        const int rj = r + j * rlanes;
+        u[j] = rj < r_end ? __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(rj) * ld))
+                          : make_uint4(0u, 0u, 0u, 0u);  // zeros add nothing to either moment
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(u[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+      }
     }
-    float* ps = s_part + static_cast<size_t>(rl) * ctot + ch0;
-    float* pss = s_part + static_cast<size_t>(rlanes + rl) * ctot + ch0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ps[i] = s[i]; pss[i] = ss[i]; }
+    float4* ps = reinterpret_cast<float4*>(s_part + static_cast<size_t>(rl) * ctot + ch0);
+    float4* pss = reinterpret_cast<float4*>(s_part + static_cast<size_t>(rlanes + rl) * ctot + ch0);
+    ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+    ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+    pss[0] = make_float4(ss[0], ss[1], ss[2], ss[3]);
+    pss[1] = make_float4(ss[4], ss[5], ss[6], ss[7]);
   }
   __syncthreads();
-  if (threadIdx.x < GN_GROUPS * 2) {
-    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+  // 64 outputs (group, which), four threads each; fixed summation order
+  const int sub = threadIdx.x & 3;
+  for (int o = threadIdx.x >> 2; o < GN_GROUPS * 2; o += blockDim.x >> 2) {
+    const int g = o >> 1, which = o & 1;
     const float* base = s_part + static_cast<size_t>(which) * rlanes * ctot + g * cg;
     float acc = 0.f;
-    for (int r = 0; r < rlanes; ++r)
-      for (int c = 0; c < cg; ++c) acc += base[static_cast<size_t>(r) * ctot + c];
-    partial[(static_cast<long long>(b) * gridDim.x + chunk) * GN_GROUPS * 2 + threadIdx.x] = acc;
+    const int n = rlanes * cg;
+    for (int i = sub; i < n; i += 4) {
+      const int rr = i / cg, c = i - rr * cg;
+      acc += base[static_cast<size_t>(rr) * ctot + c];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (sub == 0)
+      partial[(static_cast<long long>(b) * gridDim.x + chunk) * GN_GROUPS * 2 + o] = acc;
   }
 }
 
@@ -78,6 +100,7 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        __nv_bfloat16* __restrict__ out, int hw, int rows_per_block, float eps,
                        int apply_silu) {
+  CD360_TL(3);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float s_dyn[];  // scale[ctot] | shift[ctot]
@@ -87,19 +110,29 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
   const int cg = ctot / GN_GROUPS;
   float* s_scale = s_dyn;
   float* s_shift = s_dyn + ctot;
-  if (threadIdx.x < GN_GROUPS) {
+  {  // finalise the moments: 8 threads per group, fixed order (blockDim.x == 256)
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     double su = 0.0, sq = 0.0;
-    const float* pp = partial + static_cast<long long>(b) * nchunks * GN_GROUPS * 2;
-    for (int c = 0; c < nchunks; ++c) {
-      su += pp[(c * GN_GROUPS + threadIdx.x) * 2];
-      sq += pp[(c * GN_GROUPS + threadIdx.x) * 2 + 1];
+    const float2* pp = reinterpret_cast<const float2*>(partial) +
+                       static_cast<long long>(b) * nchunks * GN_GROUPS;
+    for (int c = sub; c < nchunks; c += 8) {
+      const float2 t = __ldg(pp + c * GN_GROUPS + g);
+      su += t.x;
+      sq += t.y;
     }
-    const double n = static_cast<double>(hw) * cg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      su += __shfl_xor_sync(0xffffffffu, su, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (sub == 0) {
+      const double n = static_cast<double>(hw) * cg;
+      const double mean = su / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < ctot; c += blockDim.x) {
@@ -112,26 +145,55 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
   const int nvec = ctot / 8;
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(hw, r_begin + rows_per_block);
-  const long long total = static_cast<long long>(r_end - r_begin) * nvec;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r_begin + static_cast<int>(i / nvec);
-    const int ch0 = static_cast<int>(i % nvec) * 8;
-    const long long grow = static_cast<long long>(b) * hw + r;
-    const __nv_bfloat16* src = (ch0 < c0) ? (x0 + grow * c0 + ch0) : (x1 + grow * c1 + (ch0 - c0));
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
-    float f[8];
-    unpack8(u, f);
+  // item i of this block = (row r_begin + i / nvec, vector i % nvec); threads stride the items by
+  // blockDim.x and track (row, vec) incrementally (no division in the loop), 4 loads in flight
+  const int dr = static_cast<int>(blockDim.x) / nvec, dv = static_cast<int>(blockDim.x) % nvec;
+  int r = r_begin + static_cast<int>(threadIdx.x) / nvec;
+  int v = static_cast<int>(threadIdx.x) % nvec;
+  const long long img = static_cast<long long>(b) * hw;
+  while (r < r_end) {
+    uint4 u[4];
+    int rr[4], vv[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float y = fmaf(f[k], s_scale[ch0 + k], s_shift[ch0 + k]);
-      f[k] = apply_silu ? silu_f(y) : y;
+    for (int j = 0; j < 4; ++j) {
+      rr[j] = r;
+      vv[j] = v;
+      if (r < r_end) {
+        const int ch0 = v * 8;
+        const long long grow = img + r;
+        const __nv_bfloat16* src =
+            (ch0 < c0) ? (x0 + grow * c0 + ch0) : (x1 + grow * c1 + (ch0 - c0));
+        u[j] = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+      r += dr;
+      v += dv;
+      if (v >= nvec) { v -= nvec; ++r; }
     }
-    uint4 o;
-    o.x = pack_bf16x2(f[0], f[1]);
-    o.y = pack_bf16x2(f[2], f[3]);
-    o.z = pack_bf16x2(f[4], f[5]);
-    o.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(out + grow * ctot + ch0) = o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rr[j] < r_end) {
+        const int ch0 = vv[j] * 8;
+        float f[8];
+        unpack8(u[j], f);
+        const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + ch0);
+        const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + ch0 + 4);
+        const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + ch0);
+        const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + ch0 + 4);
+        const float scs[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float shs[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float y = fmaf(f[k], scs[k], shs[k]);
+          f[k] = apply_silu ? silu_f(y) : y;
+        }
+        uint4 o;
+        o.x = pack_bf16x2(f[0], f[1]);
+        o.y = pack_bf16x2(f[2], f[3]);
+        o.z = pack_bf16x2(f[4], f[5]);
+        o.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(out + (img + rr[j]) * ctot + ch0) = o;
+      }
+    }
   }
 }
 
@@ -141,6 +203,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, int rows, int c,
                  float eps) {
+  CD360_TL(4);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -203,9 +266,9 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 }
 
 static int gn_chunks(int batch, int hw) {
-  int chunks = (4 * kNumSMsB200 + batch - 1) / batch;
+  int chunks = (2 * kNumSMsB200) / batch;  // two resident CTAs per SM, one wave
   if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  const int max_by_rows = (hw + 15) / 16;
+  const int max_by_rows = (hw + 7) / 8;
   if (chunks > max_by_rows) chunks = max_by_rows;
   if (chunks < 1) chunks = 1;
   return chunks;
@@ -230,22 +293,25 @@ extern "C" int cd360_groupnorm_silu_bf16(const void* x0, int32_t c0, const void*
   const int ctot = c0 + c1;
   if ((c0 & 7) || (c1 & 7) || (ctot % GN_GROUPS) != 0) return CD360_ERR_SHAPE;
   const int nvec = ctot / 8;
-  if (nvec > 1024) return CD360_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x0) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
       (x1 && (reinterpret_cast<uintptr_t>(x1) & 15)))
     return CD360_ERR_ALIGN;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const int chunks = gn_chunks(batch, hw);
   const int rows_per_chunk = (hw + chunks - 1) / chunks;
-  int rlanes = nvec <= 256 ? 256 / nvec : 1;
+  if (nvec > 512) return CD360_ERR_SHAPE;
+  int rlanes = 512 / nvec;
+  if (rlanes > rows_per_chunk) rlanes = rows_per_chunk;
   if (rlanes < 1) rlanes = 1;
-  const int threads = ((nvec * rlanes + 31) / 32) * 32;
-  const size_t stats_smem = static_cast<size_t>(2) * rlanes * ctot * sizeof(float);  // <= 20 KiB
+  int threads = ((nvec * rlanes + 31) / 32) * 32;
+  if (threads < 256) threads = 256;
+  const size_t stats_smem = static_cast<size_t>(2) * rlanes * ctot * sizeof(float);  // <= 40 KiB
   launch_ex(groupnorm_stats_kernel, dim3(chunks, batch), dim3(threads), stats_smem, stream, 1,
       reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1),
       c1, workspace, hw, rows_per_chunk, nvec, rlanes);
   CD360_CHECK_LAUNCH();
-  int row_blocks = (8 * kNumSMsB200 + batch - 1) / batch;
+  int row_blocks = (4 * kNumSMsB200) / batch;  // four resident CTAs per SM, one wave
+  if (row_blocks < 1) row_blocks = 1;
   if (row_blocks > hw) row_blocks = hw;
   const int rows_per_block = (hw + row_blocks - 1) / row_blocks;
   row_blocks = (hw + rows_per_block - 1) / rows_per_block;
@@ -274,3 +340,5 @@ extern "C" int cd360_layernorm_bf16(const void* x, const float* gamma, const flo
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }
+
+CD360_TL_SETTER(norm)
