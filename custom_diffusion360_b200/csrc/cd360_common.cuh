@@ -131,6 +131,10 @@ __device__ __forceinline__ void tma_store_commit() {
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// ... all but the most recent one (double-buffered staging)
+__device__ __forceinline__ void tma_store_wait_read_1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 // ... and have been written to global memory
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -335,13 +339,20 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// MUFU.RCP (1 ulp); `__frcp_rn` and `/` expand to the IEEE-rounded sequence (Newton steps plus a
+// slow-path branch), which made the SiLU / GELU epilogues several times longer than the main loop
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx_f(1.0f + __expf(-x)); }
 // erf via Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 output rounding):
 // 2 MUFU + ~10 FMA-pipe instructions instead of libdevice erff's ~40 — the GEGLU epilogue has to
 // keep up with a 128x256x640 main loop.
 __device__ __forceinline__ float erf_as_f(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx_f(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

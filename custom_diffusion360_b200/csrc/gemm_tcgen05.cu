@@ -65,7 +65,7 @@ constexpr int BK = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int SLAB_BYTES = BM * 64 * 2;     // 128 rows x 64 bf16 = 16 KiB epilogue staging tile
+constexpr int WSLAB_BYTES = 32 * 64 * 2;    // 32 rows x 64 bf16 = 4 KiB: one epilogue warp's staging slab
 
 struct GemmKParams {
   int M, N, N_out;
@@ -101,11 +101,11 @@ struct GemmSmem {
   static constexpr int BNC = BN / CG;  // W rows this CTA stages
   static constexpr int B_TILE_BYTES = BNC * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;       // out[2] | res[2] slabs
-  static constexpr int BIAS_OFFSET = EPI_OFFSET + 4 * SLAB_BYTES;  // float[2][BN] tile bias
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;       // [8 epilogue warps][2] 4 KiB slabs
+  static constexpr int BIAS_OFFSET = EPI_OFFSET + kEpiWarps * 2 * WSLAB_BYTES;  // float[2][BN] tile bias
   static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * BN * 4;
-  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] res_full[2] + tmem ptr
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 6) * 8 + 16;
+  // full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] res_full[8 warps][2] + tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4 + 2 * kEpiWarps) * 8 + 16;
   // no static __shared__ in the kernel: the dynamic window starts at offset 0 of the CTA's shared
   // memory and is 1024 B aligned (checked at kernel entry), so no alignment slack is reserved
   static constexpr int DYN_BYTES = TOTAL;
@@ -217,7 +217,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,8 +249,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs)
-      mbar_init(&res_full[b], 1);
     }
+    for (int b = 0; b < 2 * kEpiWarps; ++b) mbar_init(&res_full[b], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -366,11 +366,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int q = warp & 3;               // TMEM lane quarter this warp may access (warp % 4)
     const int half = (warp - 4) >> 2;     // which half of the tile's columns
     const int row_in_tile = q * 32 + lane;
-    const bool half_leader = (q == 0) && (lane == 0);
-    uint8_t* out_buf = smem + L::EPI_OFFSET + half * SLAB_BYTES;
-    uint8_t* res_buf = smem + L::EPI_OFFSET + (2 + half) * SLAB_BYTES;
-    const uint32_t bar_id = 1 + 2 * half;  // named barriers (1,2) / (3,4) for the two halves
-    const int sw = row_in_tile & 7;
+    // Each warp stages ITS 32 rows x 64 columns in its own two 4 KiB buffers and issues its own TMA
+    // stores / residual loads (box 64 x 32): no cross-warp barrier anywhere in the slab loop.  The
+    // residual slab is TMA-loaded into the buffer, added in registers, and the result is written
+    // back IN PLACE and stored from there; the two buffers alternate slab by slab.
+    uint8_t* wbuf = smem + L::EPI_OFFSET + (warp - 4) * 2 * WSLAB_BYTES;
+    uint64_t* wres = res_full + (warp - 4) * 2;
+    const int sw = lane & 7;
     const bool use_res = p.epi_tma && p.residual != nullptr;
     // out slabs this half produces per tile, and the slab's first OUTPUT column inside the tile
     constexpr int SLABS = BN / 128;                 // plain: 64-col slabs per half
@@ -379,12 +381,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     auto slab_col = [&](int n_blk, int s) {         // first output column of slab s of this half
       return n_blk * out_tile_cols + (half * n_slabs + s) * 64;
     };
-    uint32_t res_cnt = 0;  // residual slabs consumed so far (parity of res_full[half])
-    if (use_res && half_leader && unit < num_tiles) {
+    uint32_t slab_cnt = 0;  // slabs this warp has processed: buffer = cnt & 1, parity = (cnt >> 1) & 1
+    if (use_res && lane == 0 && unit < num_tiles) {
       const int m_blk = unit % p.num_m_blocks, n_blk = unit / p.num_m_blocks;
-      mbar_arrive_expect_tx(&res_full[half], SLAB_BYTES);
-      tma_load_2d(res_buf, &tmRes, &res_full[half], slab_col(n_blk, 0),
-                  (m_blk * CG + static_cast<int>(rank)) * BM);
+      mbar_arrive_expect_tx(&wres[0], WSLAB_BYTES);
+      tma_load_2d(wbuf, &tmRes, &wres[0], slab_col(n_blk, 0),
+                  (m_blk * CG + static_cast<int>(rank)) * BM + q * 32);
     }
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
@@ -450,14 +452,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           float v[64];
           if (!p.geglu) {
             const int c0 = (half * SLABS + s) * 2;  // first 32-col chunk of this slab
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(taddr + c0 * 32, r0);
+            tmem_ld_32x32b_x32(taddr + (c0 + 1) * 32, r1);
+            tmem_ld_wait();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              uint32_t r[32];
-              tmem_ld_32x32b_x32(taddr + (c0 + h) * 32, r);
-              tmem_ld_wait();
               float vv[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(r[j]);
+              for (int j = 0; j < 32; ++j) vv[j] = __uint_as_float(h == 0 ? r0[j] : r1[j]);
               const int col0 = n0 + (c0 + h) * 32;
               const int nvalid = max(0, min(32, p.N - col0));
               if (nvalid > 0) {
@@ -523,37 +526,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               else mbar_arrive(&tmem_empty[buf]);
             }
           }
+          uint8_t* sbuf = wbuf + (slab_cnt & 1u) * WSLAB_BYTES;
+          uint8_t* brow = sbuf + lane * 128;
           if (use_res) {
-            mbar_wait(&res_full[half], res_cnt & 1);
-            ++res_cnt;
-            const uint8_t* rrow = res_buf + row_in_tile * 128;
+            mbar_wait(&wres[slab_cnt & 1u], (slab_cnt >> 1) & 1u);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((c ^ sw) << 4));
+              const uint4 u = *reinterpret_cast<const uint4*>(brow + ((c ^ sw) << 4));
               float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
                      f3 = unpack_bf16x2(u.w);
               v[8 * c + 0] += f0.x; v[8 * c + 1] += f0.y; v[8 * c + 2] += f1.x;
               v[8 * c + 3] += f1.y; v[8 * c + 4] += f2.x; v[8 * c + 5] += f2.y;
               v[8 * c + 6] += f3.x; v[8 * c + 7] += f3.y;
             }
+          } else {
+            // the store issued from this buffer two slabs ago must have finished reading it
+            if (lane == 0) tma_store_wait_read_1();
+            __syncwarp();
           }
           CD360_TRACE_CLK(trace_me && s < 2, 18 + 5 * s);
-          // the previous TMA store of this half must have finished reading out_buf
-          if (half_leader) tma_store_wait_read();
-          CD360_TRACE_CLK(trace_me && s < 2, 19 + 5 * s);
-          named_bar_sync(bar_id, 128);  // res_buf fully consumed, out_buf reusable
-          CD360_TRACE_CLK(trace_me && s < 2, 20 + 5 * s);
-          if (use_res && half_leader) {  // prefetch the next residual slab (this or next tile)
-            int nt = tile, ns = s + 1;
-            if (ns == n_slabs) { nt = tile + num_units; ns = 0; }
-            if (nt < num_tiles) {
-              const int nm = nt % p.num_m_blocks, nn = nt / p.num_m_blocks;
-              mbar_arrive_expect_tx(&res_full[half], SLAB_BYTES);
-              tma_load_2d(res_buf, &tmRes, &res_full[half], slab_col(nn, ns),
-                          (nm * CG + static_cast<int>(rank)) * BM);
-            }
-          }
-          uint8_t* orow = out_buf + row_in_tile * 128;
           float so1 = 0.f, so2 = 0.f;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -562,7 +553,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             u.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
             u.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
             u.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-            *reinterpret_cast<uint4*>(orow + ((c ^ sw) << 4)) = u;
+            *reinterpret_cast<uint4*>(brow + ((c ^ sw) << 4)) = u;
             if (p.stats_out != nullptr) {  // moments of the ROUNDED values a LayerNorm would read
               const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z),
                            f3 = unpack_bf16x2(u.w);
@@ -577,11 +568,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             reinterpret_cast<float2*>(p.stats_out)[row * p.stats_slabs + slab_col(n_blk, s) / 64] =
                 make_float2(so1, so2);
           fence_proxy_async_smem();
-          named_bar_sync(bar_id + 1, 128);  // slab complete in smem
-          if (half_leader) {
-            tma_store_2d(&tmOut, out_buf, slab_col(n_blk, s), row0);
+          __syncwarp();  // the warp's 32 rows are complete in smem
+          CD360_TRACE_CLK(trace_me && s < 2, 20 + 5 * s);
+          if (lane == 0) {
+            tma_store_2d(&tmOut, sbuf, slab_col(n_blk, s), row0 + q * 32);
             tma_store_commit();
+            if (use_res) {  // prefetch the next residual slab (this or the next tile) into the other buffer
+              int nt = tile, ns = s + 1;
+              if (ns == n_slabs) { nt = tile + num_units; ns = 0; }
+              if (nt < num_tiles) {
+                const int nm = nt % p.num_m_blocks, nn = nt / p.num_m_blocks;
+                tma_store_wait_read_1();  // the previous slab's store has released that buffer
+                uint64_t* nb = &wres[(slab_cnt + 1u) & 1u];
+                mbar_arrive_expect_tx(nb, WSLAB_BYTES);
+                tma_load_2d(wbuf + ((slab_cnt + 1u) & 1u) * WSLAB_BYTES, &tmRes, nb, slab_col(nn, ns),
+                            (nm * CG + static_cast<int>(rank)) * BM + q * 32);
+              }
+            }
           }
+          __syncwarp();
+          ++slab_cnt;
           CD360_TRACE_CLK(trace_me && s < 2, 21 + 5 * s);
         }
       } else {
@@ -647,7 +653,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     if (warp == 4 && lane == 0) CD360_TRACE(10);
     // smem must outlive the bulk stores' READS; the writes are complete at grid completion
-    if (p.epi_tma && half_leader) tma_store_wait_read();
+    if (p.epi_tma && lane == 0) tma_store_wait_read();
     if (warp == 4 && lane == 0) CD360_TRACE(11);
     CD360_TRACE_CLK(warp == 4 && lane == 0, 27);
   }
@@ -902,7 +908,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   tmRes = tmB;
   if (p.epi_tma) {
     uint64_t dims[2] = {static_cast<uint64_t>(p.N_out), static_cast<uint64_t>(a->M)};
-    uint32_t box[2] = {64, BM};
+    uint32_t box[2] = {64, 32};  // one epilogue warp's rows
     uint64_t so[1] = {static_cast<uint64_t>(a->ldo) * 2};
     rc = encode_tmap_bf16(&tmOut, a->out, 2, dims, so, box, false);
     if (rc != CD360_OK) return rc;
