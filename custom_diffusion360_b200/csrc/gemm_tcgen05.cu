@@ -425,11 +425,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         ln_mu = s1 * p.ln_inv_c;
         ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
-      const float* s_bias = reinterpret_cast<const float*>(smem + L::BIAS_OFFSET) + buf * BN;
-      if (p.bias != nullptr) {  // columns beyond N read as 0; double buffered by tile parity
-        for (int e = (warp - 4) * 32 + lane; e < BN; e += kEpiWarps * 32)
-          reinterpret_cast<float*>(smem + L::BIAS_OFFSET)[buf * BN + e] =
-              (n0 + e < p.N) ? __ldg(p.bias + n0 + e) : 0.f;
+      // tile bias (and, with a folded LayerNorm, the column sums of W') staged in smem; columns
+      // beyond N read as 0.  Plain: bias double buffered by tile parity.  LN folded: [bias | colsum]
+      // single buffered, released by the barrier at the end of the tile.
+      const bool ln_in = p.ln_stats != nullptr;
+      float* s_stage = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+      const float* s_bias = s_stage + (ln_in ? 0 : buf * BN);
+      const float* s_cs = s_stage + BN;
+      if (p.bias != nullptr || ln_in) {
+        for (int e = (warp - 4) * 32 + lane; e < BN; e += kEpiWarps * 32) {
+          const bool ok = n0 + e < p.N;
+          s_stage[(ln_in ? 0 : buf * BN) + e] = (ok && p.bias != nullptr) ? __ldg(p.bias + n0 + e) : 0.f;
+          if (ln_in) s_stage[BN + e] = ok ? __ldg(p.ln_colsum + n0 + e) : 0.f;
+        }
         named_bar_sync(5, kEpiWarps * 32);
       }
       mbar_wait(&tmem_full[buf], acc_phase);
@@ -464,13 +472,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               const int col0 = n0 + (c0 + h) * 32;
               const int nvalid = max(0, min(32, p.N - col0));
               if (nvalid > 0) {
-                if (p.ln_stats != nullptr) {
-                  float cs[32];
+                if (ln_in) {
+                  const float4* cs4 = reinterpret_cast<const float4*>(s_cs + (c0 + h) * 32);
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) cs[j] = 0.f;
-                  load_bias32(cs, p.ln_colsum, col0, nvalid);
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) vv[j] = fmaf(-ln_mu, cs[j], vv[j]) * ln_rstd;
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 c = cs4[j];
+                    vv[4 * j + 0] = fmaf(-ln_mu, c.x, vv[4 * j + 0]) * ln_rstd;
+                    vv[4 * j + 1] = fmaf(-ln_mu, c.y, vv[4 * j + 1]) * ln_rstd;
+                    vv[4 * j + 2] = fmaf(-ln_mu, c.z, vv[4 * j + 2]) * ln_rstd;
+                    vv[4 * j + 3] = fmaf(-ln_mu, c.w, vv[4 * j + 3]) * ln_rstd;
+                  }
                 }
                 if (p.bias != nullptr) add_bias32_smem(vv, s_bias + (c0 + h) * 32);
                 if (rb != nullptr) load_bias32(vv, rb, col0, nvalid);
@@ -497,16 +508,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                 xv[j] = __uint_as_float(rx[j]);
                 gv[j] = __uint_as_float(rg[j]);
               }
-              if (p.ln_stats != nullptr) {
-                float cx[32], cgt[32];
+              if (ln_in) {
+                const float4* cx4 = reinterpret_cast<const float4*>(s_cs + (c0 + h) * 32);
+                const float4* cg4 = reinterpret_cast<const float4*>(s_cs + BN / 2 + (c0 + h) * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { cx[j] = 0.f; cgt[j] = 0.f; }
-                load_bias32(cx, p.ln_colsum, n0 + (c0 + h) * 32, 32);
-                load_bias32(cgt, p.ln_colsum, n0 + BN / 2 + (c0 + h) * 32, 32);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  xv[j] = fmaf(-ln_mu, cx[j], xv[j]) * ln_rstd;
-                  gv[j] = fmaf(-ln_mu, cgt[j], gv[j]) * ln_rstd;
+                for (int j = 0; j < 8; ++j) {
+                  const float4 a = cx4[j], g = cg4[j];
+                  xv[4 * j + 0] = fmaf(-ln_mu, a.x, xv[4 * j + 0]) * ln_rstd;
+                  xv[4 * j + 1] = fmaf(-ln_mu, a.y, xv[4 * j + 1]) * ln_rstd;
+                  xv[4 * j + 2] = fmaf(-ln_mu, a.z, xv[4 * j + 2]) * ln_rstd;
+                  xv[4 * j + 3] = fmaf(-ln_mu, a.w, xv[4 * j + 3]) * ln_rstd;
+                  gv[4 * j + 0] = fmaf(-ln_mu, g.x, gv[4 * j + 0]) * ln_rstd;
+                  gv[4 * j + 1] = fmaf(-ln_mu, g.y, gv[4 * j + 1]) * ln_rstd;
+                  gv[4 * j + 2] = fmaf(-ln_mu, g.z, gv[4 * j + 2]) * ln_rstd;
+                  gv[4 * j + 3] = fmaf(-ln_mu, g.w, gv[4 * j + 3]) * ln_rstd;
                 }
               }
               if (p.bias != nullptr) {
@@ -650,6 +665,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           else mbar_arrive(&tmem_empty[buf]);
         }
       }
+      if (ln_in) named_bar_sync(6, kEpiWarps * 32);  // [bias | colsum] may be overwritten
     }
     if (warp == 4 && lane == 0) CD360_TRACE(10);
     // smem must outlive the bulk stores' READS; the writes are complete at grid completion

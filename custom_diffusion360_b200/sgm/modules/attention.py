@@ -30,12 +30,13 @@ from .nerfsd_pytorch3d import NerfSDModule, VolRender
 from .utils_cameraray import pack_pose
 
 bf16 = torch.bfloat16
-# LayerNorms folded into the neighbouring GEMM epilogues on the token fast path.  Measured on B200
-# (profiles/README_r01.md): the extra epilogue work on the single-tile GEMMs costs slightly more
-# than the 210 LayerNorm launches it removes (29.66 vs 29.37 ms / step), so it is OFF by default;
-# CD360_LN_FUSED=1 enables it (parity-tested either way).
+# LayerNorms folded into the neighbouring GEMM epilogues on the token fast path (removes 210
+# launches per step).  Measured on B200 (profiles/README_r01.md): a loss while the epilogue fetched
+# bias / column sums from global memory (29.66 vs 29.37 ms / step), a gain since they are staged in
+# shared memory (26.1 vs 26.5 ms), so it is ON by default; CD360_LN_FUSED=0 disables it
+# (parity-tested either way).
 import os as _os
-LN_FUSED = _os.environ.get("CD360_LN_FUSED", "0") != "0"
+LN_FUSED = _os.environ.get("CD360_LN_FUSED", "1") != "0"
 
 
 def to_tokens(x: torch.Tensor) -> torch.Tensor:
