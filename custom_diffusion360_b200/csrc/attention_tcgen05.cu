@@ -80,12 +80,38 @@ __device__ __forceinline__ uint64_t make_smem_desc_ones(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;         // the 256-byte ones region; layout type 0 = no swizzle
   return d;
 }
+// 2^x for a pair of arguments on the FMA / ALU pipes instead of the MUFU: round-to-nearest range
+// reduction (adding 1.5 * 2^23 leaves rint(x) in the low mantissa bits), a degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P)
+// and an integer add into the exponent field.  The softmax is bound by the 16 ex2/clk/SM MUFU rate,
+// so a fixed fraction of every row's exponentials takes this path (ATT_POLY_MASK).
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 one2 = make_float2(1.f, 1.f);
+  const float2 magic2 = make_float2(12582912.f, 12582912.f);
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = ffma2(x, one2, magic2);                               // rint(x) in the mantissa
+  const float2 fl = ffma2(t, one2, make_float2(-12582912.f, -12582912.f));  // rint(x), exact
+  const float2 f = ffma2(fl, make_float2(-1.f, -1.f), x);                // x - rint(x)
+  float2 pl = ffma2(make_float2(0.0551716682f, 0.0551716682f), f,
+                    make_float2(0.2426111221f, 0.2426111221f));
+  pl = ffma2(pl, f, make_float2(0.6932609856f, 0.6932609856f));
+  pl = ffma2(pl, f, make_float2(0.9999280735f, 0.9999280735f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+// Which of every 8 element pairs take the polynomial: template parameter of the kernel
+// (bit k set = pair k).  Default 0xA4 (37.5 %); CD360_ATT_POLY=<eighths> selects 0..5 eighths.
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
 
+template <uint32_t ATT_POLY_MASK>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
                               const __grid_constant__ CUtensorMap tmK,
@@ -248,7 +274,12 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         for (int i = 0; i < 64; i += 2) {
           const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
                                  sc2, nmb2);
-          pk[i >> 1] = pack_bf16x2(ex2_approx(a.x), ex2_approx(a.y));
+          if ((ATT_POLY_MASK >> ((i >> 1) & 7)) & 1u) {
+            const float2 e = ex2_poly2(a);
+            pk[i >> 1] = pack_bf16x2(e.x, e.y);
+          } else {
+            pk[i >> 1] = pack_bf16x2(ex2_approx(a.x), ex2_approx(a.y));
+          }
         }
       } else {
 #pragma unroll
@@ -369,13 +400,25 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   if (rc != CD360_OK) return rc;
   rc = make_qkv_map(&tv, v, ldv, heads, nkv, batch, ATT_BKV);
   if (rc != CD360_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(attention_bf16_tcgen05_kernel,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             ATT_SMEM_BYTES) != cudaSuccess)
+  typedef void (*AttnKern)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  static AttnKern kern = nullptr;
+  if (kern == nullptr) {
+    int eighths = 3;
+    const char* e = getenv("CD360_ATT_POLY");
+    if (e != nullptr && e[0] >= '0' && e[0] <= '5') eighths = e[0] - '0';
+    AttnKern k = attention_bf16_tcgen05_kernel<0xA4u>;
+    switch (eighths) {
+      case 0: k = attention_bf16_tcgen05_kernel<0x00u>; break;
+      case 1: k = attention_bf16_tcgen05_kernel<0x08u>; break;
+      case 2: k = attention_bf16_tcgen05_kernel<0x88u>; break;
+      case 3: k = attention_bf16_tcgen05_kernel<0xA4u>; break;
+      case 4: k = attention_bf16_tcgen05_kernel<0xAAu>; break;
+      default: k = attention_bf16_tcgen05_kernel<0xB6u>; break;
+    }
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES) !=
+        cudaSuccess)
       return CD360_ERR_LAUNCH;
-    attr_set = true;
+    kern = k;
   }
   AttnParams p;
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -385,8 +428,8 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   p.heads = heads;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   dim3 grid((nq + ATT_BQ - 1) / ATT_BQ, heads, batch);
-  if (launch_ex(attention_bf16_tcgen05_kernel, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1,
-                tq, tk, tv, p) != cudaSuccess)
+  if (launch_ex(kern, grid, dim3(ATT_THREADS), ATT_SMEM_BYTES, stream, 1, tq, tk, tv, p) !=
+      cudaSuccess)
     return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
   return CD360_OK;

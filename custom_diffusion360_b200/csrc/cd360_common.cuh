@@ -155,6 +155,17 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// pair load multicast to every CTA in `cta_mask` (same smem offset in each destination; the
+// transaction bytes are credited to the barrier at this offset in each destination's pair leader)
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* smem_dst, const CUtensorMap* tm,
+                                                   uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)),
+      "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm,
                                                 uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(

@@ -29,7 +29,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 // out[b, n] = act_out(sum_k act_in(x[b,k]) W[n,k] + bias[n]) + add[b,n]
 // (time_embed / label_emb, openaimodel.py:679-713,1026-1031; ResBlock.emb_layers, :307-313,363)
 constexpr int SL_BCHUNK = 4;
-constexpr int SL_OUT_PER_WARP = 4;
+constexpr int SL_OUT_PER_WARP = 2;
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ add,
@@ -52,37 +52,64 @@ small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = k >> 3;
-  for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi) {
-    const int col = (blockIdx.x * 8 + warp) * SL_OUT_PER_WARP + oi;
-    if (col >= n) break;
-    const __nv_bfloat16* wr = w + static_cast<long long>(col) * k;
-    float acc[SL_BCHUNK];
+  // a warp owns SL_OUT_PER_WARP consecutive output columns and walks their weight rows TOGETHER:
+  // SL_OUT_PER_WARP x 2 independent 16-byte loads in flight per lane (the M = batch <= 4 product is
+  // pure weight streaming; one dependent load per lane left it latency-bound at ~0.1 TB/s)
+  const int col0 = (blockIdx.x * 8 + warp) * SL_OUT_PER_WARP;
+  if (col0 < n) {
+    float acc[SL_OUT_PER_WARP][SL_BCHUNK];
 #pragma unroll
-    for (int bi = 0; bi < SL_BCHUNK; ++bi) acc[bi] = 0.f;
-    for (int v = lane; v < nvec; v += 32) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + v * 8));
-      const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z),
-                   w3 = unpack_bf16x2(u.w);
-      const float wf[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+    for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi)
 #pragma unroll
-      for (int bi = 0; bi < SL_BCHUNK; ++bi) {
-        const float* xr = s_x + bi * k + v * 8;
+      for (int bi = 0; bi < SL_BCHUNK; ++bi) acc[oi][bi] = 0.f;
+    for (int v0 = lane; v0 < nvec; v0 += 64) {
+      uint4 u[SL_OUT_PER_WARP][2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[bi] = fmaf(wf[j], xr[j], acc[bi]);
+      for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi) {
+        const int col = min(col0 + oi, n - 1);  // clamped: duplicates are discarded below
+        const __nv_bfloat16* wr = w + static_cast<long long>(col) * k;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int v = v0 + 32 * h;
+          u[oi][h] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(wr + v * 8))
+                              : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int v = min(v0 + 32 * h, nvec - 1);  // zero weights make the clamped x harmless
+#pragma unroll
+        for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi) {
+          const uint4 uu = u[oi][h];
+          const float2 w0 = unpack_bf16x2(uu.x), w1 = unpack_bf16x2(uu.y), w2 = unpack_bf16x2(uu.z),
+                       w3 = unpack_bf16x2(uu.w);
+          const float wf[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+#pragma unroll
+          for (int bi = 0; bi < SL_BCHUNK; ++bi) {
+            const float* xr = s_x + bi * k + v * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[oi][bi] = fmaf(wf[j], xr[j], acc[oi][bi]);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int bi = 0; bi < SL_BCHUNK; ++bi) {
+    for (int oi = 0; oi < SL_OUT_PER_WARP; ++oi) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[bi] += __shfl_xor_sync(0xffffffffu, acc[bi], o);
-    }
-    if (lane == 0) {
-      for (int bi = 0; bi < nb; ++bi) {
-        float r = acc[bi] + (bias ? bias[col] : 0.f);
-        if (act_out == CD360_ACT_SILU) r = r / (1.0f + expf(-r));
-        const long long o = static_cast<long long>(b0 + bi) * n + col;
-        if (add) r += add[o];
-        out[o] = r;
+      for (int bi = 0; bi < SL_BCHUNK; ++bi) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          acc[oi][bi] += __shfl_xor_sync(0xffffffffu, acc[oi][bi], o);
+      }
+      const int col = col0 + oi;
+      if (lane == 0 && col < n) {
+        for (int bi = 0; bi < nb; ++bi) {
+          float r = acc[oi][bi] + (bias ? bias[col] : 0.f);
+          if (act_out == CD360_ACT_SILU) r = r / (1.0f + expf(-r));
+          const long long o = static_cast<long long>(b0 + bi) * n + col;
+          if (add) r += add[o];
+          out[o] = r;
+        }
       }
     }
   }

@@ -202,7 +202,7 @@ __device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams&
 }
 
 // ---- kernel ------------------------------------------------------------------------------------
-template <int BN, int STAGES, int CG>
+template <int BN, int STAGES, int CG, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                          const __grid_constant__ CUtensorMap tmA1,
@@ -221,10 +221,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  // cluster = MC CTA pairs (or single CTAs); pair `pr` works on M block m_blk*MC + pr of the SAME
+  // N block, so with MC == 2 the two pairs share every W tile (TMA multicast below)
+  const uint32_t crank = (CG * MC > 1) ? cluster_ctarank() : 0u;
+  const uint32_t rank = crank % CG;          // rank inside the pair
+  const uint32_t pr = crank / CG;            // pair inside the cluster
+  const uint32_t leader_rank = pr * CG;      // cluster rank of this pair's MMA-issuing CTA
   const bool leader = rank == 0;
-  const int unit = blockIdx.x / CG;         // CTA (CG=1) or cluster (CG=2) index
-  const int num_units = gridDim.x / CG;
+  const int unit = blockIdx.x / (CG * MC);   // cluster (or lone CTA) index
+  const int num_units = gridDim.x / (CG * MC);
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int nkb = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -244,7 +249,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], CG);  // pair: leader's expect_tx arrive + peer's remote arrive
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);  // one multicast commit per pair sharing the slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -263,7 +268,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   }
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (CG * MC > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (threadIdx.x == 0) CD360_TRACE(1);
@@ -277,7 +282,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     for (int tile = unit; tile < num_tiles; tile += num_units) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
-      const int m0 = (m_blk * CG + static_cast<int>(rank)) * BM;
+      const int m0 = ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM;
       const int n0 = n_blk * BN + static_cast<int>(rank) * L::BNC;
       int cb = 0, cy = 0, cx = 0;
       if (p.conv) {
@@ -297,7 +302,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         } else if (leader) {
           mbar_arrive_expect_tx(fb, 2 * L::STAGE_BYTES);
         } else {
-          mbar_arrive_remote(fb, 0);
+          mbar_arrive_remote(fb, leader_rank);
         }
         if (p.conv) {
           const int tap = kb / p.cblocks;
@@ -311,8 +316,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           if (CG == 2) tma_load_2d_2sm(sa, tm, fb, kk, m0);
           else tma_load_2d(sa, tm, fb, kk, m0);
         }
-        if (CG == 2) tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0);
-        else tma_load_2d(sb, &tmB, fb, kb * BK, n0);
+        if (MC == 2) {
+          // this CTA fetches one half of its W rows and multicasts it to the CTA of the same pair
+          // rank in the other pair (which fetches the other half): W crosses L2 -> SM once per
+          // cluster instead of once per pair
+          constexpr int QR = L::BNC / 2;
+          tma_load_2d_2sm_mc(sb + pr * QR * 128, &tmB, fb, kb * BK, n0 + static_cast<int>(pr) * QR,
+                             static_cast<uint16_t>((1u << rank) | (1u << (CG + rank))));
+        } else if (CG == 2) {
+          tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0);
+        } else {
+          tma_load_2d(sb, &tmB, fb, kb * BK, n0);
+        }
         if (tile == unit && kb == 0) CD360_TRACE(3);
         if (tile + num_units >= num_tiles && kb == nkb - 1) CD360_TRACE(4);
         if (++stage == STAGES) {
@@ -348,10 +363,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         // free the smem slot (in both CTAs) once these MMAs retire
-        if (CG == 2) umma_commit_2sm(&empty_bar[stage], 0x3);
+        if (CG == 2) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>((1u << (CG * MC)) - 1u));
         else umma_commit(&empty_bar[stage]);
         if (kb == nkb - 1) {
-          if (CG == 2) umma_commit_2sm(&tmem_full[buf], 0x3);
+          if (CG == 2) umma_commit_2sm(&tmem_full[buf], static_cast<uint16_t>(0x3u << (pr * 2)));
           else umma_commit(&tmem_full[buf]);
           if (tile + num_units >= num_tiles) CD360_TRACE(7);
         }
@@ -386,7 +401,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int m_blk = unit % p.num_m_blocks, n_blk = unit / p.num_m_blocks;
       mbar_arrive_expect_tx(&wres[0], WSLAB_BYTES);
       tma_load_2d(wbuf, &tmRes, &wres[0], slab_col(n_blk, 0),
-                  (m_blk * CG + static_cast<int>(rank)) * BM + q * 32);
+                  ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32);
     }
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
@@ -394,7 +409,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int n_blk = tile / p.num_m_blocks;
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
-      const int row0 = (m_blk * CG + static_cast<int>(rank)) * BM;
+      const int row0 = ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM;
       const long long row = static_cast<long long>(row0) + row_in_tile;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
@@ -537,7 +552,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
+              if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], leader_rank);
               else mbar_arrive(&tmem_empty[buf]);
             }
           }
@@ -597,7 +612,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                 uint64_t* nb = &wres[(slab_cnt + 1u) & 1u];
                 mbar_arrive_expect_tx(nb, WSLAB_BYTES);
                 tma_load_2d(wbuf + ((slab_cnt + 1u) & 1u) * WSLAB_BYTES, &tmRes, nb, slab_col(nn, ns),
-                            (nm * CG + static_cast<int>(rank)) * BM + q * 32);
+                            ((nm * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32);
               }
             }
           }
@@ -661,7 +676,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], 0);
+          if (CG == 2 && !leader) mbar_arrive_remote(&tmem_empty[buf], leader_rank);
           else mbar_arrive(&tmem_empty[buf]);
         }
       }
@@ -676,7 +691,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
 
   // ---- teardown ----
   tc_fence_before();
-  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (CG * MC > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
@@ -738,24 +753,44 @@ int num_sms() {
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int BN, int STAGES, int CG>
+template <int BN, int STAGES, int CG, int MC>
 static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                        const CUtensorMap& o, const CUtensorMap& r, const GemmKParams& p,
                        int max_ctas, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, CG>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, CG>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, CG, MC>;
+  constexpr int CL = CG * MC;  // CTAs per cluster
+  static int max_units = 0;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES) !=
         cudaSuccess)
       return CD360_ERR_LAUNCH;
+    max_units = num_sms() / CL;
+    if (CL > 2) {  // clusters of 4 may not tile every GPC: ask the driver how many fit at once
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(num_sms() / CL * CL);
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = L::DYN_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CL;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters > 0 &&
+          nclusters < max_units)
+        max_units = nclusters;
+    }
     attr_set = true;
   }
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  int units = num_sms() / CG;
-  if (max_ctas > 0 && max_ctas / CG >= 1 && max_ctas / CG < units) units = max_ctas / CG;
+  int units = max_units;
+  if (max_ctas > 0 && max_ctas / CL >= 1 && max_ctas / CL < units) units = max_ctas / CL;
   if (tiles < units) units = tiles;
-  if (launch_ex(kern, dim3(units * CG), dim3(kGemmThreads), L::DYN_BYTES, stream, CG, a0, a1, b, o,
+  if (launch_ex(kern, dim3(units * CL), dim3(kGemmThreads), L::DYN_BYTES, stream, CL, a0, a1, b, o,
                 r, p) != cudaSuccess)
     return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
@@ -763,18 +798,29 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 }
 
 // tile configuration: block_n = 128 selects the single-CTA 128x128 kernel, 256 / 512 the
-// 256x256 CTA-pair (cta_group::2) kernel; 0 = heuristic (pair whenever M spans two CTAs).
+// 256x256 CTA-pair (cta_group::2) kernel, 1024 the pair kernel in clusters of two pairs that share
+// W through TMA multicast; 0 = heuristic (pair whenever M spans two CTAs, multicast whenever the
+// number of 256-row blocks is even).  Returns 128, 512 or 1024.
 static int pick_config(int M, int N, int geglu, int requested) {
   static int pair_ok = -1;
   if (pair_ok < 0) {
     const char* e = getenv("CD360_GEMM_PAIR");
     pair_ok = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
+  static int mc_ok = -1;
+  if (mc_ok < 0) {
+    const char* e = getenv("CD360_GEMM_MULTICAST");
+    // measured on B200 (profiles/README_r01.md): no faster for one-wave shapes, slower for
+    // multi-wave ones (fewer co-resident clusters of four; L2 already merges the two pairs' reads)
+    mc_ok = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
   if (requested == 128) return 128;
-  if (requested == 256 || requested == 512) return (geglu && (N % 256) != 0) ? 128 : 512;
   if (geglu && (N % 256) != 0) return 128;
+  if (requested == 256 || requested == 512) return 512;
+  if (requested == 1024) return 1024;
   if (N <= 128 || M <= 128 || !pair_ok) return (geglu && (N % 256) == 0) ? 512 : 128;
-  return 512;
+  const int pair_blocks = (M + 2 * BM - 1) / (2 * BM);
+  return (mc_ok && pair_blocks >= 2 && (pair_blocks & 1) == 0) ? 1024 : 512;
 }
 
 }  // namespace cd360
@@ -793,8 +839,9 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (a->M <= 0 || a->N <= 0) return CD360_ERR_SHAPE;
   const int cfgsel = pick_config(a->M, a->N, a->geglu, a->block_n);
-  const int CGsel = cfgsel == 512 ? 2 : 1;
-  const int BN = cfgsel == 512 ? 256 : 128;
+  const int CGsel = cfgsel >= 512 ? 2 : 1;
+  const int MCsel = cfgsel == 1024 ? 2 : 1;
+  const int BN = cfgsel >= 512 ? 256 : 128;
   if (a->geglu && (a->N % BN != 0 || (a->N & 1))) return CD360_ERR_SHAPE;
   if (a->geglu && a->act != CD360_ACT_NONE) return CD360_ERR_UNSUPPORTED;
 
@@ -802,7 +849,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   p.M = a->M;
   p.N = a->N;
   p.N_out = a->geglu ? a->N / 2 : a->N;
-  p.num_m_blocks = (a->M + BM * CGsel - 1) / (BM * CGsel);
+  p.num_m_blocks = (a->M + BM * CGsel * MCsel - 1) / (BM * CGsel * MCsel);  // per cluster step
   p.num_n_blocks = (a->N + BN - 1) / BN;
   p.bias = a->bias;
   p.row_bias = a->row_bias;
@@ -916,7 +963,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(BN / CGsel)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(BN / CGsel / MCsel)};
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, true);
     if (rc != CD360_OK) return rc;
   }
@@ -934,9 +981,11 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
       if (rc != CD360_OK) return rc;
     }
   }
+  if (cfgsel == 1024)
+    return launch_gemm<256, 5, 2, 2>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
   if (cfgsel == 512)
-    return launch_gemm<256, 5, 2>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
-  return launch_gemm<128, 5, 1>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
+    return launch_gemm<256, 5, 2, 1>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
+  return launch_gemm<128, 5, 1, 1>(tmA0, tmA1, tmB, tmOut, tmRes, p, a->max_ctas, stream);
 }
 
 CD360_TL_SETTER(gemm)

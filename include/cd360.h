@@ -87,7 +87,7 @@ typedef struct cd360_gemm_args {
   int32_t B, H, W, C;
   int32_t act;   /* CD360_ACT_* */
   int32_t geglu; /* 0 / 1 */
-  int32_t block_n; /* 0 = auto, 128 = single-CTA 128x128 tiles, 256/512 = CTA-pair 256x256 tiles */
+  int32_t block_n; /* 0 = auto, 128 = single-CTA 128x128 tiles, 256/512 = CTA-pair 256x256 tiles, 1024 = pair tiles in 4-CTA clusters sharing W by TMA multicast */
   int32_t max_ctas; /* 0 = one per SM */
   /* LayerNorm folded into the contraction (linear mode, bf16 output).  With W' = W diag(gamma)
    * and bias' = bias + W beta supplied as `w` / `bias`:

@@ -66,24 +66,28 @@ def test_gemm_linear(M, N, K, bn):
     (640, 5120, 1280),
     (129, 264, 64),           # peer CTA owns a single valid row; N tail inside the peer's W half
 ])
-def test_gemm_cta_pair(M, N, K):
-    """cta_group::2 kernel (block_n=512): 256 x 256 tiles across a two-CTA cluster."""
+@pytest.mark.parametrize("bn", [512, 1024])
+def test_gemm_cta_pair(M, N, K, bn):
+    """cta_group::2 kernel: 256 x 256 tiles across a two-CTA cluster (block_n=512), and the same in
+    clusters of two pairs that share every W tile through TMA multicast (block_n=1024; odd numbers
+    of 256-row blocks leave the second pair of the last cluster step out of range)."""
     from custom_diffusion360_b200 import ops
     torch.manual_seed(12)
     a, af = _rt(torch.randn(M, K, device=_dev()))
     w, wf = _rt(torch.randn(N, K, device=_dev()) / math.sqrt(K))
     bias = torch.randn(N, device=_dev()) if N % 4 == 0 else None
     res, resf = _rt(torch.randn(M, N, device=_dev()))
-    out = ops.gemm(a, w, bias=bias, residual=res, block_n=512)
+    out = ops.gemm(a, w, bias=bias, residual=res, block_n=bn)
     ref = af @ wf.t() + resf + (bias if bias is not None else 0)
-    _assert_close(out, ref, what="gemm cta pair")
-    for max_ctas in (2, 6):  # one / three clusters looping over all tiles: ring + TMEM wrap-around
-        out = ops.gemm(a, w, block_n=512, max_ctas=max_ctas)
-        _assert_close(out, af @ wf.t(), what=f"gemm cta pair max_ctas={max_ctas}")
+    _assert_close(out, ref, what=f"gemm cta pair bn={bn}")
+    for max_ctas in (4, 12):  # one / three clusters looping over all tiles: ring + TMEM wrap-around
+        out = ops.gemm(a, w, block_n=bn, max_ctas=max_ctas)
+        _assert_close(out, af @ wf.t(), what=f"gemm cta pair bn={bn} max_ctas={max_ctas}")
 
 
 @gpu
-def test_cta_pair_conv_geglu_segments():
+@pytest.mark.parametrize("bn", [512, 1024])
+def test_cta_pair_conv_geglu_segments(bn):
     from custom_diffusion360_b200 import ops
     from custom_diffusion360_b200.sgm.prepack import pack_conv3x3, pack_geglu
     torch.manual_seed(13)
@@ -93,7 +97,7 @@ def test_cta_pair_conv_geglu_segments():
     bias = torch.randn(Cout, device=_dev())
     emb = torch.randn(B, Cout, device=_dev())
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cin)
-    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, bias=bias, row_bias=emb, block_n=512)
+    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, bias=bias, row_bias=emb, block_n=bn)
     ref = torch.nn.functional.conv2d(xf, wf, bias, padding=1) + emb[:, :, None, None]
     _assert_close(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), what="conv3x3 cta pair")
     # small image: a 128-row tile spans two images, the pair spans four
@@ -101,7 +105,7 @@ def test_cta_pair_conv_geglu_segments():
     x, xf = _rt(torch.randn(B, Cin, H, W, device=_dev()))
     w, wf = _rt(torch.randn(Cout, Cin, 3, 3, device=_dev()) / math.sqrt(9 * Cin))
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().view(B * H * W, Cin)
-    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, block_n=512)
+    out = ops.conv3x3(x_nhwc, pack_conv3x3(w), B, H, W, block_n=bn)
     ref = torch.nn.functional.conv2d(xf, wf, None, padding=1)
     _assert_close(out, ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout), what="conv3x3 cta pair small")
     # GEGLU + two K segments
@@ -110,14 +114,14 @@ def test_cta_pair_conv_geglu_segments():
     w, wf = _rt(torch.randn(8 * c, c, device=_dev()) / math.sqrt(c))
     b8 = torch.randn(8 * c, device=_dev())
     wp, bp = pack_geglu(w, b8)
-    out = ops.gemm(a, wp, bias=bp, geglu=True, block_n=512)
+    out = ops.gemm(a, wp, bias=bp, geglu=True, block_n=bn)
     h = af @ wf.t() + b8
     xx, gate = h.chunk(2, dim=-1)
     _assert_close(out, xx * torch.nn.functional.gelu(gate), abs_=2e-3, what="geglu cta pair")
     a0, a0f = _rt(torch.randn(M, 1280, device=_dev()))
     a1, a1f = _rt(torch.randn(M, 640, device=_dev()))
     w2, w2f = _rt(torch.randn(640, 1920, device=_dev()) / math.sqrt(1920))
-    out = ops.gemm(a0, w2, a1=a1, block_n=512)
+    out = ops.gemm(a0, w2, a1=a1, block_n=bn)
     _assert_close(out, torch.cat([a0f, a1f], 1) @ w2f.t(), what="two segments cta pair")
 
 

@@ -78,7 +78,7 @@ def main():
             if geglu:
                 w, bias = pack_geglu(w, bias)
             o = torch.empty(M, N // 2 if geglu else N, device=dev, dtype=torch.bfloat16)
-            for cfg in (512, 256, 128):
+            for cfg in (1024, 512, 128):
                 if geglu and cfg == 128:
                     continue
                 med, mn = timeit(lambda: ops.gemm(a, w, bias=bias, residual=res, geglu=geglu, out=o, block_n=cfg), args.reps)
@@ -92,7 +92,7 @@ def main():
             w = pack_conv3x3(torch.randn(Co, C, 3, 3, device=dev) / math.sqrt(9 * C))
             bias = torch.randn(Co, device=dev)
             o = torch.empty(B * H * H, Co, device=dev, dtype=torch.bfloat16)
-            for cfg in (512, 256, 128):
+            for cfg in (1024, 512, 128):
                 med, mn = timeit(lambda: ops.conv3x3(x, w, B, H, H, bias=bias, out=o, block_n=cfg), args.reps)
                 report("conv3x3", f"B{B} {H}x{H} {what}", 2.0 * B * H * H * Co * 9 * C, med, mn, cfg=cfg)
             del x, w, o
