@@ -251,6 +251,12 @@ class BasicTransformerBlock(nn.Module):
         """Reference tokens per CFG row from the stored `references` buffer (sample.py:85-96):
         row group 0 -> the 'null' reference (last row) repeated n times, other groups -> the chosen
         real references.  bf16 [batch*n*hw, c]; cached (static across the sampling loop)."""
+        live = self.__dict__.get("_live_ctxref")
+        if live is not None:  # UNetModel.forward(input_ref=...): tokens of the live reference stream
+            tok, n = live
+            assert tok.shape[0] % (batch * n) == 0
+            self._ctxref_cache = (("live", tok.data_ptr()), tok, n)
+            return tok
         refs = self.references
         choices = list(self.choices) if self.choices is not None else list(range(refs.shape[0] - 1))
         key = (batch, tuple(choices), refs.data_ptr())
@@ -324,7 +330,16 @@ class BasicTransformerBlock(nn.Module):
                 aux = (fg, alphas, rgb)
             x = self.pose_emb_layers.tokens(x, a1=self.rendered_feat)  # Linear(cat[x, xref]) w/o the cat
         x = self.ff.tokens(self.norm3.tokens(x), residual=x, out=x)
+        self._capture_out(x)
         return x, aux
+
+    def _capture_out(self, x):
+        """Reference-stream capture (UNetModel.capture_references): pose-capable blocks record the
+        tokens they emit — what the reference's validation hook stores as `references`
+        (diffusion.py:28-40, main.py:594-602).  x is updated in place downstream, hence the copy."""
+        cap = self.__dict__.get("_capture")
+        if cap is not None and self.image_cross:
+            cap.append(x.clone())
 
     # ---- token fast path with the three LayerNorms folded into the GEMMs -------------------------
     def ln_packed(self):
@@ -406,6 +421,7 @@ class BasicTransformerBlock(nn.Module):
                      ln_eps=eps)
         st = new_stats()
         x = self.ff.net[2].tokens(h, residual=x, out=x, stats_out=st)
+        self._capture_out(x)
         return x, st, aux
 
     # ---- reference-signature entry point ---------------------------------------------------------

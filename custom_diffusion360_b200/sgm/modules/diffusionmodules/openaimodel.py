@@ -277,6 +277,28 @@ class UNetModel(nn.Module, _Packed):
                 m.register_buffer("references", t)
                 m._ctxref_cache = None
 
+    @torch.no_grad()
+    def capture_references(self, x_ref, timesteps, context, y):
+        """The UNet's reference stream (openaimodel.py:79-111, attention.py:830-868): run the
+        reference latents x_ref [R,4,L,L] through the SAME weights without pose conditioning and
+        return {"<pose block name>": bf16 tokens [R, hw, c]} — the tensors the reference's validation
+        hook saves as each pose block's `references` buffer (diffusion.py:28-40, main.py:594-602).
+        Feed the result (plus the run's "null" row, sample.py:85-96) to `register_references`."""
+        blocks = list(self.pose_blocks())
+        for _, m in blocks:
+            m.__dict__["_capture"] = []
+        try:
+            self.forward_tokens(x_ref, timesteps, context, y, pose=None)
+        finally:
+            caps = {name: m.__dict__.pop("_capture") for name, m in blocks}
+        r = x_ref.shape[0]
+        out = {}
+        for name, lst in caps.items():
+            assert len(lst) == 1, f"{name}: expected one reference-stream pass, got {len(lst)}"
+            t = lst[0]
+            out[name] = t.view(r, t.shape[0] // r, t.shape[1])
+        return out
+
     def resblocks(self):
         return [m for m in self.modules() if isinstance(m, ResBlock)]
 
@@ -341,14 +363,42 @@ class UNetModel(nn.Module, _Packed):
     def forward(self, x, timesteps=None, context=None, y=None, timesteps2=None, **kwargs):
         """x [B,4,L,L] fp32, timesteps [B], context [B,77,ctx], y [B,adm] ->
         (eps [B,4,L,L] fp32, fg_mask_list, alphas_list, predicted_rgb_list)."""
-        if kwargs.get("input_ref") is not None:
-            raise NotImplementedError("reference-image stream (training path) is a later row of SURVEY §8f")
         if kwargs.get("mask_ref") is not None:
             raise NotImplementedError("mask_ref is not supported on the inference path")
         assert (y is not None), "must specify y: the model is class-conditional (num_classes='sequential')"
         # (CPU tensors are rejected by the first kernel wrapper: there is no CPU path)
-        eps_tok, b, hh, ww, aux = self.forward_tokens(x, timesteps, context, y, kwargs.get("pose"),
-                                                      kwargs.get("in_scale"))
+        xr = kwargs.get("input_ref")
+        if xr is None:
+            eps_tok, b, hh, ww, aux = self.forward_tokens(x, timesteps, context, y, kwargs.get("pose"),
+                                                          kwargs.get("in_scale"))
+        else:
+            # The call shape of the training step, forward only (reference :1008-1051): the reference
+            # latents input_ref [b, n, 4, L, L] form a second, pose-free stream through the same
+            # weights (time embedding of `sigmas_ref` broadcast over the n views, text / vector
+            # conditioning = the second halves of context / y) and every pose block of the main
+            # stream reads that stream's tokens as its context_ref (attention.py:852-854).
+            b, n = xr.shape[:2]
+            assert context.shape[0] == b + b * n and y.shape[0] == b + b * n, \
+                "context / y must hold the b target rows followed by the b*n reference rows"
+            sig = kwargs.get("sigmas_ref", timesteps2)
+            if sig is None:
+                sig = torch.zeros_like(timesteps)
+            t_ref = sig.reshape(b, 1).expand(b, n).reshape(b * n)
+            caps = self.capture_references(xr.reshape(b * n, *xr.shape[2:]), t_ref, context[b:], y[b:])
+            blocks = dict(self.pose_blocks())
+            self.clear_rendered_feat()
+            for name, m in blocks.items():
+                t = caps[name]                                   # [b*n, hw, c]
+                m.__dict__["_live_ctxref"] = (t.reshape(-1, t.shape[-1]), n)
+                m._ctxref_cache = None
+            try:
+                eps_tok, b, hh, ww, aux = self.forward_tokens(x, timesteps, context[:b], y[:b],
+                                                              kwargs.get("pose"), kwargs.get("in_scale"))
+            finally:
+                for m in blocks.values():
+                    m.__dict__.pop("_live_ctxref", None)
+                    m._ctxref_cache = None
+                self.clear_rendered_feat()  # FeatureNeRF output is per call on this path (no caching)
         eps = ops.nhwc_to_nchw_f32(eps_tok, b, hh * ww, self.out_channels).view(b, self.out_channels, hh, ww)
         fg = [a[0].view(b, -1, 1) for a in aux]
         al = [a[1].view(b, a[1].shape[1], a[1].shape[2], 1) for a in aux]

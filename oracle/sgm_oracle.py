@@ -357,8 +357,13 @@ def build_context_ref(references: Tensor, choices: Sequence[int], batch: int) ->
 
 
 def transformer_block(sd, p: str, x: Tensor, context: Tensor, heads: int, cfg: dict,
-                      cams: Optional[Tensor] = None, choices=None, cache: Optional[dict] = None):
-    """BasicTransformerBlock as run at inference: _customforward (sample.py:82-136)."""
+                      cams: Optional[Tensor] = None, choices=None, cache: Optional[dict] = None,
+                      capture: Optional[dict] = None, ctx_ref: Optional[dict] = None):
+    """BasicTransformerBlock as run at inference: _customforward (sample.py:82-136).
+    capture: reference-stream mode — the block runs WITHOUT pose conditioning
+    (attention.py:852-853: `xr = block(xr, context=contextr[i])`) and the output tokens of every
+    block that owns pose weights are recorded under its prefix, which is what the validation hook
+    stores as `references` (diffusion.py:28-40 keeps outputs whose fg_mask is None; main.py:594-602)."""
     aux = None
     x = cross_attention(sd, p + "attn1.", layer_norm(sd, p + "norm1.", x), None, heads) + x
     x = cross_attention(sd, p + "attn2.", layer_norm(sd, p + "norm2.", x), context, heads) + x
@@ -366,18 +371,24 @@ def transformer_block(sd, p: str, x: Tensor, context: Tensor, heads: int, cfg: d
         if cache is not None and p in cache:
             xref = cache[p]
         else:
-            ctx_ref = build_context_ref(sd[p + "references"], choices, x.size(0))
-            xref, fg, alphas, rgb = reference_attn(sd, p, cams, ctx_ref, context, heads, cfg)
+            if ctx_ref is not None and p in ctx_ref:  # live reference stream (attention.py:852-854)
+                cref = ctx_ref[p]
+            else:
+                cref = build_context_ref(sd[p + "references"], choices, x.size(0))
+            xref, fg, alphas, rgb = reference_attn(sd, p, cams, cref, context, heads, cfg)
             aux = (fg, alphas, rgb)
             if cache is not None:
                 cache[p] = xref
         x = F.linear(torch.cat([x, xref], -1), sd[p + "pose_emb_layers.weight"])
     x = feed_forward(sd, p + "ff.", layer_norm(sd, p + "norm3.", x)) + x
+    if capture is not None and (p + "pose_emb_layers.weight") in sd:
+        capture[p] = x
     return x, aux
 
 
 def spatial_transformer(sd, p: str, x: Tensor, context: Tensor, heads: int, depth: int, cfg: dict,
-                        image_cross: bool, cams=None, choices=None, cache=None, aux_out=None):
+                        image_cross: bool, cams=None, choices=None, cache=None, aux_out=None,
+                        capture=None, ctx_ref=None):
     """SpatialTransformer at inference: customforward (sample.py:33-79), use_linear=True."""
     b, c, h, w = x.shape
     x_in = x
@@ -388,7 +399,7 @@ def spatial_transformer(sd, p: str, x: Tensor, context: Tensor, heads: int, dept
     for i in range(depth):
         pose_here = image_cross and (i % interval == 0)
         x, aux = transformer_block(sd, f"{p}transformer_blocks.{i}.", x, context, heads, cfg,
-                                   cams if pose_here else None, choices, cache)
+                                   cams if pose_here else None, choices, cache, capture, ctx_ref)
         if aux is not None and aux_out is not None:
             aux_out.append(aux)
     x = F.linear(x, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
@@ -448,7 +459,8 @@ def unet_layout(cfg: dict) -> dict:
     return {"input_blocks": inputs, "middle_block": middle, "output_blocks": outputs, "out_ch": ch}
 
 
-def _run_layers(sd, prefix, layers, h, emb, context, cfg, cams, choices, cache, aux_out):
+def _run_layers(sd, prefix, layers, h, emb, context, cfg, cams, choices, cache, aux_out, capture=None,
+                ctx_ref=None):
     for j, layer in enumerate(layers):
         p = f"{prefix}{j}."
         kind = layer[0]
@@ -459,7 +471,7 @@ def _run_layers(sd, prefix, layers, h, emb, context, cfg, cams, choices, cache, 
         elif kind == "st":
             _, ch, heads, depth, image_cross = layer
             h = spatial_transformer(sd, p, h, context, heads, depth, cfg, image_cross, cams, choices,
-                                    cache, aux_out)
+                                    cache, aux_out, capture, ctx_ref)
         elif kind == "down":  # Downsample (openaimodel.py:183-230)
             h = F.conv2d(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)
         elif kind == "up":  # Upsample (openaimodel.py:114-164)
@@ -469,11 +481,16 @@ def _run_layers(sd, prefix, layers, h, emb, context, cfg, cams, choices, cache, 
 
 
 def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor, context: Tensor,
-                 y: Tensor, cams: Optional[Tensor] = None, choices=None, cache: Optional[dict] = None):
+                 y: Tensor, cams: Optional[Tensor] = None, choices=None, cache: Optional[dict] = None,
+                 capture: Optional[dict] = None, ctx_ref: Optional[dict] = None):
     """UNetModel.forward (openaimodel.py:975-1093) as executed by sample.py: no reference stream
     (input_ref absent), pose-enabled blocks take their reference tokens from the stored
     `references` buffers.  Returns (eps, aux) with aux = list of (fg_mask, alphas, rgb) per pose
-    block that ran FeatureNeRF in this call."""
+    block that ran FeatureNeRF in this call.
+    capture (dict, with cams=None): reference-stream pass over reference latents x — the tokens
+    leaving every pose-capable block are stored as capture["<block prefix>"] = [B, hw, c]
+    (the UNet's ref stream, openaimodel.py:79-111 / attention.py:830-868, shares all weights with
+    the main stream and never sees pose conditioning)."""
     aux_out: list = []
     layout = unet_layout(cfg)
     t_emb = timestep_embedding(timesteps, cfg["model_channels"])
@@ -484,14 +501,36 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor,
     h = x
     hs = []
     for i, layers in enumerate(layout["input_blocks"]):
-        h = _run_layers(sd, f"input_blocks.{i}.", layers, h, emb, context, cfg, cams, choices, cache, aux_out)
+        h = _run_layers(sd, f"input_blocks.{i}.", layers, h, emb, context, cfg, cams, choices, cache, aux_out,
+                        capture, ctx_ref)
         hs.append(h)
-    h = _run_layers(sd, "middle_block.", layout["middle_block"], h, emb, context, cfg, cams, choices, cache, aux_out)
+    h = _run_layers(sd, "middle_block.", layout["middle_block"], h, emb, context, cfg, cams, choices, cache, aux_out,
+                    capture, ctx_ref)
     for i, layers in enumerate(layout["output_blocks"]):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, context, cfg, cams, choices, cache, aux_out)
+        h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, context, cfg, cams, choices, cache, aux_out,
+                        capture, ctx_ref)
     h = F.silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"]))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1), aux_out
+
+
+def unet_forward_with_reference_stream(sd, cfg: dict, x: Tensor, timesteps: Tensor, context: Tensor,
+                                       y: Tensor, cams: Tensor, input_ref: Tensor, sigmas_ref: Tensor,
+                                       context_ref: Tensor, y_ref: Tensor):
+    """UNetModel.forward WITH `input_ref` (openaimodel.py:1008-1051, the training-time call shape,
+    forward only): the reference latents input_ref [b, n, 4, L, L] run through the same weights as
+    a second, pose-free stream whose time embedding is `timestep_embedding(sigmas_ref)` broadcast
+    over the n views (:1041-1049) and whose text / vector conditioning are the second halves of
+    context / y; every pose block of the main stream then reads the reference stream's tokens of
+    that block as its context_ref (attention.py:852-854) instead of a stored `references` buffer.
+    Returns ((eps, aux), captured reference tokens)."""
+    b, n = input_ref.shape[:2]
+    cap: dict = {}
+    t_ref = sigmas_ref.reshape(b, 1).expand(b, n).reshape(b * n)
+    unet_forward(sd, cfg, input_ref.reshape(b * n, *input_ref.shape[2:]), t_ref, context_ref,
+                 y_ref.reshape(b * n, -1), capture=cap)
+    live = {p: v.reshape(b, n, *v.shape[1:]) for p, v in cap.items()}
+    return unet_forward(sd, cfg, x, timesteps, context, y, cams=cams, ctx_ref=live), cap
 
 
 # --------------------------------------------------------------------------------------------

@@ -77,3 +77,52 @@ def test_guider_and_scalings(ns):
     a2 = g2.prepare_inputs(x, s, c, uc)
     b2 = O.guider_prepare_inputs(x, s, c, uc, 2)
     assert all(torch.equal(a2[2][k], b2[2][k]) for k in c)
+
+
+def test_reference_stream_forward(ns):
+    """UNetModel.forward WITH input_ref (the training-step call shape, forward only): the
+    reference's own un-patched modules vs the restatement, including the tokens the validation hook
+    would store as `references` (diffusion.py:28-40 keeps block outputs whose fg_mask is None)."""
+    torch.manual_seed(0)
+    cfg = dict(O.TINY_CFG)
+    L, n, b = 16, 3, 1
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=n + 1)
+    model = H.build_reference_unet(ns, cfg, sd, patch_for_sampling=False)
+    captured = {}
+
+    def hook(name):
+        def fn(module, inp, out):
+            if isinstance(out, tuple) and out[1] is None:
+                captured.setdefault(name, []).append(out[0].detach())
+        return fn
+
+    handles = []
+    for name, module in model.named_modules():
+        parts = name.split(".")
+        if len(parts) > 1 and parts[-2] == "transformer_blocks" and hasattr(module, "pose_emb_layers"):
+            handles.append(module.register_forward_hook(hook(name)))
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(b, 4, L, L, generator=g)
+    xr = torch.randn(b, n, 4, L, L, generator=g)
+    ctx = torch.randn(b, 77, cfg["context_dim"], generator=g)
+    ctxr = torch.randn(b * n, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(b, cfg["adm_in_channels"], generator=g)
+    yr = torch.randn(b * n, cfg["adm_in_channels"], generator=g)
+    t = torch.tensor([500])
+    sig = torch.tensor([120])
+    cams = O.lookat_cameras(n, seed=3)[None]
+    pose = [H.cameras_from_packed(cams[0])]
+    with torch.no_grad():
+        eps, fg, alphas, rgb = model(x, timesteps=t, context=torch.cat([ctx, ctxr]), y=torch.cat([y, yr]),
+                                     input_ref=xr, sigmas_ref=sig, pose=pose, mask_ref=None)
+        (eps2, aux2), cap2 = O.unet_forward_with_reference_stream(sd, cfg, x, t, ctx, y, cams, xr, sig,
+                                                                  ctxr, yr)
+    for h in handles:
+        h.remove()
+    assert len(fg) == len(aux2) == len(cap2) == len(captured) > 0
+    assert (eps - eps2).abs().max() < 2e-4 * max(1.0, float(eps.abs().max()))
+    for name, lst in captured.items():
+        assert len(lst) == 1
+        assert (lst[0] - cap2[name + "."]).abs().max() < 2e-4 * max(1.0, float(lst[0].abs().max()))
+    for f, (f2, a2, r2) in zip(fg, aux2):
+        assert (f - f2.reshape(f.shape)).abs().max() < 1e-4

@@ -121,6 +121,82 @@ def test_tiny_unet_pose_on_and_cache(gold):
 
 
 @gpu
+def test_reference_stream_capture_vs_oracle(gold):
+    """the UNet's reference stream — reference latents through the same weights,
+    pose conditioning off — and the tokens each pose block hands to `references`; then the captured
+    buffers drive a pose-conditioned forward exactly like stored ones."""
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    L, nv = gold["latent"], gold["n_views"]
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=nv + 1)
+    model = _build(cfg, sd, dev)
+    g = torch.Generator().manual_seed(5)
+    xr = torch.randn(nv, 4, L, L, generator=g)
+    ctx = torch.randn(nv, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(nv, cfg["adm_in_channels"], generator=g)
+    t = torch.full((nv,), 300)
+    cap_ref = {}
+    with torch.no_grad():
+        O.unet_forward(sd, cfg, xr, t, ctx, y, capture=cap_ref)
+        caps = model.capture_references(xr.to(dev), t.to(dev), ctx.to(dev), y.to(dev))
+    names = [n for n, _ in model.pose_blocks()]
+    assert sorted(caps) == sorted(names) == sorted(k[:-1] for k in cap_ref)
+    for n in names:
+        assert caps[n].shape == cap_ref[n + "."].shape
+        _check(f"refstream_{n}", caps[n], cap_ref[n + "."])
+    # captured references (+ a null row) are accepted where stored ones were
+    refs = {n: torch.cat([caps[n], torch.zeros_like(caps[n][:1])]).float() for n in names}
+    model.register_references(refs)
+    model.set_reference_choices(list(range(nv)))
+    inp, c, uc = _cfg_inputs(cfg, gold)
+    cams = inp["cams"][0][None].expand(3, -1, -1).contiguous()
+    x3 = torch.cat([inp["x"]] * 3)
+    ctx3 = torch.cat([uc["crossattn"], uc["crossattn"], c["crossattn"]])
+    y3 = torch.cat([uc["vector"], uc["vector"], c["vector"]])
+    sd2 = dict(sd)
+    for n in names:
+        sd2[n + ".references"] = refs[n].cpu()
+    with torch.no_grad():
+        eps, fg, _, _ = model(x3.to(dev), timesteps=torch.tensor([500] * 3, device=dev), context=ctx3.to(dev),
+                              y=y3.to(dev), pose=cams.to(dev))
+        ref, _ = O.unet_forward(sd2, cfg, x3, torch.tensor([500] * 3), ctx3, y3, cams=cams,
+                                choices=list(range(nv)))
+    assert len(fg) == len(names)
+    _check("refstream_then_pose_forward", eps, ref)
+
+
+@gpu
+def test_forward_with_input_ref_vs_oracle(gold):
+    """UNetModel.forward(input_ref=..., sigmas_ref=...) — the training step's call shape, forward
+    only (reference openaimodel.py:1008-1051): live reference stream feeding the pose blocks."""
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    L, n, b = gold["latent"], 4, 2
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=n + 1)
+    model = _build(cfg, sd, dev)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(b, 4, L, L, generator=g)
+    xr = torch.randn(b, n, 4, L, L, generator=g)
+    ctx = torch.randn(b, 77, cfg["context_dim"], generator=g)
+    ctxr = torch.randn(b * n, 77, cfg["context_dim"], generator=g)
+    y = torch.randn(b, cfg["adm_in_channels"], generator=g)
+    yr = torch.randn(b * n, cfg["adm_in_channels"], generator=g)
+    t, sig = torch.tensor([500, 300]), torch.tensor([120, 40])
+    cams = torch.stack([O.lookat_cameras(n, seed=3), O.lookat_cameras(n, seed=4, target_azimuth=2.0)])
+    with torch.no_grad():
+        (ref, aux_ref), _ = O.unet_forward_with_reference_stream(sd, cfg, x, t, ctx, y, cams, xr, sig, ctxr, yr)
+        eps, fg, al, rgb = model(x.to(dev), timesteps=t.to(dev), context=torch.cat([ctx, ctxr]).to(dev),
+                                 y=torch.cat([y, yr]).to(dev), input_ref=xr.to(dev), sigmas_ref=sig.to(dev),
+                                 pose=cams.to(dev))
+    assert len(fg) == len(aux_ref) > 0
+    _check("input_ref_forward_eps", eps, ref)
+    for i, (f, (f2, a2, r2)) in enumerate(zip(fg, aux_ref)):
+        _check(f"input_ref_fg_{i}", f, f2.reshape(f.shape), rel_tol=2e-2)
+    # the stream leaves no state behind: stored references drive the next call again
+    assert all(m.rendered_feat is None and "_live_ctxref" not in m.__dict__ for _, m in model.pose_blocks())
+
+
+@gpu
 def test_feature_nerf_module_vs_oracle():
     """NerfSDModule (hoisted / fused kernels) vs the literal restatement, one block, c=128."""
     from custom_diffusion360_b200.sgm.modules.nerfsd_pytorch3d import NerfSDModule
