@@ -260,8 +260,12 @@ def test_conv3x3(B, H, W, Cin, Cout):
     (1, 2, 64, 200),          # ragged queries and keys
     (2, 20, 384, 77),
 ])
-def test_attention(batch, heads, nq, nkv):
+@pytest.mark.parametrize("kernel", ["1", "2"])
+def test_attention(batch, heads, nq, nkv, kernel, monkeypatch):
+    """kernel 1: default (two CTAs per SM, 64-key tiles); kernel 2: opt-in ping-pong kernel (one CTA
+    per SM, two query tiles, 128-key tiles), selected per call through CD360_ATT_KERNEL."""
     from custom_diffusion360_b200 import ops
+    monkeypatch.setenv("CD360_ATT_KERNEL", kernel)
     torch.manual_seed(5)
     c = heads * 64
     q, qf = _rt(torch.randn(batch * nq, c, device=_dev()))
