@@ -22,6 +22,8 @@ SOURCES = [
     "norm.cu",
     "elementwise.cu",
     "nerf.cu",
+    "attention_bwd.cu",
+    "train.cu",
 ]
 
 NVCC_FLAGS = [

@@ -67,6 +67,26 @@ SIGNATURES = {
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
     "cd360_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "cd360_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    # training step (backward / loss / optimiser)
+    "cd360_attention_bwd_bf16": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L,
+                                           _P, _P, _I, _I, _I, _I, _P]),
+    "cd360_layernorm_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "cd360_groupnorm_bwd_workspace_floats": (C.c_int64, [_I]),
+    "cd360_groupnorm_silu_bwd_bf16": (C.c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P,
+                                                _I, _I, _F, _I, _P]),
+    "cd360_geglu_bwd_bf16": (C.c_int, [_P, _P, _P, _L, _I, _I, _P]),
+    "cd360_add_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
+    "cd360_transpose_to_bf16": (C.c_int, [_P, _I, _L, _P, _L, _I, _I, _P]),
+    "cd360_colsum_bf16": (C.c_int, [_P, _L, _P, _L, _I, _P]),
+    "cd360_col2im3x3_s2_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "cd360_upsample_nearest2x_bwd_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
+    "cd360_nerf_volrender_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cd360_nerf_combine_bwd": (C.c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "cd360_nerf_nviews_geo_bwd": (C.c_int, [_P, _P, _P, _I, _I, _L, _P]),
+    "cd360_diffusion_loss": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
+    "cd360_nerf_aux_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "cd360_resize_bilinear_aa": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "cd360_adamw_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 
 _lib = None

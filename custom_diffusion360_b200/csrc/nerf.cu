@@ -245,7 +245,11 @@ nerf_combine_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
 
   // --- weighted sum over views of SiLU(hpre + gather(G)) ---
   const int nvec = c >> 3;
-  for (int vi = lane; vi < nvec; vi += 32) {
+  // every lane runs every iteration: the shuffles below name the whole warp, and their source
+  // lanes (views) must be converged with it even when c/8 is not a multiple of 32 (c = 640)
+  for (int v0 = 0; v0 < nvec; v0 += 32) {
+    const int vi = v0 + lane;
+    const bool act = vi < nvec;
     float out[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) out[k] = 0.f;
@@ -258,6 +262,7 @@ nerf_combine_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
         idx[k] = __shfl_sync(0xffffffffu, my_idx[k], v);
         wk[k] = __shfl_sync(0xffffffffu, my_w[k], v);
       }
+      if (!act) continue;
       const long long point = ((static_cast<long long>(b) * n + v) * hw) * d + p;
       float h[8];
       {
@@ -275,6 +280,7 @@ nerf_combine_kernel(const __nv_bfloat16* __restrict__ g, long long ldg,
 #pragma unroll
       for (int k = 0; k < 8; ++k) out[k] = fmaf(a_v, silu_f(h[k]), out[k]);
     }
+    if (!act) continue;
     uint4 o;
     o.x = pack_bf16x2(out[0], out[1]);
     o.y = pack_bf16x2(out[2], out[3]);
@@ -336,14 +342,17 @@ nerf_volrender_kernel(const __nv_bfloat16* __restrict__ feats, const float* __re
     rgb[wid * 3 + 2] = s2;
   }
   const int nvec = c >> 3;
-  for (int vi = lane; vi < nvec; vi += 32) {
+  for (int v0 = 0; v0 < nvec; v0 += 32) {  // whole warp in every iteration (see nerf_combine_kernel)
+    const int vi = v0 + lane;
+    const bool act = vi < nvec;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     for (int s = 0; s < d; ++s) {
       const float ws = __shfl_sync(0xffffffffu, w, s);
-      fma8(acc, __ldg(reinterpret_cast<const uint4*>(feats + (wid * d + s) * c + vi * 8)), ws);
+      if (act) fma8(acc, __ldg(reinterpret_cast<const uint4*>(feats + (wid * d + s) * c + vi * 8)), ws);
     }
+    if (!act) continue;
     uint4 o;
     o.x = pack_bf16x2(acc[0], acc[1]);
     o.y = pack_bf16x2(acc[2], acc[3]);

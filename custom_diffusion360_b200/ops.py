@@ -360,3 +360,222 @@ def nerf_volrender(feats, raw, dists, b, hw, d, c):
                                    _ptr(alphas), _ptr(rgb), b, hw, d, c, _stream()),
           "cd360_nerf_volrender")
     return rendered, fg, alphas, rgb
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: backward / loss / optimiser kernels (csrc/train.cu, csrc/attention_bwd.cu)
+# ------------------------------------------------------------------------------------------------
+@_op("attention_bwd")
+def attention_bwd(q, k, v, o, dout, batch, heads, nq, nkv, *, dq, dk=None, dv=None):
+    """Gradients of `attention`.  q/k/v/o/dout and dq/dk/dv are 2-D views (row strides taken from
+    the views, so slices of a fused QKV buffer work).  dk/dv None: query gradient only."""
+    lib = _lib.load()
+    dev = q.device
+    lse = torch.empty((batch, heads, nq), device=dev, dtype=f32)
+    dsum = torch.empty((batch, heads, nq), device=dev, dtype=f32)
+    LaunchStats.launches += 1 if dk is None else 2  # stats + dq (+ dkdv)
+    check(lib.cd360_attention_bwd_bf16(
+        _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
+        _ptr(dout), dout.stride(0), _ptr(dq), dq.stride(0), _ptr(dk), 0 if dk is None else dk.stride(0),
+        _ptr(dv), 0 if dv is None else dv.stride(0), _ptr(lse), _ptr(dsum), batch, heads, nq, nkv,
+        _stream()), "cd360_attention_bwd_bf16")
+    return dq, dk, dv
+
+
+@_op("layernorm_bwd")
+def layernorm_bwd(x, gamma, dy, *, add=None, eps=1e-5, out=None):
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    _req(dy, bf16, "dy")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.cd360_layernorm_bwd_bf16(_ptr(x), _ptr(gamma), _ptr(dy), _ptr(add), _ptr(out), rows, c,
+                                       eps, _stream()), "cd360_layernorm_bwd_bf16")
+    return out
+
+
+@_op("groupnorm_bwd")
+def groupnorm_bwd(x0, gamma, beta, dy, batch, hw, *, x1=None, add0=None, add1=None, eps=1e-5,
+                  silu=True):
+    """Returns (dx0, dx1 | None).  add0 / add1 may be column slices (row stride from the view)."""
+    lib = _lib.load()
+    _req(x0, bf16, "x0")
+    _req(dy, bf16, "dy")
+    c0 = x0.shape[-1]
+    c1 = 0 if x1 is None else x1.shape[-1]
+    dev = x0.device
+    dx0 = torch.empty((batch * hw, c0), device=dev, dtype=bf16)
+    dx1 = None if x1 is None else torch.empty((batch * hw, c1), device=dev, dtype=bf16)
+    ws = torch.empty(int(lib.cd360_groupnorm_bwd_workspace_floats(batch)), device=dev, dtype=f32)
+    LaunchStats.launches += 1
+    check(lib.cd360_groupnorm_silu_bwd_bf16(
+        _ptr(x0), c0, _ptr(x1), c1, _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(add0),
+        0 if add0 is None else add0.stride(0), _ptr(add1), 0 if add1 is None else add1.stride(0),
+        _ptr(dx0), _ptr(dx1), _ptr(ws), batch, hw, eps, int(silu), _stream()),
+        "cd360_groupnorm_silu_bwd_bf16")
+    return dx0, dx1
+
+
+@_op("geglu_bwd")
+def geglu_bwd(raw, dh, block=None):
+    lib = _lib.load()
+    _req(raw, bf16, "raw")
+    _req(dh, bf16, "dh")
+    rows, f = dh.shape
+    out = torch.empty_like(raw)
+    check(lib.cd360_geglu_bwd_bf16(_ptr(raw), _ptr(dh), _ptr(out), rows, f, f if block is None else block,
+                                   _stream()), "cd360_geglu_bwd_bf16")
+    return out
+
+
+@_op("add")
+def add_bf16(a, b, *, out=None):
+    lib = _lib.load()
+    _req(a, bf16, "a")
+    _req(b, bf16, "b")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.cd360_add_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "cd360_add_bf16")
+    return out
+
+
+@_op("transpose")
+def transpose_to_bf16(x, *, ld_out=None):
+    """x [rows, cols] bf16 / fp32 (row stride from the view) -> bf16 [cols, ld_out >= rows]."""
+    lib = _lib.load()
+    rows, cols = x.shape
+    if ld_out is None:
+        ld_out = (rows + 7) // 8 * 8
+    out = torch.empty((cols, ld_out), device=x.device, dtype=bf16)
+    check(lib.cd360_transpose_to_bf16(_ptr(x), int(x.dtype == f32), x.stride(0), _ptr(out), ld_out, rows,
+                                      cols, _stream()), "cd360_transpose_to_bf16")
+    return out
+
+
+@_op("colsum")
+def colsum(x, *, out=None):
+    """fp32 [c] += column sums of bf16 x [rows, c]; `out` is accumulated into (zeros if None)."""
+    lib = _lib.load()
+    rows, c = x.shape
+    if out is None:
+        out = torch.zeros(c, device=x.device, dtype=f32)
+    check(lib.cd360_colsum_bf16(_ptr(x), x.stride(0), _ptr(out), rows, c, _stream()), "cd360_colsum_bf16")
+    return out
+
+
+@_op("col2im_s2")
+def col2im3x3_s2(dcol, batch, h, w, c):
+    lib = _lib.load()
+    _req(dcol, bf16, "dcol")
+    out = torch.empty((batch * h * w, c), device=dcol.device, dtype=bf16)
+    check(lib.cd360_col2im3x3_s2_bf16(_ptr(dcol), _ptr(out), batch, h, w, c, _stream()),
+          "cd360_col2im3x3_s2_bf16")
+    return out
+
+
+@_op("upsample_bwd")
+def upsample_nearest2x_bwd(g, batch, h, w):
+    """g bf16 [batch*2h*2w, c] -> [batch*h*w, c]."""
+    lib = _lib.load()
+    _req(g, bf16, "g")
+    c = g.shape[-1]
+    out = torch.empty((batch * h * w, c), device=g.device, dtype=bf16)
+    check(lib.cd360_upsample_nearest2x_bwd_bf16(_ptr(g), _ptr(out), batch, h, w, c, _stream()),
+          "cd360_upsample_nearest2x_bwd_bf16")
+    return out
+
+
+@_op("nerf_bwd")
+def nerf_volrender_bwd(feats, raw, dists, d_rendered, dfg, dalphas, drgb, b, hw, d, c):
+    lib = _lib.load()
+    dev = feats.device
+    dfeats = torch.empty((b * hw * d, c), device=dev, dtype=bf16)
+    draw = torch.empty((b * hw * d, 8), device=dev, dtype=bf16)
+    check(lib.cd360_nerf_volrender_bwd(_ptr(feats), _ptr(raw), _ptr(dists), _ptr(d_rendered), _ptr(dfg),
+                                       _ptr(dalphas), _ptr(drgb), _ptr(dfeats), _ptr(draw), b, hw, d, c,
+                                       _stream()), "cd360_nerf_volrender_bwd")
+    return dfeats, draw
+
+
+@_op("nerf_bwd")
+def nerf_combine_bwd(g, hpre, gidx, gwgt, vlogit, ds, b, n, hw, d, c):
+    lib = _lib.load()
+    dev = g.device
+    dhpre = torch.empty((b * n * hw * d, c), device=dev, dtype=bf16)
+    dlogit = torch.empty((b, n, hw * d), device=dev, dtype=f32)
+    dg = torch.zeros((b * n * hw, g.stride(0)), device=dev, dtype=f32)
+    check(lib.cd360_nerf_combine_bwd(_ptr(g), g.stride(0), _ptr(hpre), _ptr(gidx), _ptr(gwgt),
+                                     _ptr(vlogit), _ptr(ds), _ptr(dhpre), _ptr(dlogit), _ptr(dg), b, n,
+                                     hw, d, c, _stream()), "cd360_nerf_combine_bwd")
+    return dhpre, dlogit, dg
+
+
+@_op("nerf_bwd")
+def nerf_nviews_geo_bwd(cams, dlogit, b, n):
+    lib = _lib.load()
+    dw = torch.zeros(198, device=cams.device, dtype=f32)
+    check(lib.cd360_nerf_nviews_geo_bwd(_ptr(cams), _ptr(dlogit), _ptr(dw), b, n, dlogit.shape[-1],
+                                        _stream()), "cd360_nerf_nviews_geo_bwd")
+    return dw
+
+
+@_op("loss")
+def diffusion_loss(eps, x_noisy, target, sigma, mask, coef, *, ldd=64):
+    """eps fp32 tokens [b*hw, 4]; x_noisy/target fp32 [b,4,h,w]; mask fp32 [b,1,h,w] | None.
+    Returns (loss [b], mask_sum [b], deps bf16 [b*hw, ldd])."""
+    lib = _lib.load()
+    _req(eps, f32, "eps")
+    _req(x_noisy, f32, "x_noisy")
+    _req(target, f32, "target")
+    b = x_noisy.shape[0]
+    hw = x_noisy.shape[2] * x_noisy.shape[3]
+    dev = eps.device
+    loss = torch.empty(b, device=dev, dtype=f32)
+    msum = torch.empty(b, device=dev, dtype=f32)
+    deps = torch.empty((b * hw, ldd), device=dev, dtype=bf16)
+    check(lib.cd360_diffusion_loss(_ptr(eps), _ptr(x_noisy), _ptr(target), _ptr(sigma), _ptr(mask),
+                                   float(coef), _ptr(loss), _ptr(msum), _ptr(deps), b, hw, ldd, _stream()),
+          "cd360_diffusion_loss")
+    return loss, msum, deps
+
+
+@_op("loss")
+def nerf_aux_loss(fg, alphas, rgb, op, mask_s, tgt, mask_sum, wfg, wbg, wrgb):
+    """Returns (loss3 [b,3], dfg, dalphas, drgb | None)."""
+    lib = _lib.load()
+    b, hw = fg.shape[0], fg.shape[1]
+    d = alphas.shape[2]
+    dev = fg.device
+    loss3 = torch.empty((b, 3), device=dev, dtype=f32)
+    dfg = torch.empty((b, hw), device=dev, dtype=f32)
+    dal = torch.empty((b, hw, d), device=dev, dtype=f32)
+    drgb = None if rgb is None else torch.empty((b, hw, 3), device=dev, dtype=f32)
+    check(lib.cd360_nerf_aux_loss(_ptr(fg), _ptr(alphas), _ptr(rgb), _ptr(op), _ptr(mask_s), _ptr(tgt),
+                                  _ptr(mask_sum), _ptr(wfg), _ptr(wbg), _ptr(wrgb), _ptr(loss3), _ptr(dfg),
+                                  _ptr(dal), _ptr(drgb), b, hw, d, _stream()), "cd360_nerf_aux_loss")
+    return loss3, dfg, dal, drgb
+
+
+@_op("other")
+def resize_bilinear_aa(x, oh, ow, *, scale=1.0, shift=0.0):
+    """fp32 [..., ih, iw] -> [..., oh, ow], torch's bilinear antialias resize."""
+    lib = _lib.load()
+    _req(x, f32, "x")
+    ih, iw = x.shape[-2:]
+    planes = x.numel() // (ih * iw)
+    out = torch.empty((*x.shape[:-2], oh, ow), device=x.device, dtype=f32)
+    check(lib.cd360_resize_bilinear_aa(_ptr(x), _ptr(out), planes, ih, iw, oh, ow, float(scale),
+                                       float(shift), _stream()), "cd360_resize_bilinear_aa")
+    return out
+
+
+@_op("adamw")
+def adamw_step(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, step=1,
+               grad_scale=1.0):
+    lib = _lib.load()
+    for t, nme in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _req(t, f32, nme)
+    check(lib.cd360_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), lr, beta1, beta2, eps,
+                               weight_decay, step, grad_scale, _stream()), "cd360_adamw_step")
+    return p

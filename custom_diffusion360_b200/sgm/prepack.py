@@ -53,3 +53,23 @@ def _geglu_block(n: int) -> int:
     if n % 128 == 0:
         return 64
     raise ValueError(f"GEGLU width {n} not a multiple of 128")
+
+
+def pack_conv3x3_bwd(w: torch.Tensor, cout_pad: int = 0) -> torch.Tensor:
+    """Weight pack of the DATA gradient of a stride-1 pad-1 3x3 conv (training step): dX is the
+    same convolution of dY with the taps flipped and the channel roles swapped,
+    W'[ci, co, ky, kx] = W[co, ci, 2-ky, 2-kx] -> bf16 [Cin, 9*Cout'] in the implicit-GEMM K order.
+    cout_pad zero-pads the (small) Cout of the UNet's 4-channel output conv to a full 64-wide K chunk."""
+    cout, cin = w.shape[:2]
+    wt = w.flip(2, 3).permute(1, 0, 2, 3)
+    if cout_pad > cout:
+        wp = torch.zeros(cin, cout_pad, 3, 3, dtype=w.dtype, device=w.device)
+        wp[:, :cout] = wt
+        wt = wp
+    return pack_conv3x3(wt)
+
+
+def transposed(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] -> contiguous bf16 [K, N]: the `w` operand of dX = dY W through cd360_gemm_bf16
+    (which computes A W'^T, so W' = W^T)."""
+    return w.detach().t().contiguous().to(torch.bfloat16)

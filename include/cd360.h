@@ -236,6 +236,117 @@ int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t
 int cd360_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t batch, int32_t hw, int32_t c,
                                 cd360_stream_t stream);
 
+/* =============================================================================================
+ * Training step: backward of the path above towards the pose weights
+ * (trainkeys 'pose', sgm/models/diffusion.py:139-144), the loss of
+ * StandardDiffusionLossImgRef (sgm/modules/diffusionmodules/loss.py:140-216) and AdamW.
+ * The reference obtains all of these from torch.autograd; here each is an explicit kernel.  The
+ * data gradients of every Linear / conv reuse cd360_gemm_bf16 with transposed / tap-flipped
+ * weight packs (dX = dY W), weight gradients are cd360_gemm_bf16 over operands transposed by
+ * cd360_transpose_to_bf16 (dW = dY^T X, fp32 out).
+ * ============================================================================================= */
+
+/* Backward of cd360_attention_bf16 (autograd of xformers memory_efficient_attention,
+ * attention.py:406).  o = forward output, dout = its gradient, all [B, n, heads*64] bf16 with row
+ * strides in elements.  dq always; dk/dv both or neither (NULL for text cross-attention, whose K/V
+ * are projections of the constant context).  lse / dsum: fp32 scratch [batch, heads, nq]. */
+int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                             int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo,
+                             void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                             float* lse, float* dsum, int32_t batch, int32_t heads, int32_t nq,
+                             int32_t nkv, cd360_stream_t stream);
+
+/* LayerNorm backward w.r.t. the input (nn.LayerNorm, attention.py:531-533; gamma/beta are frozen):
+ * dx = dLN(x)^T dy [+ add].  x, dy, add, dx bf16 [rows, c]; c <= 1280. */
+int cd360_layernorm_bwd_bf16(const void* x, const float* gamma, const void* dy, const void* add,
+                             void* dx, int32_t rows, int32_t c, float eps, cd360_stream_t stream);
+
+/* GroupNorm(32)[+SiLU] backward w.r.t. the input (GroupNorm32 + SiLU, openaimodel.py:280-283;
+ * Normalize, attention.py:118).  Input = virtual concat [x0 | x1] as in the forward; dy bf16
+ * [B*HW, c0+c1]; optional add0/add1 (bf16, row strides ld_add0/ld_add1) are accumulated into the
+ * result (the gradient arriving through the ResBlock skip path); outputs dx0 [B*HW, c0],
+ * dx1 [B*HW, c1].  workspace: cd360_groupnorm_bwd_workspace_floats(B) floats. */
+int64_t cd360_groupnorm_bwd_workspace_floats(int32_t batch);
+int cd360_groupnorm_silu_bwd_bf16(const void* x0, int32_t c0, const void* x1, int32_t c1,
+                                  const float* gamma, const float* beta, const void* dy,
+                                  const void* add0, int64_t ld_add0, const void* add1,
+                                  int64_t ld_add1, void* dx0, void* dx1, float* workspace,
+                                  int32_t batch, int32_t hw, float eps, int32_t apply_silu,
+                                  cd360_stream_t stream);
+
+/* GEGLU backward (attention.py:94-96).  raw bf16 [rows, 2f] = pre-activation [a | gate] interleaved
+ * in blocks of `block` columns (block = f: chunk(2) layout; block = cd360_geglu_pack_block(2f): the
+ * packed-weight layout), dh bf16 [rows, f] -> draw bf16 [rows, 2f] in the same column order. */
+int cd360_geglu_bwd_bf16(const void* raw, const void* dh, void* draw, int64_t rows, int32_t f,
+                         int32_t block, cd360_stream_t stream);
+
+/* out = a + b, bf16, n % 8 == 0 (sum of the gradients arriving at a skip connection,
+ * openaimodel.py:1074). */
+int cd360_add_bf16(const void* a, const void* b, void* out, int64_t n, cd360_stream_t stream);
+
+/* in [rows, cols] (bf16, or fp32 if in_is_fp32; row stride ld_in) -> out bf16 [cols, ld_out] with
+ * out[c][r] = in[r][c], zero for r in [rows, ld_out): the K-major operand of a weight-gradient GEMM. */
+int cd360_transpose_to_bf16(const void* in, int32_t in_is_fp32, int64_t ld_in, void* out,
+                            int64_t ld_out, int32_t rows, int32_t cols, cd360_stream_t stream);
+
+/* out[c] += sum_r x[r, c] (bias gradients); x bf16 [rows, c] row stride ld; out fp32, zeroed by the caller. */
+int cd360_colsum_bf16(const void* x, int64_t ld, float* out, int64_t rows, int32_t c,
+                      cd360_stream_t stream);
+
+/* Backward of cd360_im2col3x3_s2_bf16 (Downsample, openaimodel.py:215-222):
+ * dcol bf16 [B*(H/2)*(W/2), 9*C] -> dx bf16 [B*H*W, C]. */
+int cd360_col2im3x3_s2_bf16(const void* dcol, void* dx, int32_t batch, int32_t h, int32_t w,
+                            int32_t c, cd360_stream_t stream);
+/* Backward of cd360_upsample_nearest2x_bf16: g bf16 [B, 2h, 2w, C] -> dx [B, h, w, C]. */
+int cd360_upsample_nearest2x_bwd_bf16(const void* g, void* dx, int32_t batch, int32_t h, int32_t w,
+                                      int32_t c, cd360_stream_t stream);
+
+/* Backward of cd360_nerf_volrender (VolRender, nerfsd_pytorch3d.py:170-231; trunc_exp backward
+ * attention.py:201-205).  d_rendered bf16 [b*hw, c]; dfg [b,hw], dalphas [b,hw,d], drgb [b,hw,3]
+ * fp32 or NULL.  Outputs dfeats bf16 [b,hw,d,c] and draw bf16 [b,hw,d,8] = gradient of the raw
+ * decoder outputs (rgb 3, sigma 1, 4 zero columns: the K-padded GEMM operand). */
+int cd360_nerf_volrender_bwd(const void* feats, const float* raw, const float* dists,
+                             const void* d_rendered, const float* dfg, const float* dalphas,
+                             const float* drgb, void* dfeats, void* draw, int32_t b, int32_t hw,
+                             int32_t d, int32_t c, cd360_stream_t stream);
+/* Backward of cd360_nerf_combine.  ds bf16 [b, hw*d, c] -> dhpre bf16 [b, n, hw*d, c], dlogit fp32
+ * [b, n, hw*d], and dg fp32 [b, n, hw, ldg] (zeroed by the caller; bilinear scatter by atomics:
+ * columns [0,c) gradient of the hoisted first Linear's output, column c of the nviews feature term). */
+int cd360_nerf_combine_bwd(const void* g, int64_t ldg, const void* hpre, const int32_t* gidx,
+                           const float* gwgt, const float* vlogit, const void* ds, void* dhpre,
+                           float* dlogit, float* dg, int32_t b, int32_t n, int32_t hw, int32_t d,
+                           int32_t c, cd360_stream_t stream);
+/* Gradient of the geometry columns of nviews.weight (nerfsd_pytorch3d.py:139-151): dw fp32 [198],
+ * zeroed by the caller; dlogit fp32 [b, n, pts]. */
+int cd360_nerf_nviews_geo_bwd(const float* cams, const float* dlogit, float* dw, int32_t b, int32_t n,
+                              int64_t pts, cd360_stream_t stream);
+
+/* Denoising loss and its gradient (loss.py:173-181 'l2', EpsWeighting, EpsScaling):
+ * eps fp32 tokens [b*hw, 4]; x_noisy, target fp32 NCHW [b,4,hw]; sigma [b]; mask fp32 [b,hw] or NULL.
+ * loss[b]; mask_sum[b] (optional); deps bf16 [b*hw, ldd] = d(coef * sum_b loss_b)/d eps, zero padded. */
+int cd360_diffusion_loss(const float* eps, const float* x_noisy, const float* target,
+                         const float* sigma, const float* mask, float coef, float* loss,
+                         float* mask_sum, void* deps, int32_t batch, int32_t hw, int32_t ldd,
+                         cd360_stream_t stream);
+/* FeatureNeRF supervision of one pose block and its gradients (loss.py:183-206,
+ * diffusion.py:221-236).  loss3 fp32 [b, 3] = (fg, bg, rgb); gradients pre-multiplied by the
+ * per-image weights wfg / wbg / wrgb.  rgb NULL = no rgb term. */
+int cd360_nerf_aux_loss(const float* fg, const float* alphas, const float* rgb, const float* op,
+                        const float* mask_s, const float* tgt, const float* mask_sum,
+                        const float* wfg, const float* wbg, const float* wrgb, float* loss3,
+                        float* dfg, float* dalphas, float* drgb, int32_t batch, int32_t hw, int32_t d,
+                        cd360_stream_t stream);
+/* F.interpolate(mode='bilinear', antialias=True) of the supervision maps (loss.py:186,199-200):
+ * in fp32 [planes, ih, iw] -> out [planes, oh, ow] = out_scale * resized + out_shift. */
+int cd360_resize_bilinear_aa(const float* in, float* out, int32_t planes, int32_t ih, int32_t iw,
+                             int32_t oh, int32_t ow, float out_scale, float out_shift,
+                             cd360_stream_t stream);
+/* AdamW on flat fp32 buffers (torch.optim.AdamW, the default optimizer_config; diffusion.py:310-373).
+ * step >= 1 is the 1-based step count; g is multiplied by grad_scale first. */
+int cd360_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                     cd360_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
