@@ -5,7 +5,17 @@ Kept: constructor config keys, `.model` (OpenAIWrapper) / `.model.diffusion_mode
 `clear_rendered_feat()`, trainable-parameter selection by name (`trainkeys`).
 Out of scope here: the text conditioner and the VAE first stage
 are not instantiated — callers feed `cond` / `uc` embeddings and receive latents; Lightning is
-not required (plain nn.Module).  Training (`training_step`) is a later row.
+not required (plain nn.Module).
+
+Training (`training_step`, reference :221-272): there is no autograd on this path — `forward`
+evaluates the loss through the taped UNet forward and immediately runs the explicit backward
+(sgm/modules/train_path.py), leaving the gradients of the trainable (pose) parameters in `.grad`;
+`configure_optimizers()` returns the fused AdamW over the flattened pose parameters
+(sgm/optim.py), whose `step()` also performs the data-parallel gradient all-reduce.  Inputs are
+LATENTS (the VAE is outside SURVEY §8): batch[input_key] = x [b,4,L,L], batch[input_key + "_ref"]
+= reference latents [b,n,4,L,L], batch["cond"] = {"crossattn": [b+b*n,77,ctx], "vector":
+[b+b*n,adm]} (what the conditioner would emit), plus pose / mask / depth (opacity) / drop_im /
+rgb (the image for the rgb term) as in the reference's data loader.
 """
 from __future__ import annotations
 
@@ -57,6 +67,11 @@ class DiffusionEngine(nn.Module):
         self.conditioner_config = conditioner_config
         self.first_stage_config = first_stage_config
         self.loss_fn_config = loss_fn_config
+        self.loss_fn = instantiate_from_config(loss_fn_config) if loss_fn_config is not None else None
+        self.optimizer_config = optimizer_config if optimizer_config is not None else {"target": "torch.optim.AdamW"}
+        self.scheduler_config = scheduler_config
+        self.learning_rate = 1.0e-4   # base_learning_rate of the shipped yaml; main.py:1019-1050 overrides
+        self.global_step = 0
         self.conditioner = None
         self.first_stage_model = None
         # trainable set by parameter name (reference :119-147)
@@ -107,3 +122,74 @@ class DiffusionEngine(nn.Module):
         self._fused = step
         samples = self.sampler.sample_fused(step, x, num_steps=num_steps)
         return (samples, None) if return_rgb else samples
+
+    # ---- training (reference :204-272, 310-373) ----------------------------------------------------
+    def get_input(self, batch):
+        k = self.input_key
+        return (batch[k], batch.get(k + "_ref"), batch.get("pose"), batch.get("mask"), batch.get("mask_ref"),
+                batch.get("depth"), batch.get("drop_im", 0.0))
+
+    def forward(self, x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward: bool = True):
+        """Loss of one batch (reference :221-236) and — the autograd replacement — the gradients of
+        the trainable parameters in `.grad`.  Returns (loss_mean tensor, loss_dict)."""
+        loss, loss_fg, loss_bg, loss_rgb = self.loss_fn(self.model, self.denoiser, self.conditioner, x, x_rgb,
+                                                        xr, pose, mask, mask_ref, opacity, batch)
+        b = x.shape[0]
+        dev = x.device
+        loss_mean = loss.mean()
+        loss_dict = {"loss": loss_mean.item()}
+        drop = torch.as_tensor(drop_im, dtype=torch.float32, device=dev).reshape(-1).expand(b) \
+            if not torch.is_tensor(drop_im) or drop_im.numel() == 1 else drop_im.float().reshape(-1).to(dev)
+        w_fg = w_bg = w_rgb = None
+        if self.rgb and self.global_step > 0 and torch.is_tensor(loss_fg):
+            k = loss_fg.shape[1]
+            lf = (loss_fg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+            lb = (loss_bg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+            loss_mean = loss_mean + self.loss_fg_lambda * lf + self.loss_bg_lambda * lb
+            loss_dict["loss_fg"], loss_dict["loss_bg"] = lf.item(), lb.item()
+            w_fg = self.loss_fg_lambda * drop / (k * (drop.sum() + 1e-12))
+            w_bg = self.loss_bg_lambda * drop / (k * (drop.sum() + 1e-12))
+        if self.rgb_predict and torch.is_tensor(loss_rgb) and loss_rgb.mean() > 0:
+            k = loss_rgb.shape[1]
+            lr_ = (loss_rgb.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+            loss_mean = loss_mean + self.loss_rgb_lambda * lr_
+            loss_dict["loss_rgb"] = lr_.item()
+            w_rgb = self.loss_rgb_lambda * drop / (k * (drop.sum() + 1e-12))
+        if backward:
+            self.loss_fn.backward(1.0 / b, w_fg, w_bg, w_rgb)
+        return loss_mean, loss_dict
+
+    def shared_step(self, batch, backward: bool = True):
+        x, xr, pose, mask, mask_ref, opacity, drop_im = self.get_input(batch)
+        x_rgb = batch.get("rgb")
+        if xr is not None and torch.is_tensor(drop_im):
+            bb = xr.shape[0]
+            xr = drop_im.reshape(bb, 1, 1, 1, 1).to(xr) * xr          # reference :246
+        batch["global_step"] = self.global_step
+        return self(x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward=backward)
+
+    def training_step(self, batch, batch_idx=0):
+        """Loss + gradients of one batch (the Lightning hook of the reference, :251-272; here the
+        caller owns the loop: `opt.zero_grad(); loss = engine.training_step(batch); opt.step()`)."""
+        loss, loss_dict = self.shared_step(batch)
+        self.last_loss_dict = loss_dict
+        return loss
+
+    def configure_optimizers(self, group=None):
+        """AdamW over the trainable parameters selected by `trainkeys` (reference :310-373; the
+        conditioner's token rows are outside this build).  `group`: torch.distributed process group
+        for the data-parallel gradient all-reduce (None = default group if initialised)."""
+        from ..optim import PoseAdamW
+        cfg = dict(self.optimizer_config.get("params", {}))
+        target = self.optimizer_config.get("target", "torch.optim.AdamW")
+        if not target.endswith("AdamW"):
+            raise NotImplementedError(f"optimizer {target}: only AdamW (the reference default) is built")
+        named = [(n, p) for n, p in self.model.diffusion_model.named_parameters() if p.requires_grad]
+        opt = PoseAdamW(named, lr=self.learning_rate, group=group, **cfg)
+        opt.on_step = self._after_optimizer_step
+        return opt
+
+    def _after_optimizer_step(self):
+        self.global_step += 1
+        from ..modules.attention import invalidate_all_packed
+        invalidate_all_packed(self.model.diffusion_model, only_trainable=True)

@@ -63,13 +63,23 @@ class _Packed:
         self.__dict__["_pk"] = None
 
 
-def invalidate_all_packed(root: nn.Module):
+def invalidate_all_packed(root: nn.Module, only_trainable: bool = False):
+    """Drop the packed operand copies so they are rebuilt from the parameters.  only_trainable: just
+    those of the pose weights (after an optimiser step; the frozen packs stay)."""
     for m in root.modules():
+        if only_trainable:
+            if hasattr(m, "pose_emb_layers"):
+                m.pose_emb_layers.invalidate_packed()
+                m.pose_featurenerf.model._packed = None
+                m.__dict__.pop("_bwdpk_pose", None)
+            continue
         if isinstance(m, _Packed):
             m.invalidate_packed()
         if hasattr(m, "_packed"):
             m._packed = None
         m.__dict__.pop("_lnpk", None)
+        m.__dict__.pop("_bwdpk", None)   # transposed / tap-flipped packs of the training backward
+        m.__dict__.pop("_bwdpk_pose", None)
 
 
 class Linear(nn.Linear, _Packed):

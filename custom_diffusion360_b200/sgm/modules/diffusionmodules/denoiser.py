@@ -39,6 +39,30 @@ class Denoiser(nn.Module):
         return predict * c_out + input * c_skip, fg, alphas, rgbs
 
 
+    def train_forward(self, network, input, sigma, cond, sigmas_ref=None, input_ref=None, pose=None,
+                      noise_ref2=None, jitter=None):
+        """The training-time call (denoiser.py:22-44) up to the network output: quantise σ, noise the
+        reference latents a second time (:26-33 — the loss already noised them once, loss.py:163-170;
+        kept as in the reference), scale them by c_in(σ_ref) (:35-38), run the taped network with
+        c_in folded into the input convolution's load.  Returns (eps fp32 tokens [b*hw, 4], aux,
+        tape, quantised σ [b]); `D = eps c_out + input c_skip` is folded into the loss kernel."""
+        sigma = self.possibly_quantize_sigma(sigma)
+        kwargs = dict(pose=pose, jitter=jitter)
+        if sigmas_ref is not None and input_ref is not None:
+            n2 = noise_ref2.to(input_ref.device) if noise_ref2 is not None else torch.randn_like(input_ref)
+            input_ref = input_ref + n2 * append_dims(sigmas_ref, input_ref.ndim)
+            _, _, c_in_ref, _ = self.scaling(append_dims(sigmas_ref, input_ref.ndim))
+            kwargs["input_ref"] = (input_ref * c_in_ref).float().contiguous()
+            kwargs["sigmas_ref"] = self.possibly_quantize_c_noise(sigmas_ref)
+        elif input_ref is not None:
+            kwargs["input_ref"] = input_ref.float().contiguous()
+        _, _, c_in, c_noise = self.scaling(sigma)
+        c_noise = self.possibly_quantize_c_noise(c_noise)
+        eps_tok, aux, tape = network.train_forward(input, c_noise, cond, in_scale=c_in.float().contiguous(),
+                                                   **kwargs)
+        return eps_tok, aux, tape, sigma
+
+
 class DiscreteDenoiser(Denoiser):
     def __init__(self, weighting_config, scaling_config, num_idx, discretization_config,
                  do_append_zero=False, quantize_c_noise=True, flip=True):

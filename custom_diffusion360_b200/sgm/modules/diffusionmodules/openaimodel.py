@@ -405,6 +405,41 @@ class UNetModel(nn.Module, _Packed):
         rgb = [a[2] for a in aux] if self.rgb_predict else []
         return eps, fg, al, rgb
 
+    # ---- training step (explicit backward) ------------------------------------------
+    def forward_train(self, x, timesteps=None, context=None, y=None, *, pose=None, input_ref=None,
+                      sigmas_ref=None, in_scale=None, jitter=None, **_ignored):
+        """The training-time call of the reference (openaimodel.py:1008-1093 with `input_ref`):
+        the reference latents input_ref [b, n, 4, L, L] run as the no-grad reference stream
+        (timesteps `sigmas_ref` broadcast over the views; second halves of context / y), the main
+        stream runs taped.  Returns (eps fp32 tokens [b*L*L, 4], aux [(pose block, (fg [b,hw],
+        alphas [b,hw,d], rgb [b,hw,3]))] in execution order, tape) for `backward`."""
+        from .. import train_path
+        b, n = input_ref.shape[:2]
+        assert context.shape[0] == b + b * n and y.shape[0] == b + b * n, \
+            "context / y must hold the b target rows followed by the b*n reference rows"
+        sig = sigmas_ref if sigmas_ref is not None else torch.zeros_like(timesteps)
+        t_ref = sig.reshape(b, 1).expand(b, n).reshape(b * n)
+        with torch.no_grad():
+            caps = self.capture_references(input_ref.reshape(b * n, *input_ref.shape[2:]), t_ref,
+                                           context[b:], y[b:])
+        blocks = dict(self.pose_blocks())
+        for name, m in blocks.items():
+            t = caps[name]
+            m.__dict__["_live_ctxref"] = (t.reshape(-1, t.shape[-1]), n)
+            m._ctxref_cache = None
+        try:
+            return train_path.unet_forward(self, x, timesteps, context[:b], y[:b], pose, in_scale, jitter)
+        finally:
+            for m in blocks.values():
+                m.__dict__.pop("_live_ctxref", None)
+                m._ctxref_cache = None
+
+    def backward(self, tape, deps, daux_of=None):
+        """Gradients of the pose weights (into `.grad`, fp32) from deps = dL/d(eps tokens) bf16
+        [b*L*L, 64] (columns >= 4 zero) and daux_of = {id(pose block): (dfg, dalphas, drgb)}."""
+        from .. import train_path
+        train_path.unet_backward(self, tape, deps, daux_of or {})
+
     def forward_tokens(self, x, timesteps, context, y, pose=None, in_scale=None, batch=None):
         """Same as forward but returns eps in token layout: fp32 [B*L*L, out_channels].
         in_scale: optional fp32 [B] multiplied into x on load (the denoiser's c_in).

@@ -23,3 +23,8 @@ class OpenAIWrapper(IdentityWrapper):
             x = torch.cat((x, concat.type_as(x)), dim=1)
         return self.diffusion_model(x, timesteps=t, context=c.get("crossattn", None),
                                     y=c.get("vector", None), **kwargs)
+
+    def train_forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, **kwargs):
+        """Taped forward of the training step (UNetModel.forward_train); same dict -> kwargs mapping."""
+        return self.diffusion_model.forward_train(x, timesteps=t, context=c.get("crossattn", None),
+                                                  y=c.get("vector", None), **kwargs)

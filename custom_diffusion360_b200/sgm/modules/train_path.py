@@ -1,0 +1,484 @@
+"""Training forward + explicit backward of the pose-conditioned UNet on the sm_100a kernels.
+
+Reference: `DiffusionEngine.training_step` -> `StandardDiffusionLossImgRef.__call__` -> denoiser ->
+`UNetModel.forward` with `input_ref` (sgm/models/diffusion.py:221-272, loss.py:140-216,
+openaimodel.py:975-1093), differentiated by torch.autograd.  Only the pose weights train
+(`trainkeys: pose`, diffusion.py:139-144): `pose_emb_layers.weight` and the FeatureNeRF MLP
+(`pose_featurenerf.model.{plane_coefs.0,plane_coefs.2,nviews,decoder}`) of every pose block.
+
+There is no autograd here.  The main stream runs once in "taped" form (out-of-place residual
+updates, the activations the backward needs are kept), then `unet_backward` walks the tape in
+reverse and launches, per layer, the gradient kernels:
+  * dX of every Linear / 1x1 / 3x3 conv = the tcgen05 GEMM over transposed / tap-flipped weight
+    packs built once (`bwd_pack`);
+  * attention, LayerNorm, GroupNorm+SiLU, GEGLU, resampling, FeatureNeRF gather / view-softmax /
+    volume rendering: the dedicated backward kernels of csrc/train.cu and csrc/attention_bwd.cu;
+  * dW of the (few, small) trainable Linears = GEMMs over transposed operands, fp32 out.
+The walk stops at the first pose block in forward order: nothing upstream of it is trainable.
+The reference-image stream is `no_grad` in the reference (attention.py:851-868) and stays a plain
+forward here (`UNetModel.capture_references`).
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace as NS
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..prepack import pack_conv3x3_bwd, transposed
+from .attention import BasicTransformerBlock, SpatialTransformer
+from .nerfsd_pytorch3d import KPE
+from .utils_cameraray import patch_ray_xy
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------------
+# backward weight packs (built lazily, once per module; invalidated with the forward packs)
+# ------------------------------------------------------------------------------------------------
+def bwd_pack(m) -> dict:
+    p = m.__dict__.get("_bwdpk")
+    dev = next(m.parameters()).device
+    if p is not None and p["dev"] == dev:
+        return p
+    from .diffusionmodules import openaimodel as U  # late: avoid an import cycle
+
+    p = dict(dev=dev)
+    if isinstance(m, BasicTransformerBlock):
+        a1, a2 = m.attn1, m.attn2
+        p1, p2 = a1.packed(), a2.packed()
+        p.update(wqkv_t=transposed(p1["wqkv"]), wo1_t=transposed(p1["wo"]),
+                 wq2_t=transposed(p2["wq"]), wo2_t=transposed(p2["wo"]),
+                 wff_t=transposed(m.ff.net[0].packed()["w"]),        # packed (interleaved) row order
+                 w2_t=transposed(m.ff.net[2].packed()["w"]),
+                 g1=m.norm1.packed()["g"], g2=m.norm2.packed()["g"], g3=m.norm3.packed()["g"])
+    elif isinstance(m, SpatialTransformer):
+        p.update(win_t=transposed(m.proj_in.packed()["w"]), wout_t=transposed(m.proj_out.packed()["w"]))
+    elif isinstance(m, U.ResBlock):
+        p.update(w1=pack_conv3x3_bwd(m.in_layers[2].weight.detach()),
+                 w2=pack_conv3x3_bwd(m.out_layers[3].weight.detach()))
+        fp = m.packed()
+        if "ws" in fp:
+            p["ws_t"] = transposed(fp["ws"])
+    elif isinstance(m, U.Downsample):
+        p["w_t"] = transposed(m.packed()["w"])
+    elif isinstance(m, U.Upsample):
+        p["w"] = pack_conv3x3_bwd(m.conv.weight.detach())
+    elif isinstance(m, U.UNetModel):
+        p["cout"] = pack_conv3x3_bwd(m.out[2].weight.detach(), cout_pad=64)
+    else:
+        raise TypeError(type(m))
+    m.__dict__["_bwdpk"] = p
+    return p
+
+
+def pose_bwd_pack(block: BasicTransformerBlock) -> dict:
+    """Transposed packs of the TRAINABLE weights of a pose block (rebuilt after every optimiser
+    step, unlike the frozen packs above)."""
+    p = block.__dict__.get("_bwdpk_pose")
+    dev = block.pose_emb_layers.weight.device
+    if p is not None and p["dev"] == dev:
+        return p
+    c = block.pose_emb_layers.weight.shape[0]
+    wp = block.pose_emb_layers.packed()["w"]
+    pk = block.pose_featurenerf.model.packed()
+    wd8 = torch.zeros(8, c, device=dev, dtype=bf16)
+    wd8[: pk["wd"].shape[0]] = pk["wd"]
+    p = dict(dev=dev, wp_x_t=transposed(wp[:, :c]), wp_r_t=transposed(wp[:, c:]),
+             w2n_t=transposed(pk["w2"]), wd_t8=transposed(wd8))
+    block.__dict__["_bwdpk_pose"] = p
+    return p
+
+
+def _grad_buf(param: torch.nn.Parameter) -> torch.Tensor:
+    """fp32 gradient storage of a trainable parameter (a view of the flat gradient buffer when the
+    optimiser has flattened the parameters; allocated on first use otherwise)."""
+    if param.grad is None:
+        param.grad = torch.zeros_like(param, dtype=f32)
+    return param.grad
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor):
+    """out[N, K] (fp32, may be a strided view) = dy^T x for dy bf16/fp32 [M, N], x bf16 [M, K]."""
+    return ops.gemm(ops.transpose_to_bf16(dy), ops.transpose_to_bf16(x), out=out)
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureNeRF: reference_attn forward (taped) and backward
+# ------------------------------------------------------------------------------------------------
+def nerf_bins(nerf, hw: int, dev, jitter: Optional[dict]):
+    """(xy [hw,2], depths [hw,d], dists [hw,d]).  With `jitter` = {"xy_rand": (rx [res+1], ry [res+1]),
+    "t_rand": [hw, d+1]} (one such dict per pose block and call) the stratified training-time sampling of the reference is reproduced from
+    the INJECTED uniform variates (get_patch_raybundle, utils_cameraray.py:111-140;
+    Raymarcher.stratified_sampling, nerfsd_pytorch3d.py:317-325) — parity needs the same random
+    numbers, not the same generator."""
+    res = int(math.sqrt(hw))
+    rm = nerf.raymarcher
+    if not jitter:
+        depths, dists = rm.bins(hw, dev)
+        return patch_ray_xy(res, dev), depths, dists
+
+    def jittered_positions(r):
+        edges = torch.linspace(1, -1, res + 1, dtype=f32)
+        center = (edges[1:] + edges[:-1]) / 2.0
+        upper = torch.cat([center, edges[-1:]], -1)
+        lower = torch.cat([edges[:1], center], -1)
+        return (lower + (upper - lower) * r.float().cpu())[:-1]
+
+    xr, yr = jitter["xy_rand"]
+    hpos, vpos = jittered_positions(xr), jittered_positions(yr)
+    xs = hpos[None, :].expand(res, res)
+    ys = vpos[:, None].expand(res, res)
+    xy = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1).contiguous().to(dev)
+    lower = rm.lengths_lower.to(device=dev, dtype=f32)
+    upper = rm.lengths_upper.to(device=dev, dtype=f32)
+    jit = lower[None] + (upper - lower)[None] * jitter["t_rand"].to(device=dev, dtype=f32)
+    depths = ((jit[:, :-1] + jit[:, 1:]) / 2.0).contiguous()
+    dists = (jit[:, 1:] - jit[:, :-1]).contiguous()
+    return xy, depths, dists
+
+
+def nerf_forward(block: BasicTransformerBlock, cams, xref_tok, n, kv, nkv, batch, hw, jitter=None):
+    """reference_attn (attention.py:571-598) keeping what the backward needs.
+    Returns (rendered bf16 [batch*hw, c], (fg, alphas, rgb), saved)."""
+    nerf = block.pose_featurenerf
+    if not nerf.rgb_predict:
+        raise NotImplementedError("training path is built for rgb_predict=True (the shipped config)")
+    pk = nerf.model.packed()
+    c, d = pk["c"], nerf.raymarcher.num_samples
+    res = int(math.sqrt(hw))
+    dev = xref_tok.device
+    xy, depths, dists = nerf_bins(nerf, hw, dev, jitter)
+    g = ops.gemm(xref_tok, pk["wg"])
+    pe, gidx, gwgt, vlogit = ops.nerf_points(cams, xy, depths, pk["wnv_geo"], pk["bnv"], batch, n, res, d, KPE)
+    hpre = ops.gemm(pe, pk["w1p"], bias=pk["b1"])
+    s, _ = ops.nerf_combine(g, hpre, gidx, gwgt, vlogit, batch, n, hw, d, c)
+    final = ops.gemm(s, pk["w2"], bias=pk["b2"])
+    raw = ops.gemm(final, pk["wd"], out_fp32=True)                      # [P', 4] (rgb 3, sigma 1)
+    a2 = block.attn2
+    p2 = a2.packed()
+    inner = a2.heads * a2.dim_head
+    q = ops.gemm(block.norm2.tokens(final), p2["wq"])
+    k, v = kv[:, :inner], kv[:, inner:2 * inner]
+    att = ops.attention(q, k, v, batch, a2.heads, hw * d, nkv, ldq=inner, ldk=kv.stride(0), ldv=kv.stride(0))
+    feats2 = ops.gemm(att, p2["wo"], bias=p2["bo"], residual=final)
+    rendered, fg, alphas, rgb = ops.nerf_volrender(feats2, raw, dists, batch, hw, d, c)
+    saved = NS(cams=cams, xref=xref_tok, n=n, g=g, pe=pe, gidx=gidx, gwgt=gwgt, vlogit=vlogit, hpre=hpre,
+               s=s, final=final, raw=raw, q=q, k=k, v=v, att=att, feats2=feats2, dists=dists, nkv=nkv,
+               batch=batch, hw=hw, d=d, c=c)
+    return rendered, (fg, alphas, rgb), saved
+
+
+def nerf_backward(block: BasicTransformerBlock, sv, d_rendered, daux):
+    """Gradients of the FeatureNeRF weights of `block` from d(rendered) and the gradients of the
+    supervised outputs daux = (dfg [b,hw], dalphas [b,hw,d], drgb [b,hw,3]) (any may be None)."""
+    bp = bwd_pack(block)
+    pp = pose_bwd_pack(block)
+    model = block.pose_featurenerf.model
+    a2 = block.attn2
+    b, hw, d, c, n = sv.batch, sv.hw, sv.d, sv.c, sv.n
+    dfg, dal, drgb = daux if daux is not None else (None, None, None)
+    dfeats2, draw8 = ops.nerf_volrender_bwd(sv.feats2, sv.raw, sv.dists, d_rendered, dfg, dal, drgb, b, hw, d, c)
+    # feats2 = final + to_out(attn(to_q(LN2 final), K, V))   (the block's own norm2 / attn2, frozen)
+    da = ops.gemm(dfeats2, bp["wo2_t"])
+    dq = torch.empty_like(sv.q)
+    ops.attention_bwd(sv.q, sv.k, sv.v, sv.att, da, b, a2.heads, hw * d, sv.nkv, dq=dq)
+    dfn = ops.gemm(dq, bp["wq2_t"])
+    dfinal = ops.layernorm_bwd(sv.final, bp["g2"], dfn, add=dfeats2, eps=block.norm2.eps)
+    # raw = final Wd^T
+    dfinal = ops.gemm(draw8, pp["wd_t8"], residual=dfinal, out=dfinal)
+    dwd = ops.gemm(ops.transpose_to_bf16(draw8), ops.transpose_to_bf16(sv.final), out_fp32=True)   # [8, c]
+    _grad_buf(model.decoder.weight).copy_(dwd[: model.decoder.weight.shape[0]])
+    # final = S W2^T + b2
+    _wgrad(dfinal, sv.s, _grad_buf(model.plane_coefs[2].weight))
+    ops.colsum(dfinal, out=_grad_buf(model.plane_coefs[2].bias).zero_())
+    ds = ops.gemm(dfinal, pp["w2n_t"])
+    # gather / SiLU / view softmax
+    dhpre, dlogit, dg = ops.nerf_combine_bwd(sv.g, sv.hpre, sv.gidx, sv.gwgt, sv.vlogit, ds, b, n, hw, d, c)
+    # hpre = pe W1p^T + b1  |  G = xref [W1f ; w_nv_f]^T
+    dw1 = _grad_buf(model.plane_coefs[0].weight)                                   # [c, c + 198]
+    dw1p = ops.gemm(ops.transpose_to_bf16(dhpre), ops.transpose_to_bf16(sv.pe), out_fp32=True)  # [c, KPE]
+    dw1[:, c:].copy_(dw1p[:, :198])
+    ops.colsum(dhpre, out=_grad_buf(model.plane_coefs[0].bias).zero_())
+    dwg = ops.gemm(ops.transpose_to_bf16(dg[:, : c + 8]), ops.transpose_to_bf16(sv.xref), out_fp32=True)  # [c+8, c]
+    dw1[:, :c].copy_(dwg[:c])
+    dnv = _grad_buf(model.nviews.weight)                                           # [1, c + 198]
+    dnv[0, :c].copy_(dwg[c])
+    dnv[0, c:].copy_(ops.nerf_nviews_geo_bwd(sv.cams, dlogit, b, n))
+    _grad_buf(model.nviews.bias).zero_()                                           # sum_v dlogit_v == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# BasicTransformerBlock
+# ------------------------------------------------------------------------------------------------
+def block_forward(block: BasicTransformerBlock, x, batch, n, kv, nctx, cams=None, jitter=None):
+    """Taped `BasicTransformerBlock._forward` (attention.py:600-637) in token layout.  Residual
+    updates are out of place: every saved tensor stays valid until the backward."""
+    a1, a2 = block.attn1, block.attn2
+    p1, p2 = a1.packed(), a2.packed()
+    inner = a1.heads * a1.dim_head
+    qkv = ops.gemm(block.norm1.tokens(x), p1["wqkv"])
+    att1 = ops.attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], batch, a1.heads, n, n,
+                         ldq=3 * inner, ldk=3 * inner, ldv=3 * inner)
+    x1 = ops.gemm(att1, p1["wo"], bias=p1["bo"], residual=x)
+    q2 = ops.gemm(block.norm2.tokens(x1), p2["wq"])
+    k2, v2 = kv[:, :inner], kv[:, inner:2 * inner]
+    att2 = ops.attention(q2, k2, v2, batch, a2.heads, n, nctx, ldq=inner, ldk=kv.stride(0), ldv=kv.stride(0))
+    x2 = ops.gemm(att2, p2["wo"], bias=p2["bo"], residual=x1)
+    sv = NS(x0=x, qkv=qkv, att1=att1, x1=x1, q2=q2, k2=k2, v2=v2, att2=att2, x2=x2, batch=batch, n=n,
+            nctx=nctx, inner=inner, nerf=None, rendered=None)
+    aux = None
+    x3 = x2
+    if block.image_cross and cams is not None:
+        xref_tok = block.context_ref_tokens(batch)
+        n_views = block._ctxref_cache[2]
+        rendered, aux, sv.nerf = nerf_forward(block, cams, xref_tok, n_views, kv, nctx, batch, n,
+                                              next(jitter) if jitter is not None else None)
+        sv.rendered = rendered
+        x3 = block.pose_emb_layers.tokens(x2, a1=rendered)
+    sv.x3 = x3
+    x4 = block.ff.tokens(block.norm3.tokens(x3), residual=x3)
+    return x4, aux, sv
+
+
+def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
+    """g = dL/d(block output) bf16 [M, c] -> dL/d(block input), or None when the walk stops at this
+    block's pose layers (`stop_here`: nothing upstream is trainable)."""
+    bp = bwd_pack(block)
+    ff = block.ff
+    blk = ops.geglu_pack_block(ff.net[0].proj.out_features)
+    # ---- feed-forward: x4 = x3 + W2 geglu(Wff LN3(x3) + bff) + b2
+    dh = ops.gemm(g, bp["w2_t"])
+    pk = ff.net[0].packed()
+    raw = ops.gemm(block.norm3.tokens(sv.x3), pk["w"], bias=pk["b"])        # recomputed, packed column order
+    draw = ops.geglu_bwd(raw, dh, blk)
+    del raw, dh
+    g = ops.layernorm_bwd(sv.x3, bp["g3"], ops.gemm(draw, bp["wff_t"]), add=g, eps=block.norm3.eps)
+    del draw
+    # ---- pose_emb_layers: x3 = [x2 | rendered] Wp^T
+    if sv.nerf is not None:
+        c = sv.x2.shape[1]
+        dwp = _grad_buf(block.pose_emb_layers.weight)                       # [c, 2c]
+        gt = ops.transpose_to_bf16(g)
+        ops.gemm(gt, ops.transpose_to_bf16(sv.x2), out=dwp[:, :c])
+        ops.gemm(gt, ops.transpose_to_bf16(sv.rendered), out=dwp[:, c:])
+        pp = pose_bwd_pack(block)
+        nerf_backward(block, sv.nerf, ops.gemm(g, pp["wp_r_t"]), daux)
+        if stop_here:
+            return None
+        g = ops.gemm(g, pp["wp_x_t"])
+    # ---- text cross-attention (K / V: projections of the constant context, no gradient)
+    a1, a2 = block.attn1, block.attn2
+    da = ops.gemm(g, bp["wo2_t"])
+    dq = torch.empty_like(sv.q2)
+    ops.attention_bwd(sv.q2, sv.k2, sv.v2, sv.att2, da, sv.batch, a2.heads, sv.n, sv.nctx, dq=dq)
+    g = ops.layernorm_bwd(sv.x1, bp["g2"], ops.gemm(dq, bp["wq2_t"]), add=g, eps=block.norm2.eps)
+    # ---- self-attention
+    inner = sv.inner
+    da = ops.gemm(g, bp["wo1_t"])
+    dqkv = torch.empty_like(sv.qkv)
+    ops.attention_bwd(sv.qkv[:, :inner], sv.qkv[:, inner:2 * inner], sv.qkv[:, 2 * inner:], sv.att1, da,
+                      sv.batch, a1.heads, sv.n, sv.n, dq=dqkv[:, :inner], dk=dqkv[:, inner:2 * inner],
+                      dv=dqkv[:, 2 * inner:])
+    return ops.layernorm_bwd(sv.x0, bp["g1"], ops.gemm(dqkv, bp["wqkv_t"]), add=g, eps=block.norm1.eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# SpatialTransformer / ResBlock / resampling
+# ------------------------------------------------------------------------------------------------
+def st_forward(st: SpatialTransformer, x, batch, hw, nctx, kv_all, cams, aux_out, jitter=None):
+    p = st.packed()
+    xn = ops.groupnorm(x, p["g"], p["b"], batch, hw, eps=st.norm.eps, silu=False)
+    h = st.proj_in.tokens(xn)
+    saved = []
+    for i, block in enumerate(st.transformer_blocks):
+        use_pose = st.image_cross and (i % st.poscontrol_interval == 0)
+        off, width = block.__dict__["_kv_slice"]
+        h, aux, sv = block_forward(block, h, batch, hw, kv_all[:, off:off + width], nctx,
+                                   cams if use_pose else None, jitter)
+        if aux is not None:
+            aux_out.append((block, aux))
+        saved.append(sv)
+    out = st.proj_out.tokens(h, residual=x)
+    return out, NS(x=x, blocks=saved, batch=batch, hw=hw)
+
+
+def st_backward(st: SpatialTransformer, sv, g, daux_of, first_pose_block):
+    bp = bwd_pack(st)
+    p = st.packed()
+    dh = ops.gemm(g, bp["wout_t"])
+    for block, bsv in zip(reversed(list(st.transformer_blocks)), reversed(sv.blocks)):
+        dh = block_backward(block, bsv, dh, daux_of.get(id(block)), stop_here=block is first_pose_block)
+        if dh is None:
+            return None
+    dxn = ops.gemm(dh, bp["win_t"])
+    dx, _ = ops.groupnorm_bwd(sv.x, p["g"], p["b"], dxn, sv.batch, sv.hw, add0=g, eps=st.norm.eps, silu=False)
+    return dx
+
+
+def res_forward(rb, x, batch, h, w, emb_out, skip=None):
+    p = rb.packed()
+    hw = h * w
+    hn = ops.groupnorm(x, p["g1"], p["b1"], batch, hw, x1=skip, eps=rb.in_layers[0].eps, silu=True)
+    h1 = ops.conv3x3(hn, p["w1"], batch, h, w, bias=p["cb1"], row_bias=emb_out)
+    hn2 = ops.groupnorm(h1, p["g2"], p["b2"], batch, hw, eps=rb.out_layers[0].eps, silu=True)
+    xs = ops.gemm(x, p["ws"], bias=p["bs"], a1=skip) if "ws" in p else x
+    out = ops.conv3x3(hn2, p["w2"], batch, h, w, bias=p["cb2"], residual=xs)
+    return out, NS(x=x, skip=skip, h1=h1, batch=batch, h=h, w=w)
+
+
+def res_backward(rb, sv, g):
+    """-> (dL/dx, dL/dskip | None)"""
+    bp = bwd_pack(rb)
+    p = rb.packed()
+    b, h, w = sv.batch, sv.h, sv.w
+    hw = h * w
+    dhn2 = ops.conv3x3(g, bp["w2"], b, h, w)
+    dh1, _ = ops.groupnorm_bwd(sv.h1, p["g2"], p["b2"], dhn2, b, hw, eps=rb.out_layers[0].eps, silu=True)
+    dhn = ops.conv3x3(dh1, bp["w1"], b, h, w)
+    c0 = sv.x.shape[1]
+    if "ws_t" in bp:
+        dxs = ops.gemm(g, bp["ws_t"])
+        add0, add1 = dxs[:, :c0], (dxs[:, c0:] if sv.skip is not None else None)
+    else:
+        add0, add1 = g, None
+    return ops.groupnorm_bwd(sv.x, p["g1"], p["b1"], dhn, b, hw, x1=sv.skip, add0=add0, add1=add1,
+                             eps=rb.in_layers[0].eps, silu=True)
+
+
+def down_backward(layer, g, batch, h, w):
+    """Downsample (stride-2 conv through im2col + GEMM); h, w = INPUT size."""
+    bp = bwd_pack(layer)
+    dcol = ops.gemm(g, bp["w_t"])
+    return ops.col2im3x3_s2(dcol, batch, h, w, layer.channels)
+
+
+def up_backward(layer, g, batch, h, w):
+    """Upsample = nearest x2 + conv3x3; h, w = INPUT size."""
+    bp = bwd_pack(layer)
+    dup = ops.conv3x3(g, bp["w"], batch, 2 * h, 2 * w)
+    return ops.upsample_nearest2x_bwd(dup, batch, h, w)
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet
+# ------------------------------------------------------------------------------------------------
+def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=None):
+    """Taped main-stream forward (pose blocks read the live reference-stream tokens installed by the
+    caller).  Returns (eps fp32 tokens [B*L*L, 4], aux list [(block, (fg, alphas, rgb))], tape).
+    Tape entries, in forward order: ("layer", kind, module, saved), ("push", i) = h became skip
+    tensor hs[i] (openaimodel.py:1055-1071), ("pop", i) = the next ResBlock consumed hs[i] (:1074)."""
+    from .diffusionmodules import openaimodel as U
+    from .attention import to_tokens
+    from .utils_cameraray import pack_pose
+    from ..._lib import ACT_SILU
+
+    p = unet.packed()
+    b, cin, hh, ww = x.shape
+    dev = x.device
+    t_emb = ops.timestep_embedding(timesteps.to(device=dev, dtype=f32).contiguous(), unet.model_channels)
+    e1 = ops.small_linear(t_emb, p["te0w"], p["te0b"], act_out=ACT_SILU)
+    emb = ops.small_linear(e1, p["te2w"], p["te2b"])
+    l1 = ops.small_linear(y.float().contiguous(), p["le0w"], p["le0b"], act_out=ACT_SILU)
+    emb = ops.small_linear(l1, p["le2w"], p["le2b"], add=emb)
+    emb_all = ops.small_linear(emb, p["embw"], p["embb"], act_in=ACT_SILU)
+    ctx_tok, nctx = to_tokens(context), context.shape[1]
+    cams = pack_pose(pose, dev) if pose is not None else None
+    kv_all = ops.gemm(ctx_tok, p["kvw"])
+    aux: list = []
+    tape: list = []
+    jitter = iter(jitter) if jitter else None   # per-pose-block variates, consumed in execution order
+
+    def run(layers, h, hh, ww, skip=None):
+        for layer in layers:
+            if isinstance(layer, U.ResBlock):
+                off, n = p["emb_off"][id(layer)]
+                h, sv = res_forward(layer, h, b, hh, ww, emb_all[:, off:off + n], skip=skip)
+                skip = None
+                tape.append(("layer", "res", layer, sv))
+            elif isinstance(layer, SpatialTransformer):
+                h, sv = st_forward(layer, h, b, hh * ww, nctx, kv_all, cams, aux, jitter)
+                tape.append(("layer", "st", layer, sv))
+            elif isinstance(layer, U.Downsample):
+                tape.append(("layer", "down", layer, NS(h=hh, w=ww)))
+                h = layer.tokens(h, b, hh, ww)
+                hh, ww = hh // 2, ww // 2
+            elif isinstance(layer, U.Upsample):
+                tape.append(("layer", "up", layer, NS(h=hh, w=ww)))
+                h = layer.tokens(h, b, hh, ww)
+                hh, ww = hh * 2, ww * 2
+            else:
+                raise TypeError(type(layer))
+        return h, hh, ww
+
+    col = ops.im2col3x3_nchw(x.float().contiguous(), 64, scale=in_scale, batch=b)
+    h = ops.gemm(col, p["cin_w"], bias=p["cin_b"])
+    hs = [h]
+    tape.append(("push", 0))
+    for block in list(unet.input_blocks)[1:]:
+        h, hh, ww = run(block, h, hh, ww)
+        tape.append(("push", len(hs)))
+        hs.append(h)
+    h, hh, ww = run(unet.middle_block, h, hh, ww)
+    for block in unet.output_blocks:
+        tape.append(("pop", len(hs) - 1))
+        h, hh, ww = run(block, h, hh, ww, skip=hs.pop())
+    hn = ops.groupnorm(h, p["og"], p["ob"], b, hh * ww, eps=unet.out[0].eps, silu=True)
+    eps = ops.conv3x3(hn, p["cout_w"], b, hh, ww, bias=p["cout_b"], out_fp32=True)
+    return eps, aux, NS(tape=tape, h_last=h, batch=b, hh=hh, ww=ww)
+
+
+def first_pose_block(unet) -> Optional[BasicTransformerBlock]:
+    """The pose block that runs first in the forward pass: the backward walk ends there."""
+    order = [m for blk in list(unet.input_blocks) + [unet.middle_block] + list(unet.output_blocks)
+             for layer in blk if isinstance(layer, SpatialTransformer)
+             for m in layer.transformer_blocks if m.image_cross]
+    return order[0] if order else None
+
+
+def unet_backward(unet, fw, deps, daux_of: Dict[int, tuple]):
+    """deps: bf16 [B*L*L, 64] gradient of the loss w.r.t. the UNet output tokens (columns >= 4
+    zero); daux_of: {id(pose block): (dfg, dalphas, drgb)}.  Writes the gradients of every pose
+    parameter into its `.grad` (fp32)."""
+    p = unet.packed()
+    bp = bwd_pack(unet)
+    b = fw.batch
+    stop = first_pose_block(unet)
+    g = ops.conv3x3(deps, bp["cout"], b, fw.hh, fw.ww)
+    g, _ = ops.groupnorm_bwd(fw.h_last, p["og"], p["ob"], g, b, fw.hh * fw.ww, eps=unet.out[0].eps, silu=True)
+    skip_grads: Dict[int, torch.Tensor] = {}
+    pending_skip = None
+    trace = unet.__dict__.get("_grad_trace")   # tests: list collecting (tag, activation gradient)
+    n_out = len(unet.output_blocks)
+    if trace is not None:
+        trace.append((f"out{n_out - 1}", g.clone()))
+    for entry in reversed(fw.tape):
+        if entry[0] == "push":
+            sg = skip_grads.pop(entry[1], None)
+            if sg is not None:
+                g = ops.add_bf16(g, sg)
+            continue
+        if entry[0] == "pop":
+            skip_grads[entry[1]] = pending_skip
+            pending_skip = None
+            if trace is not None:   # g = gradient of the previous block's output
+                n_out -= 1
+                trace.append((f"out{n_out - 1}" if n_out > 0 else "middle", g.clone()))
+            continue
+        _, kind, layer, sv = entry
+        if kind == "res":
+            g, dskip = res_backward(layer, sv, g)
+            if dskip is not None:
+                pending_skip = dskip
+        elif kind == "st":
+            g = st_backward(layer, sv, g, daux_of, stop)
+            if g is None:
+                return
+        elif kind == "down":
+            g = down_backward(layer, g, b, sv.h, sv.w)
+        elif kind == "up":
+            g = up_backward(layer, g, b, sv.h, sv.w)

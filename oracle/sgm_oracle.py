@@ -264,8 +264,48 @@ def plucker(ray: Tensor) -> Tensor:
     return torch.cat([d, torch.cross(o, d, dim=-1)], dim=-1)
 
 
+def stratified_ray_xy(res: int, rx: Tensor, ry: Tensor) -> Tensor:
+    """get_patch_raybundle, stratified branch (utils_cameraray.py:111-140): each patch position is
+    drawn uniformly between the centres of the neighbouring patches; rx / ry are the uniform
+    variates [res+1] the reference draws with torch.rand_like (injected for reproducibility)."""
+    def positions(r):
+        edges = torch.linspace(1, -1, res + 1)
+        center = (edges[1:] + edges[:-1]) / 2.0
+        upper = torch.cat([center, edges[-1:]], -1)
+        lower = torch.cat([edges[:1], center], -1)
+        return (lower + (upper - lower) * r)[:-1]
+    h_pos, v_pos = torch.meshgrid(positions(rx), positions(ry), indexing="xy")
+    return torch.stack([h_pos.reshape(-1), v_pos.reshape(-1)], -1)
+
+
+def stratified_depths(num_samples: int, far_plane: float, near_plane: float, t_rand: Tensor):
+    """Raymarcher.stratified_sampling, training branch (nerfsd_pytorch3d.py:317-325): bin edges
+    jittered between the neighbouring bin centres; t_rand [num_rays, S+1] uniform variates.
+    Returns per-ray (depths [hw, S], dists [hw, S])."""
+    lengths = torch.linspace(near_plane, near_plane + far_plane, num_samples + 1)
+    center = (lengths[1:] + lengths[:-1]) / 2.0
+    upper = torch.cat([center, lengths[-1:]], -1)
+    lower = torch.cat([lengths[:1], center], -1)
+    jit = lower[None] + (upper - lower)[None] * t_rand
+    return (jit[:, :-1] + jit[:, 1:]) / 2.0, jit[:, 1:] - jit[:, :-1]
+
+
+class _TruncExp(torch.autograd.Function):
+    """attention.py:192-208: exp forward, gradient exp(clamp(x, max=15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * torch.exp(ctx.saved_tensors[0].clamp(max=15))
+
+
 def feature_nerf_encoding(sd, p: str, cams: Tensor, xref: Tensor, num_samples: int, far: float,
-                          near: float = 0.0, num_freqs: int = 16, rgb_predict: bool = True):
+                          near: float = 0.0, num_freqs: int = 16, rgb_predict: bool = True,
+                          jitter: Optional[dict] = None):
     """Raymarcher.forward (eval, prev_weights=None; nerfsd_pytorch3d.py:332-394) +
     FeatureNeRFEncoding.forward (:53-161) + the split in NerfSDModule.forward (:443-449).
     cams [b, n+1, 16] (index 0 = target), xref [b, n, hw, c].
@@ -274,14 +314,18 @@ def feature_nerf_encoding(sd, p: str, cams: Tensor, xref: Tensor, num_samples: i
     b, n, hw, c = xref.shape
     res = int(math.sqrt(hw))
     d = num_samples
-    xy = patch_ray_xy(res)
+    xy = patch_ray_xy(res) if jitter is None else stratified_ray_xy(res, *jitter["xy_rand"])
     centers = camera_centers(cams)                                   # [b, n+1, 3]
     dirs = unproject_ndc_depth1_dirs(cams, xy)                       # [b, n+1, hw, 3]
     rays = torch.cat([centers[:, :, None, :].expand(-1, -1, hw, -1), dirs], -1)  # [b, n+1, hw, 6]
-    depths, deltas = raymarcher_depths(d, near + far, near)
+    if jitter is None:
+        depths, deltas = raymarcher_depths(d, near + far, near)
+        depths, deltas = depths[None].expand(hw, d), deltas[None].expand(hw, d)
+    else:  # training with stratified=True: per-ray jittered bins
+        depths, deltas = stratified_depths(d, near + far, near, jitter["t_rand"])
     # ray_bundle_to_ray_points on the TARGET rays only (:381-387)
-    ray_points = rays[:, 0, :, None, :3] + depths[None, None, :, None] * rays[:, 0, :, None, 3:]  # [b,hw,d,3]
-    dists = deltas[None, None, :].expand(1, hw, d)[..., None]
+    ray_points = rays[:, 0, :, None, :3] + depths[None, :, :, None] * rays[:, 0, :, None, 3:]  # [b,hw,d,3]
+    dists = deltas[None, :, :, None]
 
     R, T, _, _ = _cam_fields(cams)
     # :72-98 project into every camera, sample the reference feature maps
@@ -334,14 +378,16 @@ def vol_render(features: Tensor, densities: Tensor, dists: Tensor, rgb: Optional
 def reference_attn(sd, p: str, cams: Tensor, xref: Tensor, context: Tensor, heads: int, cfg: dict):
     """BasicTransformerBlock.reference_attn (attention.py:571-598): FeatureNeRF, the block's own
     norm2/attn2 over every depth sample, trunc_exp, volume rendering, sigmoid on rgb."""
+    jit = cfg.get("_jitter")            # training: iterator over the per-block injected variates
     feats, rgb_raw, sigma_raw, dists, _ = feature_nerf_encoding(
         sd, p + "pose_featurenerf.model.", cams, xref, cfg["num_samples"], cfg.get("far", 2.0),
-        cfg.get("near_plane", 0.0), cfg.get("num_freqs", 16), cfg.get("rgb_predict", True))
+        cfg.get("near_plane", 0.0), cfg.get("num_freqs", 16), cfg.get("rgb_predict", True),
+        jitter=next(jit) if jit is not None else None)
     b, hw, d, c = feats.shape
     f2 = feats.reshape(b, hw * d, c)
     f2 = cross_attention(sd, p + "attn2.", layer_norm(sd, p + "norm2.", f2), context, heads) + f2
     feats = f2.reshape(b, hw, d, c)
-    rendered, fg, alphas, rgb = vol_render(feats, torch.exp(sigma_raw), dists,
+    rendered, fg, alphas, rgb = vol_render(feats, _TruncExp.apply(sigma_raw), dists,
                                            torch.sigmoid(rgb_raw) if rgb_raw is not None else None)
     return rendered, fg, alphas, rgb
 
@@ -379,7 +425,13 @@ def transformer_block(sd, p: str, x: Tensor, context: Tensor, heads: int, cfg: d
             aux = (fg, alphas, rgb)
             if cache is not None:
                 cache[p] = xref
-        x = F.linear(torch.cat([x, xref], -1), sd[p + "pose_emb_layers.weight"])
+        cat_in = torch.cat([x, xref], -1)
+        x = F.linear(cat_in, sd[p + "pose_emb_layers.weight"])
+        probe = cfg.get("_probe")       # tests: (input, output) of pose_emb_layers, output keeps its grad
+        if probe is not None:
+            if x.requires_grad:
+                x.retain_grad()
+            probe[p] = (cat_in, x)
     x = feed_forward(sd, p + "ff.", layer_norm(sd, p + "norm3.", x)) + x
     if capture is not None and (p + "pose_emb_layers.weight") in sd:
         capture[p] = x
@@ -506,10 +558,17 @@ def unet_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, timesteps: Tensor,
         hs.append(h)
     h = _run_layers(sd, "middle_block.", layout["middle_block"], h, emb, context, cfg, cams, choices, cache, aux_out,
                     capture, ctx_ref)
+    probe_h = cfg.get("_probe_h")       # tests: activations along the decoder, keeping their gradients
+    def _keep(tag, t):
+        if probe_h is not None and t.requires_grad:
+            t.retain_grad()
+            probe_h[tag] = t
+    _keep("middle", h)
     for i, layers in enumerate(layout["output_blocks"]):
         h = torch.cat([h, hs.pop()], dim=1)
         h = _run_layers(sd, f"output_blocks.{i}.", layers, h, emb, context, cfg, cams, choices, cache, aux_out,
                         capture, ctx_ref)
+        _keep(f"out{i}", h)
     h = F.silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"]))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1), aux_out
 

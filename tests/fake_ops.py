@@ -131,6 +131,95 @@ class Fake:
         self._log("volrender", b=b, hw=hw)
         return torch.zeros(b * hw, c, dtype=bf16), torch.zeros(b, hw), torch.zeros(b, hw, d), torch.zeros(b, hw, 3)
 
+    # ---- training step -----------------------------------------------------------------------------
+    def attention_bwd(self, q, k, v, o, dout, batch, heads, nq, nkv, *, dq, dk=None, dv=None):
+        inner = heads * 64
+        assert q.shape == (batch * nq, inner) and k.shape == (batch * nkv, inner) and v.shape == k.shape
+        assert o.shape == q.shape and dout.shape == q.shape and dq.shape == q.shape
+        assert (dk is None) == (dv is None) and (dk is None or (dk.shape == k.shape and dv.shape == k.shape))
+        self._log("attention_bwd", nq=nq, nkv=nkv, kv_grad=dk is not None)
+        return dq, dk, dv
+
+    def layernorm_bwd(self, x, gamma, dy, *, add=None, eps=1e-5, out=None):
+        assert x.dtype == bf16 and dy.shape == x.shape and gamma.shape == (x.shape[1],)
+        assert add is None or add.shape == x.shape
+        self._log("layernorm_bwd")
+        return torch.zeros_like(x)
+
+    def groupnorm_bwd(self, x0, gamma, beta, dy, batch, hw, *, x1=None, add0=None, add1=None, eps=1e-5, silu=True):
+        c0 = x0.shape[1]
+        c1 = 0 if x1 is None else x1.shape[1]
+        assert x0.shape[0] == batch * hw and dy.shape == (batch * hw, c0 + c1) and gamma.shape == (c0 + c1,)
+        assert add0 is None or add0.shape == x0.shape
+        assert add1 is None or (x1 is not None and add1.shape == x1.shape)
+        self._log("groupnorm_bwd", c=c0 + c1)
+        return torch.zeros_like(x0), (None if x1 is None else torch.zeros_like(x1))
+
+    def geglu_bwd(self, raw, dh, block=None):
+        assert raw.shape == (dh.shape[0], 2 * dh.shape[1]) and raw.dtype == bf16
+        return torch.zeros_like(raw)
+
+    def add_bf16(self, a, b, *, out=None):
+        assert a.shape == b.shape and a.dtype == bf16
+        self._log("add")
+        return torch.zeros_like(a)
+
+    def transpose_to_bf16(self, x, *, ld_out=None):
+        rows, cols = x.shape
+        return torch.zeros(cols, (rows + 7) // 8 * 8 if ld_out is None else ld_out, dtype=bf16)
+
+    def colsum(self, x, *, out=None):
+        assert out is None or out.shape == (x.shape[1],)
+        return out if out is not None else torch.zeros(x.shape[1])
+
+    def col2im3x3_s2(self, dcol, batch, h, w, c):
+        assert dcol.shape == (batch * (h // 2) * (w // 2), 9 * c)
+        return torch.zeros(batch * h * w, c, dtype=bf16)
+
+    def upsample_nearest2x_bwd(self, g, batch, h, w):
+        assert g.shape[0] == 4 * batch * h * w
+        return torch.zeros(batch * h * w, g.shape[1], dtype=bf16)
+
+    def nerf_volrender_bwd(self, feats, raw, dists, d_rendered, dfg, dalphas, drgb, b, hw, d, c):
+        assert feats.shape == (b * hw * d, c) and d_rendered.shape == (b * hw, c) and raw.shape == (b * hw * d, 4)
+        assert dfg is None or dfg.shape == (b, hw)
+        assert dalphas is None or dalphas.shape == (b, hw, d)
+        assert drgb is None or drgb.shape == (b, hw, 3)
+        self._log("volrender_bwd", seeded=dfg is not None)
+        return torch.zeros_like(feats), torch.zeros(b * hw * d, 8, dtype=bf16)
+
+    def nerf_combine_bwd(self, g, hpre, gidx, gwgt, vlogit, ds, b, n, hw, d, c):
+        assert ds.shape == (b * hw * d, c) and hpre.shape == (b * n * hw * d, c)
+        return torch.zeros_like(hpre), torch.zeros(b, n, hw * d), torch.zeros(b * n * hw, c + 8)
+
+    def nerf_nviews_geo_bwd(self, cams, dlogit, b, n):
+        assert dlogit.shape[:2] == (b, n)
+        return torch.zeros(198)
+
+    def diffusion_loss(self, eps, x_noisy, target, sigma, mask, coef, *, ldd=64):
+        b = x_noisy.shape[0]
+        hw = x_noisy.shape[2] * x_noisy.shape[3]
+        assert eps.shape == (b * hw, 4) and target.shape == x_noisy.shape and sigma.shape == (b,)
+        assert mask is None or mask.numel() == b * hw
+        self._log("diffusion_loss", coef=coef)
+        return torch.ones(b), torch.ones(b), torch.zeros(b * hw, ldd, dtype=bf16)
+
+    def nerf_aux_loss(self, fg, alphas, rgb, op, mask_s, tgt, mask_sum, wfg, wbg, wrgb):
+        b, hw = fg.shape
+        assert alphas.shape[:2] == (b, hw) and op.shape == (b, hw)
+        assert rgb is None or (rgb.shape == (b, hw, 3) and mask_s.shape == (b, hw) and tgt.shape == (b, 3, hw))
+        self._log("nerf_aux_loss")
+        return (torch.ones(b, 3), torch.zeros(b, hw), torch.zeros_like(alphas),
+                None if rgb is None else torch.zeros(b, hw, 3))
+
+    def resize_bilinear_aa(self, x, oh, ow, *, scale=1.0, shift=0.0):
+        return torch.zeros(*x.shape[:-2], oh, ow)
+
+    def adamw_step(self, p, g, m, v, **kw):
+        assert p.shape == g.shape == m.shape == v.shape
+        self._log("adamw", step=kw.get("step"))
+        return p
+
 
 @contextlib.contextmanager
 def patched_ops():

@@ -117,3 +117,36 @@ def test_real_ops_refuse_cpu_tensors():
     m = _model(dict(O.TINY_CFG, image_cross_blocks=[]))
     with pytest.raises(Cd360Error):
         m(torch.randn(1, 4, 16, 16), timesteps=torch.tensor([1]), context=torch.randn(1, 77, 128), y=torch.randn(1, 96))
+
+
+def test_training_step_control_flow_with_fake_kernels():
+    """Host logic of the training step (loss -> taped forward -> explicit backward walk -> flat
+    AdamW) with shape-checking stand-ins for the kernels: every pose block gets a FeatureNeRF
+    backward, skip-connection gradients are joined, the walk stops at the first pose block."""
+    from collections import Counter
+
+    from tests import test_train_step_gpu as G
+    from oracle import train_oracle as T
+    cfg = dict(O.TINY_CFG)
+    sd = O.synthetic_state_dict(cfg, seed=2)
+    batch = T.synthetic_train_batch(cfg, 16, n_views=3, b=2, seed=5, image=48, jitter=True)
+    n_pose = len(O.pose_block_prefixes(cfg))
+    with patched_ops() as fake:
+        eng = G._engine(cfg, sd, torch.device("cpu"))
+        eng.global_step = 1
+        opt = eng.configure_optimizers()
+        assert len(opt.buckets) == n_pose
+        names = [n for n, p in eng.model.diffusion_model.named_parameters() if p.requires_grad]
+        assert names and all("pose" in n for n in names)
+        opt.zero_grad()
+        loss = eng.training_step(G._to_engine_batch(batch, torch.device("cpu")))
+        assert set(eng.last_loss_dict) == {"loss", "loss_fg", "loss_bg", "loss_rgb"}
+        opt.step()
+        calls = Counter(k for k, _ in fake.calls)
+    assert calls["volrender"] == calls["volrender_bwd"] == n_pose
+    assert calls["nerf_aux_loss"] == 2 * n_pose and calls["diffusion_loss"] == 2 and calls["adamw"] == 1
+    assert eng.global_step == 2
+    # parameters / gradients are views of the flat buffers, each 16-byte aligned
+    for p_, o in zip(opt.flat.params, opt.flat.offsets):
+        assert o % 4 == 0 and p_.data_ptr() == opt.flat.data.data_ptr() + 4 * o
+        assert p_.grad.data_ptr() == opt.flat.grad.data_ptr() + 4 * o

@@ -94,3 +94,36 @@ def test_guided_euler_sampler(gold):
                                  scale=7.5, scale_im=3.5)
     ref = gold["sample_final"]
     assert (out - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max()))
+
+
+def test_training_oracle_vs_reference_golden():
+    """oracle/train_oracle.py against tests/golden/train_step_golden.pt — loss terms and pose
+    gradients produced by the reference's own training code (tests/golden/make_train_golden.py),
+    replaying the random draws it made (stratified jitter on, b = 2)."""
+    import os
+
+    from oracle import train_oracle as T
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "train_step_golden.pt"), map_location="cpu")
+    case = gold["case"]
+    cfg = dict(O.TINY_CFG)
+    sd = O.synthetic_state_dict(cfg, seed=case["weights_seed"])
+    batch = T.synthetic_train_batch(cfg, case["latent"], n_views=case["n_views"], b=case["b"], seed=case["batch_seed"],
+                                    image=case["image"])
+    batch["drop_im"] = torch.tensor(case["drop_im"])
+    batch["rand"] = gold["rand"]
+    total, terms, grads = T.training_gradients(sd, cfg, batch)
+    assert abs(float(total) - gold["total"]) <= 1e-4 * max(1.0, abs(gold["total"]))
+    for k, v in gold["terms"].items():
+        assert abs(float(terms[k]) - v) <= 1e-4 * max(1.0, abs(v)), k
+    assert set(grads) == set(gold["grads"])
+    for k, ref in gold["grads"].items():
+        g = grads[k]
+        if k.endswith("nviews.bias"):      # sum over views of a softmax gradient: analytically zero, roundoff only
+            assert float(g.abs().max()) <= 1e-7 and ref["norm"] <= 1e-7
+            continue
+        flat = g.reshape(-1)
+        step = max(1, flat.numel() // 256)
+        smp = flat[::step][:256]
+        scale = max(float(ref["sample"].abs().max()), 1e-3 * ref["norm"], 1e-9)
+        assert float((smp - ref["sample"]).abs().max()) <= 2e-3 * scale, k
+        assert abs(float(g.norm()) - ref["norm"]) <= 2e-3 * max(ref["norm"], 1e-9), k

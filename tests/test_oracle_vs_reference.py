@@ -126,3 +126,116 @@ def test_reference_stream_forward(ns):
         assert (lst[0] - cap2[name + "."]).abs().max() < 2e-4 * max(1.0, float(lst[0].abs().max()))
     for f, (f2, a2, r2) in zip(fg, aux2):
         assert (f - f2.reshape(f.shape)).abs().max() < 1e-4
+
+
+def _import_reference_training(ns):
+    """The reference's loss / denoiser / samplers, imported in place.  loss.py pulls LPIPS and the
+    conditioner at module import (loss.py:6-7); neither is used by the 'l2' branch, so both are
+    stubbed as empty shells (the installed package set has no open_clip / kornia)."""
+    import importlib
+    import sys
+    import types
+
+    def shell(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+
+    class _Stub(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+    for name in ("sgm.modules.autoencoding", "sgm.modules.autoencoding.lpips", "sgm.modules.autoencoding.lpips.loss"):
+        shell(name)
+    shell("sgm.modules.autoencoding.lpips.loss.lpips", LPIPS=_Stub)
+    shell("sgm.modules.encoders")
+    shell("sgm.modules.encoders.modules", GeneralConditioner=_Stub)
+    if "fsspec" not in sys.modules:
+        try:
+            import fsspec  # noqa: F401
+        except Exception:
+            shell("fsspec")
+    ns.loss = importlib.import_module("sgm.modules.diffusionmodules.loss")
+    ns.denoiser = importlib.import_module("sgm.modules.diffusionmodules.denoiser")
+    ns.wrappers = importlib.import_module("sgm.modules.diffusionmodules.wrappers")
+    return ns
+
+
+def _reference_training_step(ns, cfg, sd, batch, seed, train_mode):
+    """Loss terms and pose gradients from the reference's OWN training code path
+    (StandardDiffusionLossImgRef -> DiscreteDenoiser -> OpenAIWrapper -> UNetModel, torch autograd),
+    plus the random draws it made (replayed from the same generator state, in its call order)."""
+    _import_reference_training(ns)
+    disc = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    loss_fn = ns.loss.StandardDiffusionLossImgRef(
+        sigma_sampler_config={"target": "sgm.modules.diffusionmodules.sigma_sampling.CubicSampling",
+                              "params": {"num_idx": 1000, "discretization_config": disc}},
+        sigma_sampler_config_ref={"target": "sgm.modules.diffusionmodules.sigma_sampling.DiscreteSampling",
+                                  "params": {"num_idx": 50, "discretization_config": disc}})
+    denoiser = ns.denoiser.DiscreteDenoiser(
+        weighting_config={"target": "sgm.modules.diffusionmodules.denoiser_weighting.EpsWeighting"},
+        scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+        num_idx=1000, discretization_config=disc)
+    unet = H.build_reference_unet(ns, cfg, sd, patch_for_sampling=False)
+    unet.train(train_mode)
+    for name, p in unet.named_parameters():       # trainkeys == 'pose' (diffusion.py:139-144)
+        p.requires_grad = "pose" in name
+    net = ns.wrappers.OpenAIWrapper(unet)
+    b, n = batch["x_ref"].shape[:2]
+    pose = [H.cameras_from_packed(batch["cams"][i]) for i in range(b)]
+    conditioner = lambda bt: {"crossattn": batch["crossattn"], "vector": batch["vector"]}
+    torch.manual_seed(seed)
+    loss, loss_fg, loss_bg, loss_rgb = loss_fn(net, denoiser, conditioner, batch["x"], batch["rgb"], batch["x_ref"],
+                                               pose, batch["mask"], None, batch["opacity"], {})
+    # DiffusionEngine.forward (diffusion.py:221-236) with the yaml's lambdas, global_step > 0
+    drop = batch["drop_im"]
+    total = loss.mean()
+    lf = (loss_fg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+    lb = (loss_bg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+    lr = (loss_rgb.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+    total = total + 10.0 * lf + 10.0 * lb + 5.0 * lr
+    total.backward()
+    grads = {k: p.grad.clone() for k, p in unet.named_parameters() if p.requires_grad}
+    # replay the draws: CubicSampling torch.rand, randn_like(input), DiscreteSampling torch.randint,
+    # randn_like(input_ref) (loss.py:147-170), randn_like(input_ref) (denoiser.py:31), then per pose
+    # block in execution order: rand_like x2 (utils_cameraray.py:111-140), torch.rand (nerfsd:317-325)
+    torch.manual_seed(seed)
+    u = torch.rand((b,))
+    rand = dict(sigma_idx=((1 - u ** 3) * 999).long(), noise=torch.randn_like(batch["x"]),
+                sigma_ref_idx=torch.randint(0, 50, (b,)), noise_ref=torch.randn_like(batch["x_ref"]),
+                noise_ref2=torch.randn_like(batch["x_ref"]))
+    if train_mode and cfg.get("stratified"):
+        L = batch["x"].shape[-1]
+        jit = []
+        for _, c, ds in O.pose_block_prefixes(cfg):
+            res = L // ds
+            rx = torch.rand(res + 1)
+            ry = torch.rand(res + 1)
+            jit.append(dict(xy_rand=(rx, ry), t_rand=torch.rand(res * res, cfg["num_samples"] + 1)))
+        rand["jitter"] = jit
+    terms = dict(loss=loss.mean().detach(), loss_fg=lf.detach(), loss_bg=lb.detach(), loss_rgb=lr.detach())
+    return total.detach(), terms, grads, rand
+
+
+@pytest.mark.parametrize("train_mode", [False, True])
+def test_training_step_vs_reference(ns, train_mode):
+    """The training oracle (oracle/train_oracle.py) against the reference's own training code:
+    loss terms and the gradient of every trainable ('pose') parameter.  train_mode=True runs the
+    reference UNet in .train() — stratified ray / depth jitter on (yaml: stratified: True)."""
+    from oracle import train_oracle as T
+    cfg = dict(O.TINY_CFG)
+    L, n = 16, 3
+    sd = O.synthetic_state_dict(cfg, seed=2)
+    batch = T.synthetic_train_batch(cfg, L, n_views=n, b=1, seed=5, image=48)
+    total_ref, terms_ref, grads_ref, rand = _reference_training_step(ns, cfg, sd, batch, seed=11, train_mode=train_mode)
+    batch = dict(batch, rand=rand)
+    total, terms, grads = T.training_gradients(sd, cfg, batch)
+    assert abs(float(total) - float(total_ref)) <= 1e-4 * max(1.0, abs(float(total_ref)))
+    for k in ("loss", "loss_fg", "loss_bg", "loss_rgb"):
+        assert abs(float(terms[k]) - float(terms_ref[k])) <= 1e-4 * max(1.0, abs(float(terms_ref[k]))), k
+    assert set(grads) == set(grads_ref) and len(grads) > 0
+    for k, g in grads_ref.items():
+        scale = max(float(g.abs().max()), 1e-6)
+        assert float((grads[k] - g).abs().max()) <= 2e-3 * scale, (k, float((grads[k] - g).abs().max()), scale)
