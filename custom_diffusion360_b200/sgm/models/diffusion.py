@@ -187,6 +187,9 @@ class DiffusionEngine(nn.Module):
         named = [(n, p) for n, p in self.model.diffusion_model.named_parameters() if p.requires_grad]
         opt = PoseAdamW(named, lr=self.learning_rate, group=group, **cfg)
         opt.on_step = self._after_optimizer_step
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            opt.attach_overlap(self.model.diffusion_model)
         return opt
 
     def _after_optimizer_step(self):

@@ -268,6 +268,9 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
         ops.gemm(gt, ops.transpose_to_bf16(sv.rendered), out=dwp[:, c:])
         pp = pose_bwd_pack(block)
         nerf_backward(block, sv.nerf, ops.gemm(g, pp["wp_r_t"]), daux)
+        ready = block.__dict__.get("_grads_ready")     # data-parallel: start this block's all-reduce now
+        if ready is not None:
+            ready()
         if stop_here:
             return None
         g = ops.gemm(g, pp["wp_x_t"])

@@ -102,6 +102,21 @@ class PoseAdamW:
         else:
             self._pending.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
+    def attach_overlap(self, unet):
+        """Start each pose block's bucket all-reduce the moment the backward walk has written that
+        block's gradients (blocks finish in reverse forward order, so the exchange of the decoder's
+        blocks overlaps the backward of everything upstream)."""
+        prefixes = []
+        for name in self.flat.names:
+            key = name.split(".pose")[0]
+            if not prefixes or prefixes[-1] != key:
+                prefixes.append(key)
+        assert len(prefixes) == len(self.buckets)
+        index = {k: i for i, k in enumerate(prefixes)}
+        for name, block in unet.pose_blocks():
+            i = index[name]
+            block.__dict__["_grads_ready"] = (lambda i=i: self.reduce_bucket(i))
+
     def reduce_all(self):
         for i in range(len(self.buckets)):
             self.reduce_bucket(i)

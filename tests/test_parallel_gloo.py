@@ -58,3 +58,50 @@ def test_shard_balance():
         for w in (1, 2, 4, 8):
             sizes = [len(image_shard(n, r, w)) for r in range(w)]
             assert sum(sizes) == n and max(sizes) - min(sizes) <= 1
+
+
+def _train_worker(rank, world, port, q):
+    """Data-parallel training exchange on CPU/gloo: flat parameter / gradient buffers, one bucket
+    per pose block, per-block all-reduce started by the backward walk's callbacks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import sgm_oracle as O
+        from custom_diffusion360_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+        from custom_diffusion360_b200.sgm.optim import PoseAdamW
+        torch.manual_seed(0)
+        unet = UNetModel(**dict(O.TINY_CFG))
+        named = [(n, p) for n, p in unet.named_parameters() if "pose" in n]
+        opt = PoseAdamW(named, lr=1e-3)
+        opt.attach_overlap(unet)
+        blocks = [m for _, m in unet.pose_blocks()]
+        assert len(opt.buckets) == len(blocks)
+        # rank r's "gradient" of parameter k is (r + 1) * (k + 1); blocks finish in reverse order
+        for k, (_, p) in enumerate(named):
+            p.grad.fill_(float((rank + 1) * (k + 1)))
+        for blk in reversed(blocks):
+            blk.__dict__["_grads_ready"]()
+        opt.wait_reduce()
+        tot = sum(r + 1 for r in range(world))
+        ok = all(bool((p.grad == float(tot * (k + 1))).all()) for k, (_, p) in enumerate(named))
+        # views survive: parameters and grads still alias the flat buffers
+        alias = all(p.data_ptr() == opt.flat.data.data_ptr() + 4 * o for p, o in zip(opt.flat.params, opt.flat.offsets))
+        q.put((rank, ok, alias, len(opt.buckets), opt.flat.numel))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_buckets_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, alias, nb, numel in results:
+        assert ok and alias and nb == 9 and numel > 0
