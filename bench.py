@@ -286,6 +286,13 @@ def run_train(args, world, rank, local_rank):
     n0 = ops.LaunchStats.launches
     loss0 = float(one_step(0))
     launches_per_step = ops.LaunchStats.launches - n0
+    eager_step = one_step
+    if not args.no_graph:
+        # the step replayed from a CUDA graph (sgm/models/diffusion.py: GraphedTrainStep); the random
+        # draws (sigma, noise, stratified variates) are renewed on the device before every replay
+        from custom_diffusion360_b200.sgm.models.diffusion import GraphedTrainStep
+        gs = GraphedTrainStep(engine, opt, batch)
+        one_step = lambda i: gs(batch)
     for i in range(1, max(args.warmup, 3)):
         one_step(i)
     torch.cuda.synchronize()
@@ -317,7 +324,7 @@ def run_train(args, world, rank, local_rank):
         return r
 
     ops.LaunchStats.hook = hook
-    one_step(999)
+    eager_step(999)
     ops.LaunchStats.hook = None
     torch.cuda.synchronize()
     kern = {}
@@ -341,14 +348,18 @@ def run_train(args, world, rank, local_rank):
                                f"{n_views} reference views (reference stream no-grad), FeatureNeRF in all 12 pose blocks with "
                                f"stratified jitter, l2 + fg/bg/rgb losses, backward to the pose weights, DDP all-reduce, AdamW",
                    "parallelism": f"data-parallel x{world} (bucketed all-reduce of {opt.flat.numel} fp32 gradients "
-                                  f"overlapped with the backward walk)", "cuda_graph": False},
+                                  f"overlapped with the backward walk when eager, after the graph replay otherwise)",
+                   "cuda_graph": not args.no_graph,
+                   "l2": "inputs larger than L2: ~5 GB of bf16 weights + ~5 GB of transposed packs stream per step"},
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (forward, dX and dW launches of one training step)", "bound": "tensor",
                      "achieved": gk.get("tflops"), "peak": peaks["burst"], "unit": "TFLOP/s",
                      "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None, "traffic": None,
                      "launches_per_step": gk.get("launches"), "launched_tflop_per_step": gk.get("launched_tflop"),
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
+        "kernels_note": "per-kernel times come from one extra EAGER step with CUDA events around every launch; that "
+                        "step is host-bound, so the intervals include launch gaps (upper bounds, shares only)",
         "kernels": kern, "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
-        "loss_first_step": loss0, "loss_last_step": float(loss), "clocks": clk,
+        "loss_first_step": loss0, "loss_last_step": float(loss), "loss_terms_last_eager_step": engine.last_loss_dict, "clocks": clk,
         "trainable_values": opt.flat.numel, "allreduce_bytes_per_step": 4 * opt.flat.numel if world > 1 else 0,
     }
     print(json.dumps(line))

@@ -322,6 +322,260 @@ attention_bwd_dkdv_kernel(const AttnBwdParams p) {
   store_acc_bf16(accV, sS, p.dv, p.lddv, batch, p.nkv, head, key0, w16);
 }
 
+
+// =================================================================================================
+// Second generation (default): the same two-pass algorithm on raw mma.sync.m16n8k16 with the score
+// tiles kept in REGISTERS (FlashAttention-2 style).  Per warp: 16 rows x 64 columns of S / dP as 8
+// accumulator tiles; the accumulator layout of two adjacent n8 tiles IS the A-operand layout of the
+// next k16 step, so P / dS feed the second product without touching shared memory.  K-major B
+// operands (K^T, V^T, Q^T, dO^T) are plain 32-bit shared loads (rows padded to 144 B: conflict
+// free); row-major B operands (K, Q, dO as [k][n]) come through ldmatrix.trans.
+//   attention_bwd_dq_mma   : pass 1 lse (online), D = rowsum(dO o O), pass 2 dQ; writes lse / D
+//   attention_bwd_dkdv_mma : dK, dV for 64 keys per CTA, looping over the query tiles
+// Measured on the training step's shapes (profiles/README_r01.md): 52 ms -> see there.
+// =================================================================================================
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four transposed 8x8 b16 matrices: lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+// A fragments (16 rows w16.. x 64 k) of a row-major smem tile: frag[ks] covers k = ks*16 .. +15
+__device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16* tile, int w16) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const __nv_bfloat16* p0 = tile + (w16 + g) * AB_LD + ks * 16 + 2 * t;
+    a[ks][0] = *reinterpret_cast<const uint32_t*>(p0);
+    a[ks][1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * AB_LD);
+    a[ks][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+    a[ks][3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * AB_LD + 8);
+  }
+}
+// acc[nt] (16 x 64, 8 tiles of n8) = A (frags) * B^T with B stored row-major [n rows][64 k]
+__device__ __forceinline__ void mma_a_bt(float (&acc)[8][4], const uint32_t (&a)[4][4],
+                                         const __nv_bfloat16* b) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const __nv_bfloat16* pb = b + (nt * 8 + g) * AB_LD + ks * 16 + 2 * t;
+      mma16816(acc[nt], a[ks], *reinterpret_cast<const uint32_t*>(pb),
+               *reinterpret_cast<const uint32_t*>(pb + 8));
+    }
+  }
+}
+// out[nt] (16 x 64) += X (16 x 64 in accumulator layout, converted to bf16 A fragments) * B with B
+// stored row-major [64 k rows][64 n]
+__device__ __forceinline__ void mma_x_b(float (&out)[8][4], const float (&x)[8][4],
+                                        const __nv_bfloat16* b) {
+  const int lane = threadIdx.x & 31;
+  const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(x[2 * kt][0], x[2 * kt][1]);
+    a[1] = pack_bf16x2(x[2 * kt][2], x[2 * kt][3]);
+    a[2] = pack_bf16x2(x[2 * kt + 1][0], x[2 * kt + 1][1]);
+    a[3] = pack_bf16x2(x[2 * kt + 1][2], x[2 * kt + 1][3]);
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      uint32_t r[4];
+      ldmatrix_x4_trans(r, b + (kt * 16 + (mi & 1) * 8 + rr) * AB_LD + dt * 16 + (mi >> 1) * 8);
+      mma16816(out[2 * dt], a, r[0], r[1]);
+      mma16816(out[2 * dt + 1], a, r[2], r[3]);
+    }
+  }
+}
+// accumulator tiles (rows g / g+8 of the warp's 16) -> bf16 global, rows < n only
+__device__ __forceinline__ void store_acc_rows(const float (&acc)[8][4], __nv_bfloat16* dst, long long ld,
+                                               int batch, int n, int head, int row_lo) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int row = row_lo + 8 * h;
+    if (row < n) {
+      __nv_bfloat16* p = dst + (static_cast<long long>(batch) * n + row) * ld + head * AB_T + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+        *reinterpret_cast<uint32_t*>(p + nt * 8) = pack_bf16x2(acc[nt][2 * h], acc[nt][2 * h + 1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS)
+attention_bwd_dq_mma_kernel(const AttnBwdParams p) {
+  __shared__ __align__(128) __nv_bfloat16 sK[AB_T * AB_LD];
+  __shared__ __align__(128) __nv_bfloat16 sV[AB_T * AB_LD];
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * AB_T, head = blockIdx.y, batch = blockIdx.z;
+  const int w16 = warp * 16;
+  const int row_lo = row0 + w16 + g;
+  // stage Q / dO through the K / V buffers into A fragments
+  load_tile(sK, p.q, p.ldq, batch, p.nq, head, row0);
+  load_tile(sV, p.dout, p.lddo, batch, p.nq, head, row0);
+  __syncthreads();
+  uint32_t qa[4][4], da[4][4];
+  load_a_frags(qa, sK, w16);
+  load_a_frags(da, sV, w16);
+  // D = sum_d dO O for rows g / g+8 (this thread's 16 columns of each, then the quad)
+  float dsum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int row = row_lo + 8 * h;
+    if (row < p.nq) {
+      const __nv_bfloat16* po = p.o + (static_cast<long long>(batch) * p.nq + row) * p.ldo + head * AB_T + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float2 o = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(po + ks * 16 + 8 * c)));
+          const float2 d = unpack_bf16x2(da[ks][h + 2 * c]);
+          dsum[h] = fmaf(o.x, d.x, fmaf(o.y, d.y, dsum[h]));
+        }
+    }
+    dsum[h] += __shfl_xor_sync(0xffffffffu, dsum[h], 1);
+    dsum[h] += __shfl_xor_sync(0xffffffffu, dsum[h], 2);
+  }
+  const int nt_kv = (p.nkv + AB_T - 1) / AB_T;
+  // ---- pass 1: lse ----
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  for (int j = 0; j < nt_kv; ++j) {
+    __syncthreads();
+    load_tile(sK, p.k, p.ldk, batch, p.nkv, head, j * AB_T);
+    __syncthreads();
+    float s[8][4];
+    mma_a_bt(s, qa, sK);
+    const int valid = p.nkv - j * AB_T;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t + (e & 1);
+        s[nt][e] = col < valid ? s[nt][e] * p.scale : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+      const float m_new = fmaxf(m[h], mx[h]);   // finite: column 0 of every tile is a valid key
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) sum += __expf(s[nt][2 * h] - m_new) + __expf(s[nt][2 * h + 1] - m_new);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      l[h] = l[h] * __expf(m[h] - m_new) + sum;
+      m[h] = m_new;
+    }
+  }
+  const float lse[2] = {m[0] + __logf(l[0]), m[1] + __logf(l[1])};
+  // ---- pass 2: dQ ----
+  float dq[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
+  for (int j = 0; j < nt_kv; ++j) {
+    __syncthreads();
+    load_tile(sK, p.k, p.ldk, batch, p.nkv, head, j * AB_T);
+    load_tile(sV, p.v, p.ldv, batch, p.nkv, head, j * AB_T);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+    mma_a_bt(s, qa, sK);
+    mma_a_bt(dp, da, sV);
+    const int valid = p.nkv - j * AB_T;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t + (e & 1);
+        const int h = e >> 1;
+        s[nt][e] = col < valid ? __expf(s[nt][e] * p.scale - lse[h]) * (dp[nt][e] - dsum[h]) * p.scale : 0.f;
+      }
+    mma_x_b(dq, s, sK);
+  }
+  store_acc_rows(dq, p.dq, p.lddq, batch, p.nq, head, row_lo);
+  if (t == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = row_lo + 8 * h;
+      if (row < p.nq) {
+        const long long idx = (static_cast<long long>(batch) * p.heads + head) * p.nq + row;
+        p.lse[idx] = lse[h];
+        p.dsum[idx] = dsum[h];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS)
+attention_bwd_dkdv_mma_kernel(const AttnBwdParams p) {
+  __shared__ __align__(128) __nv_bfloat16 sQ[AB_T * AB_LD];
+  __shared__ __align__(128) __nv_bfloat16 sDO[AB_T * AB_LD];
+  __shared__ float sLse[AB_T], sD[AB_T];
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int key0 = blockIdx.x * AB_T, head = blockIdx.y, batch = blockIdx.z;
+  const int w16 = warp * 16;
+  const int key_lo = key0 + w16 + g;
+  load_tile(sQ, p.k, p.ldk, batch, p.nkv, head, key0);
+  load_tile(sDO, p.v, p.ldv, batch, p.nkv, head, key0);
+  __syncthreads();
+  uint32_t ka[4][4], va[4][4];
+  load_a_frags(ka, sQ, w16);
+  load_a_frags(va, sDO, w16);
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      dk[nt][e] = 0.f;
+      dv[nt][e] = 0.f;
+    }
+  const bool key_ok[2] = {key_lo < p.nkv, key_lo + 8 < p.nkv};
+  const int nt_q = (p.nq + AB_T - 1) / AB_T;
+  for (int i = 0; i < nt_q; ++i) {
+    __syncthreads();
+    load_tile(sQ, p.q, p.ldq, batch, p.nq, head, i * AB_T);
+    load_tile(sDO, p.dout, p.lddo, batch, p.nq, head, i * AB_T);
+    if (threadIdx.x < AB_T) {
+      const int qrow = i * AB_T + threadIdx.x;
+      const long long idx = (static_cast<long long>(batch) * p.heads + head) * p.nq + qrow;
+      sLse[threadIdx.x] = qrow < p.nq ? p.lse[idx] : INFINITY;   // exp(-inf) = 0 for rows past the end
+      sD[threadIdx.x] = qrow < p.nq ? p.dsum[idx] : 0.f;
+    }
+    __syncthreads();
+    float st[8][4], dpt[8][4];
+    mma_a_bt(st, ka, sQ);      // S^T  [keys][queries]
+    mma_a_bt(dpt, va, sDO);    // dP^T
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t + (e & 1);
+        const float pr = key_ok[e >> 1] ? __expf(st[nt][e] * p.scale - sLse[col]) : 0.f;
+        st[nt][e] = pr;                                          // P^T
+        dpt[nt][e] = pr * (dpt[nt][e] - sD[col]) * p.scale;      // dS^T
+      }
+    mma_x_b(dv, st, sDO);      // dV += P^T dO
+    mma_x_b(dk, dpt, sQ);      // dK += dS^T Q
+  }
+  store_acc_rows(dk, p.dk, p.lddk, batch, p.nkv, head, key_lo);
+  store_acc_rows(dv, p.dv, p.lddv, batch, p.nkv, head, key_lo);
+}
+
 constexpr int AB_SMEM_STATS = 2 * AB_TILE_B + AB_TILE_F;
 constexpr int AB_SMEM_DQ = 5 * AB_TILE_B + 2 * AB_TILE_F;
 constexpr int AB_SMEM_DKDV = 6 * AB_TILE_B + 2 * AB_TILE_F + 2 * AB_T * 4;
@@ -373,6 +627,22 @@ extern "C" int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* 
   p.nq = nq; p.nkv = nkv; p.heads = heads;
   p.scale = 0.125f;
   const dim3 gq((nq + AB_T - 1) / AB_T, heads, batch);
+  static int use_wmma = -1;   // CD360_ATTBWD=wmma selects the first-generation kernels (A/B, debugging)
+  if (use_wmma < 0) {
+    const char* e = getenv("CD360_ATTBWD");
+    use_wmma = (e != nullptr && e[0] == 'w') ? 1 : 0;
+  }
+  if (!use_wmma) {
+    if (launch_ex(attention_bwd_dq_mma_kernel, gq, dim3(AB_THREADS), 0, stream, 1, p) != cudaSuccess)
+      return CD360_ERR_LAUNCH;
+    if (dk != nullptr) {
+      const dim3 gk((nkv + AB_T - 1) / AB_T, heads, batch);
+      if (launch_ex(attention_bwd_dkdv_mma_kernel, gk, dim3(AB_THREADS), 0, stream, 1, p) != cudaSuccess)
+        return CD360_ERR_LAUNCH;
+    }
+    CD360_CHECK_LAUNCH();
+    return CD360_OK;
+  }
   if (launch_ex(attention_bwd_stats_kernel, gq, dim3(AB_THREADS), AB_SMEM_STATS, stream, 1, p) != cudaSuccess)
     return CD360_ERR_LAUNCH;
   if (launch_ex(attention_bwd_dq_kernel, gq, dim3(AB_THREADS), AB_SMEM_DQ, stream, 1, p) != cudaSuccess)

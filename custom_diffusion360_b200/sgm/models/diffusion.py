@@ -129,44 +129,54 @@ class DiffusionEngine(nn.Module):
         return (batch[k], batch.get(k + "_ref"), batch.get("pose"), batch.get("mask"), batch.get("mask_ref"),
                 batch.get("depth"), batch.get("drop_im", 0.0))
 
-    def forward(self, x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward: bool = True):
+    def forward(self, x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward: bool = True,
+                sync: bool = True):
         """Loss of one batch (reference :221-236) and — the autograd replacement — the gradients of
-        the trainable parameters in `.grad`.  Returns (loss_mean tensor, loss_dict)."""
+        the trainable parameters in `.grad`.  Returns (loss_mean tensor, loss_dict).  Everything is
+        evaluated on the device (the reference's `if loss_rgb.mean() > 0` becomes a 0/1 factor), so
+        with sync=False nothing waits for the GPU and the call can be captured in a CUDA graph;
+        loss_dict then holds device scalars instead of floats."""
         loss, loss_fg, loss_bg, loss_rgb = self.loss_fn(self.model, self.denoiser, self.conditioner, x, x_rgb,
                                                         xr, pose, mask, mask_ref, opacity, batch)
         b = x.shape[0]
         dev = x.device
         loss_mean = loss.mean()
-        loss_dict = {"loss": loss_mean.item()}
-        drop = torch.as_tensor(drop_im, dtype=torch.float32, device=dev).reshape(-1).expand(b) \
-            if not torch.is_tensor(drop_im) or drop_im.numel() == 1 else drop_im.float().reshape(-1).to(dev)
+        terms = {"loss": loss_mean}
+        if torch.is_tensor(drop_im):
+            drop = drop_im.float().reshape(-1).to(dev).expand(b)
+        else:
+            drop = torch.full((b,), float(drop_im), device=dev)
+        dsum = drop.sum() + 1e-12
         w_fg = w_bg = w_rgb = None
         if self.rgb and self.global_step > 0 and torch.is_tensor(loss_fg):
             k = loss_fg.shape[1]
-            lf = (loss_fg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
-            lb = (loss_bg.mean(1) * drop).sum() / (drop.sum() + 1e-12)
+            lf = (loss_fg.mean(1) * drop).sum() / dsum
+            lb = (loss_bg.mean(1) * drop).sum() / dsum
             loss_mean = loss_mean + self.loss_fg_lambda * lf + self.loss_bg_lambda * lb
-            loss_dict["loss_fg"], loss_dict["loss_bg"] = lf.item(), lb.item()
-            w_fg = self.loss_fg_lambda * drop / (k * (drop.sum() + 1e-12))
-            w_bg = self.loss_bg_lambda * drop / (k * (drop.sum() + 1e-12))
-        if self.rgb_predict and torch.is_tensor(loss_rgb) and loss_rgb.mean() > 0:
+            terms["loss_fg"], terms["loss_bg"] = lf, lb
+            w_fg = self.loss_fg_lambda * drop / (k * dsum)
+            w_bg = self.loss_bg_lambda * drop / (k * dsum)
+        if self.rgb_predict and torch.is_tensor(loss_rgb):
             k = loss_rgb.shape[1]
-            lr_ = (loss_rgb.mean(1) * drop).sum() / (drop.sum() + 1e-12)
-            loss_mean = loss_mean + self.loss_rgb_lambda * lr_
-            loss_dict["loss_rgb"] = lr_.item()
-            w_rgb = self.loss_rgb_lambda * drop / (k * (drop.sum() + 1e-12))
+            gate = (loss_rgb.mean() > 0).float()                      # reference :232
+            lr_ = (loss_rgb.mean(1) * drop).sum() / dsum
+            loss_mean = loss_mean + gate * self.loss_rgb_lambda * lr_
+            terms["loss_rgb"] = lr_
+            w_rgb = gate * self.loss_rgb_lambda * drop / (k * dsum)
         if backward:
             self.loss_fn.backward(1.0 / b, w_fg, w_bg, w_rgb)
-        return loss_mean, loss_dict
+        if sync:
+            terms = {k_: float(v) for k_, v in terms.items()}
+        return loss_mean, terms
 
-    def shared_step(self, batch, backward: bool = True):
+    def shared_step(self, batch, backward: bool = True, sync: bool = True):
         x, xr, pose, mask, mask_ref, opacity, drop_im = self.get_input(batch)
         x_rgb = batch.get("rgb")
         if xr is not None and torch.is_tensor(drop_im):
             bb = xr.shape[0]
             xr = drop_im.reshape(bb, 1, 1, 1, 1).to(xr) * xr          # reference :246
         batch["global_step"] = self.global_step
-        return self(x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward=backward)
+        return self(x, x_rgb, xr, pose, mask, mask_ref, opacity, drop_im, batch, backward=backward, sync=sync)
 
     def training_step(self, batch, batch_idx=0):
         """Loss + gradients of one batch (the Lightning hook of the reference, :251-272; here the
@@ -196,3 +206,105 @@ class DiffusionEngine(nn.Module):
         self.global_step += 1
         from ..modules.attention import invalidate_all_packed
         invalidate_all_packed(self.model.diffusion_model, only_trainable=True)
+
+
+class GraphedTrainStep:
+    """The training step (noising -> reference stream -> taped forward -> losses -> backward to the
+    pose gradients) captured ONCE in a CUDA graph and replayed per batch: the eager step issues
+    ~3.6 k launches and is bound by the host (~26 us per launch from Python); replay is bound by
+    the GPU.  Per call: the batch and the step's random draws (sigma indices from the reference's
+    samplers, three noise tensors, stratified ray / depth variates) are written into static
+    buffers, the graph replays, then the optimiser runs (gradient all-reduce + fused AdamW).
+    The bf16 operand packs of the TRAINABLE weights are rebuilt inside the graph from the fp32
+    masters, so every replay sees the previous optimiser update."""
+
+    def __init__(self, engine: "DiffusionEngine", opt, batch: dict):
+        from ..modules.attention import invalidate_all_packed
+        from ..modules.utils_cameraray import pack_pose
+        self.engine, self.opt = engine, opt
+        unet = engine.model.diffusion_model
+        dev = engine.device
+        k = engine.input_key
+        self.keys = [key for key in (k, k + "_ref", "mask", "depth", "rgb", "drop_im") if torch.is_tensor(batch.get(key))]
+        self.static = {key: batch[key].to(dev).clone() for key in self.keys}
+        self.static["pose"] = pack_pose(batch["pose"], dev).clone()
+        self.static_cond = {n: t.to(dev).clone() for n, t in batch["cond"].items()}
+        x, xr = self.static[k], self.static[k + "_ref"]
+        b = x.shape[0]
+        self.rand = dict(sigma=torch.ones(b, device=dev), sigma_ref=torch.ones(b, device=dev),
+                         noise=torch.zeros_like(x), noise_ref=torch.zeros_like(xr), noise_ref2=torch.zeros_like(xr))
+        self.stratified = []
+        for _, blk in unet.pose_blocks():
+            rm = blk.pose_featurenerf.raymarcher
+            if not rm.stratified:
+                self.stratified = None
+                break
+            c = blk.pose_emb_layers.weight.shape[0]
+            res = x.shape[-1] // (c // unet.model_channels)
+            hw, d = res * res, rm.num_samples
+            self.stratified.append(dict(res=res, rm=rm, bins=(torch.zeros(hw, 2, device=dev), torch.zeros(hw, d, device=dev),
+                                                              torch.zeros(hw, d, device=dev))))
+        if self.stratified:
+            self.rand["jitter"] = [{"bins": s_["bins"]} for s_ in self.stratified]
+        if engine.global_step < 1:
+            raise RuntimeError("run the first optimisation step eagerly: at global_step 0 the reference "
+                               "leaves the fg / bg terms out of the total (diffusion.py:225)")
+        self._draw()
+        self.opt.zero_grad()
+        engine.shared_step(self._batch(), sync=False)              # warm-up: builds every frozen pack
+        invalidate_all_packed(unet, only_trainable=True)           # ... the trainable ones are rebuilt in the graph
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.terms = engine.shared_step(self._batch(), sync=False)
+
+    def _batch(self):
+        bt = dict(self.static)
+        bt["cond"] = self.static_cond
+        bt["rand"] = self.rand
+        return bt
+
+    @torch.no_grad()
+    def _draw(self):
+        """The step's random draws, with the reference's samplers / formulas, into the static buffers."""
+        lf = self.engine.loss_fn
+        b = self.rand["sigma"].shape[0]
+        self.rand["sigma"].copy_(lf.sigma_sampler(b))
+        self.rand["sigma_ref"].copy_(lf.sigma_sampler_ref(b))
+        for n_ in ("noise", "noise_ref", "noise_ref2"):
+            self.rand[n_].normal_()
+        for s_ in self.stratified or []:
+            res, rm = s_["res"], s_["rm"]
+            xy, depths, dists = s_["bins"]
+            dev = xy.device
+
+            def positions():   # get_patch_raybundle, stratified (utils_cameraray.py:111-140)
+                edges = torch.linspace(1, -1, res + 1, device=dev)
+                center = (edges[1:] + edges[:-1]) / 2.0
+                upper = torch.cat([center, edges[-1:]], -1)
+                lower = torch.cat([edges[:1], center], -1)
+                return (lower + (upper - lower) * torch.rand(res + 1, device=dev))[:-1]
+
+            hpos, vpos = positions(), positions()
+            xy[:, 0].copy_(hpos[None, :].expand(res, res).reshape(-1))
+            xy[:, 1].copy_(vpos[:, None].expand(res, res).reshape(-1))
+            lower = rm.lengths_lower.to(device=dev, dtype=torch.float32)
+            upper = rm.lengths_upper.to(device=dev, dtype=torch.float32)
+            jit = lower[None] + (upper - lower)[None] * torch.rand(depths.shape[0], depths.shape[1] + 1, device=dev)
+            depths.copy_((jit[:, :-1] + jit[:, 1:]) / 2.0)            # Raymarcher.stratified_sampling (:317-325)
+            dists.copy_(jit[:, 1:] - jit[:, :-1])
+
+    @torch.no_grad()
+    def __call__(self, batch: dict, step_optimizer: bool = True):
+        """One optimisation step on `batch`; returns the (device) total loss of the step."""
+        from ..modules.utils_cameraray import pack_pose
+        for key in self.keys:
+            self.static[key].copy_(batch[key], non_blocking=True)
+        self.static["pose"].copy_(pack_pose(batch["pose"], self.static["pose"].device), non_blocking=True)
+        for n_, t in batch["cond"].items():
+            self.static_cond[n_].copy_(t, non_blocking=True)
+        self._draw()
+        self.graph.replay()
+        if step_optimizer:
+            self.opt.step()
+        return self.loss

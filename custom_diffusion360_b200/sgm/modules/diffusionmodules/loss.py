@@ -8,7 +8,8 @@ autograd: the call keeps the taped UNet forward, and `backward(...)` — called 
 (diffusion.py:221-236) — seeds the gradient kernels and runs the UNet backward.
 
 Random draws (σ indices, the three noise tensors, stratified-sampling variates) are taken from
-`batch["rand"]` when present (keys: sigma_idx, sigma_ref_idx, noise, noise_ref, noise_ref2, jitter),
+`batch["rand"]` when present (keys: sigma_idx | sigma, sigma_ref_idx | sigma_ref, noise, noise_ref,
+noise_ref2, jitter),
 so a test can replay exactly what the oracle / reference drew; otherwise torch's generator is used
 like the reference does.
 """
@@ -54,13 +55,14 @@ class StandardDiffusionLossImgRef(nn.Module):
         rnd = batch.get("rand", {}) if isinstance(batch, dict) else {}
         dev = input.device
         b = input.shape[0]
-        sigmas = self.sigma_sampler(b, rand=rnd.get("sigma_idx")).to(dev)
+        sigmas = rnd["sigma"] if "sigma" in rnd else self.sigma_sampler(b, rand=rnd.get("sigma_idx")).to(dev)
         noise = rnd["noise"].to(dev) if "noise" in rnd else torch.randn_like(input)
         noised_input = (input + noise * append_dims(sigmas, input.ndim)).float().contiguous()
         extra = {}
         sigmas_ref = None
         if self.sigma_sampler_ref is not None:
-            sigmas_ref = self.sigma_sampler_ref(b, rand=rnd.get("sigma_ref_idx")).to(dev)
+            sigmas_ref = (rnd["sigma_ref"] if "sigma_ref" in rnd
+                          else self.sigma_sampler_ref(b, rand=rnd.get("sigma_ref_idx")).to(dev))
             if input_ref is not None:
                 nr = rnd["noise_ref"].to(dev) if "noise_ref" in rnd else torch.randn_like(input_ref)
                 input_ref = input_ref + nr * append_dims(sigmas_ref, input_ref.ndim)   # loss.py:163-170

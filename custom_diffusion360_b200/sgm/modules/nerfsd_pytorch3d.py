@@ -92,9 +92,14 @@ class FeatureNeRFEncoding(nn.Module):
                      w2=self.plane_coefs[2].weight.detach().to(torch.bfloat16).contiguous(),
                      b2=self.plane_coefs[2].bias.detach().float().contiguous(),
                      wnv_geo=wnv[0, c:].detach().float().contiguous(),
-                     bnv=float(self.nviews.bias.detach().float().item()),
+                     # the bias shifts every view's logit alike (the view softmax ignores it); reading it
+                     # needs a host sync, which a CUDA-graph capture forbids: keep the last value there
+                     bnv=(self.__dict__.get("_bnv_host", 0.0)
+                          if (dev.type == "cuda" and torch.cuda.is_current_stream_capturing())
+                          else float(self.nviews.bias.detach().float().item())),
                      wd=self.decoder.weight.detach().to(torch.bfloat16).contiguous())
             self._packed = p
+            self.__dict__["_bnv_host"] = p["bnv"]
         return p
 
 

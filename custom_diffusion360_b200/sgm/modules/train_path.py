@@ -121,6 +121,8 @@ def nerf_bins(nerf, hw: int, dev, jitter: Optional[dict]):
     if not jitter:
         depths, dists = rm.bins(hw, dev)
         return patch_ray_xy(res, dev), depths, dists
+    if "bins" in jitter:      # already on the device (graph-replayed step: static buffers)
+        return jitter["bins"]
 
     def jittered_positions(r):
         edges = torch.linspace(1, -1, res + 1, dtype=f32)
