@@ -24,6 +24,7 @@ SOURCES = [
     "nerf.cu",
     "attention_bwd.cu",
     "train.cu",
+    "vae.cu",
 ]
 
 NVCC_FLAGS = [

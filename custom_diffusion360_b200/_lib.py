@@ -65,6 +65,8 @@ SIGNATURES = {
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
+    "cd360_pointwise_conv_nchw_f32": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _L, C.c_float, _P]),
+    "cd360_softmax_rows_f32_bf16": (C.c_int, [_P, _L, _P, _L, _L, _I, C.c_float, _P]),
     "cd360_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),
     "cd360_nchw_f32_to_nhwc_bf16": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     # training step (backward / loss / optimiser)

@@ -907,10 +907,11 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   int rc;
   if (a->conv) {
     const int C = a->C, H = a->H, W = a->W, B = a->B;
-    if (C <= 0 || (C % BK) != 0 || !is_pow2(H) || !is_pow2(W) || W > 128 || B <= 0)
-      return CD360_ERR_SHAPE;
+    if (C <= 0 || (C % BK) != 0 || !is_pow2(H) || !is_pow2(W) || B <= 0) return CD360_ERR_SHAPE;
     if (static_cast<long long>(B) * H * W != a->M) return CD360_ERR_SHAPE;
-    const int tw = W;  // W <= 128: a tile always covers whole image rows
+    // W <= 128: a tile covers whole image rows; wider images (the VAE decoder, up to 1024):
+    // 128-pixel segments of one row — powers of two, so a tile never straddles rows or images
+    const int tw = W < BM ? W : BM;
     int th = BM / tw;
     if (th > H) th = H;
     const int tb = BM / (tw * th);

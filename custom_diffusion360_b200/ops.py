@@ -322,6 +322,36 @@ def nchw_to_nhwc_bf16(x, *, out=None):
     return out
 
 
+@_op("other")
+def pointwise_conv_nchw(x, w, bias=None, *, scale=1.0, out=None):
+    """fp32 NCHW 1x1 convolution with <= 8 channels either side (the VAE's post_quant_conv with
+    1/scale_factor folded in): out = bias + scale * w @ x."""
+    lib = _lib.load()
+    _req(x, f32, "x")
+    _req(w, f32, "w")
+    b, cin = x.shape[:2]
+    cout = w.shape[0]
+    hw = x.numel() // (b * cin)
+    if out is None:
+        out = torch.empty((b, cout) + tuple(x.shape[2:]), device=x.device, dtype=f32)
+    check(lib.cd360_pointwise_conv_nchw_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), b, cin, cout, hw,
+                                            float(scale), _stream()), "cd360_pointwise_conv_nchw_f32")
+    return out
+
+
+@_op("softmax")
+def softmax_rows(s, *, scale=1.0, out=None):
+    """softmax(scale * s) along the last dim: fp32 [rows, n] -> bf16 [rows, n]."""
+    lib = _lib.load()
+    _req(s, f32, "s")
+    rows, n = s.shape
+    if out is None:
+        out = torch.empty((rows, n), device=s.device, dtype=bf16)
+    check(lib.cd360_softmax_rows_f32_bf16(_ptr(s), s.stride(0), _ptr(out), out.stride(0), rows, n,
+                                          float(scale), _stream()), "cd360_softmax_rows_f32_bf16")
+    return out
+
+
 @_op("nerf")
 def nerf_points(cams, xy, depths, w_nv_geo, b_nv, b, n, res, d, kpe):
     lib = _lib.load()

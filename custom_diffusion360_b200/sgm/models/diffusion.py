@@ -27,6 +27,7 @@ import torch.nn as nn
 from ..modules.diffusionmodules.sampling import FusedGuidedStep
 from ..modules.diffusionmodules.wrappers import OPENAIUNETWRAPPER
 from ..util import default, get_obj_from_str, instantiate_from_config
+from .autoencoder import AutoencoderKL as _OwnAutoencoder
 
 
 def _cfg_get(cfg, path, dflt=None):
@@ -92,8 +93,31 @@ class DiffusionEngine(nn.Module):
     def set_reference_choices(self, choices):
         self.model.diffusion_model.set_reference_choices(choices)
 
+    def init_first_stage(self, config=None):
+        """Instantiate the first stage for `decode_first_stage` (reference :191-202).  Only targets of
+        this package are built (the decode-only AutoencoderKL of sgm/models/autoencoder.py); with the
+        reference's own `sgm.models.autoencoder.*` target the caller keeps the reference object and
+        assigns it to `.first_stage_model` itself."""
+        config = default(config, self.first_stage_config)
+        if config is None or not str(config.get("target", "")).startswith("custom_diffusion360_b200."):
+            raise NotImplementedError("first_stage_config.target must be custom_diffusion360_b200.sgm.models."
+                                      "autoencoder.AutoencoderKLInferenceWrapper to be built here")
+        model = instantiate_from_config(config).eval()
+        for p_ in model.parameters():
+            p_.requires_grad = False
+        self.first_stage_model = model.to(self.device)
+        return self.first_stage_model
+
+    @torch.no_grad()
     def decode_first_stage(self, z):
-        raise NotImplementedError("VAE decode is the first 'next' row of SURVEY §8f; this engine returns latents")
+        """z / scale_factor -> first_stage_model.decode (reference :207-212); the division is folded
+        into the 1x1 post_quant_conv of the decode kernel chain."""
+        if self.first_stage_model is None:
+            self.init_first_stage()
+        fs = self.first_stage_model
+        if isinstance(fs, _OwnAutoencoder):
+            return fs.decode(z, scale=1.0 / self.scale_factor)
+        return fs.decode(1.0 / self.scale_factor * z)      # a reference first stage assigned by the caller
 
     @torch.no_grad()
     def sample(self, cond: Dict, uc: Union[Dict, None] = None, batch_size: int = 16, num_steps=None,

@@ -77,3 +77,113 @@ def append_zero(x):
     import torch
 
     return torch.cat([x, x.new_zeros([1])])
+
+
+# ---- delta checkpoint + camera.bin I/O without pytorch3d -------------------------
+def delta_state_dict(engine, embed=None) -> dict:
+    """What the reference's `CUDACallback.on_save_checkpoint` keeps (main.py:611-625): every
+    state-dict entry whose key contains `pose` (but not `raymarcher`) or `references`, under the
+    Lightning module's key names (`model.diffusion_model.<name>`), plus `embed` — the two trained
+    token rows of the text encoders, which belong to the conditioner (outside this build) and are
+    passed through when the caller has them."""
+    st = engine.state_dict()
+    out = {k: v.detach().clone() for k, v in st.items()
+           if ("pose" in k and "raymarcher" not in k) or "references" in k}
+    if embed is not None:
+        out["embed"] = list(embed)
+    return out
+
+
+def save_delta_checkpoint(engine, path, embed=None, **extra):
+    """`torch.save({'delta_state_dict': …})` — the file `sample.py --custom_model_dir` reads back
+    through `load_model_from_config`'s delta branch (sgm/util.py:225-237)."""
+    import torch
+
+    torch.save({"delta_state_dict": delta_state_dict(engine, embed), **extra}, path)
+
+
+class _CameraShell:
+    """Stand-in for any pytorch3d class met while unpickling `camera.bin`: keeps the pickled
+    attribute dict (R, T, focal_length, principal_point, …) and nothing else."""
+
+    def __init__(self, *a, **kw):
+        pass
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {})
+
+
+def _camera_unpickler():
+    import pickle
+    import types
+
+    class Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split(".")[0] == "pytorch3d":
+                return type(name, (_CameraShell,), {})
+            return super().find_class(module, name)
+
+    return types.SimpleNamespace(Unpickler=Unpickler, load=lambda f, **kw: Unpickler(f, **kw).load(),
+                                 __name__="pickle")
+
+
+def _as_packed(cam):
+    import torch
+
+    from .modules.utils_cameraray import pack_camera_batch
+
+    if isinstance(cam, torch.Tensor):
+        return pack_camera_batch(cam)
+    d = cam if isinstance(cam, dict) else cam.__dict__
+    # nn.Module pickles keep plain tensor attributes in __dict__ and registered ones in _buffers / _parameters
+    fields = {}
+    for key in ("R", "T", "focal_length", "principal_point"):
+        v = d.get(key)
+        if v is None:
+            for bag in ("_buffers", "_parameters"):
+                v = (d.get(bag) or {}).get(key, v)
+        if v is None:
+            raise KeyError(f"camera.bin entry has no `{key}`")
+        fields[key] = v
+    import types
+
+    return pack_camera_batch(types.SimpleNamespace(**fields))
+
+
+def load_camera_bin(path):
+    """`camera.bin` = `torch.save([cameras_val, cameras_train])`, two lists of pytorch3d
+    `PerspectiveCameras` (main.py:1025-1029, read at sample.py:273).  Returns the same pair as packed
+    fp32 tensors `[N, 16]` = R(9) | T(3) | focal(2) | principal point(2), one row per camera —
+    directly usable as `pose` entries (`torch.cat([target_row, train_rows[choices]])`) — without
+    importing pytorch3d: its classes are unpickled into attribute shells."""
+    import torch
+
+    with open(path, "rb") as f:
+        cams_val, cams_train = torch.load(f, map_location="cpu", pickle_module=_camera_unpickler(),
+                                          weights_only=False)
+
+    def rows(lst):
+        if isinstance(lst, torch.Tensor):
+            return lst.float()
+        if not isinstance(lst, (list, tuple)):
+            lst = [lst]
+        return torch.cat([_as_packed(c) for c in lst], dim=0)
+
+    return rows(cams_val), rows(cams_train)
+
+
+def reference_choices(n_train: int, num_ref: int = 8):
+    """The stored reference views sample.py conditions on (sample.py:275-278)."""
+    import torch
+
+    max_diff = n_train / num_ref
+    return [int(x) for x in torch.linspace(0, n_train - max_diff, num_ref)]
+
+
+def sample_pose(cams_val, cams_train, target_index: int, choices=None):
+    """One `pose` entry as sample.py builds it (:302,326): target camera followed by the chosen
+    training cameras, packed `[1 + len(choices), 16]`."""
+    import torch
+
+    choices = reference_choices(cams_train.shape[0]) if choices is None else choices
+    return torch.cat([cams_val[target_index:target_index + 1], cams_train[list(choices)]], dim=0)

@@ -236,6 +236,25 @@ int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t
 int cd360_nchw_f32_to_nhwc_bf16(const float* x, void* out, int32_t batch, int32_t hw, int32_t c,
                                 cd360_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * VAE decode after the sampling loop: DiffusionEngine.decode_first_stage
+ * (sgm/models/diffusion.py:207-212) -> AutoencoderKL.decode (sgm/models/autoencoder.py:313-316) ->
+ * Decoder.forward (sgm/modules/diffusionmodules/model.py:715-757).  Convolutions, GroupNorm+swish,
+ * nearest upsampling and the 1x1 q/k/v/proj_out reuse the entry points above; these two are new.
+ * --------------------------------------------------------------------------------------------- */
+/* out[b, o, p] = bias[o] + scale * sum_c w[o, c] x[b, c, p]; fp32 NCHW, cin, cout <= 8: the 1x1
+ * post_quant_conv (autoencoder.py:314) with decode_first_stage's 1/scale_factor (diffusion.py:209)
+ * folded into the weights.  bias may be NULL. */
+int cd360_pointwise_conv_nchw_f32(const float* x, const float* w, const float* bias, float* out,
+                                  int32_t batch, int32_t cin, int32_t cout, int64_t hw, float scale,
+                                  cd360_stream_t stream);
+/* out[r, :] = softmax(scale * s[r, :]) — fp32 scores [rows, n] (row stride lds) -> bf16 weights
+ * (row stride ldo); n % 4 == 0.  The softmax of MemoryEfficientAttnBlock (model.py:231-266: ONE head
+ * of width C over all H*W pixels, scale C^-0.5), between the score GEMM q k^T (fp32 out) and the
+ * P v GEMM of cd360_gemm_bf16. */
+int cd360_softmax_rows_f32_bf16(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows,
+                                int32_t n, float scale, cd360_stream_t stream);
+
 /* =============================================================================================
  * Training step: backward of the path above towards the pose weights
  * (trainkeys 'pose', sgm/models/diffusion.py:139-144), the loss of

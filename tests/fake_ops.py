@@ -46,7 +46,7 @@ class Fake:
     def conv3x3(self, x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None,
                 out_fp32=False, block_n=0, max_ctas=0):
         assert x.dtype == bf16 and x.shape[0] == B * H * W and w.shape[1] == 9 * x.shape[1]
-        assert x.shape[1] % 64 == 0 and (H & (H - 1)) == 0 and (W & (W - 1)) == 0 and W <= 128
+        assert x.shape[1] % 64 == 0 and (H & (H - 1)) == 0 and (W & (W - 1)) == 0
         N = w.shape[0]
         if row_bias is not None:
             assert row_bias.shape == (B, N)
@@ -167,6 +167,17 @@ class Fake:
     def transpose_to_bf16(self, x, *, ld_out=None):
         rows, cols = x.shape
         return torch.zeros(cols, (rows + 7) // 8 * 8 if ld_out is None else ld_out, dtype=bf16)
+
+    def pointwise_conv_nchw(self, x, w, bias=None, *, scale=1.0, out=None):
+        assert x.dtype == f32 and w.dtype == f32 and w.shape[1] == x.shape[1] and max(w.shape) <= 8
+        self._log("pointwise_conv", cin=x.shape[1], cout=w.shape[0], scale=scale)
+        return torch.zeros(x.shape[0], w.shape[0], *x.shape[2:], dtype=f32)
+
+    def softmax_rows(self, s, *, scale=1.0, out=None):
+        assert s.dtype == f32 and s.dim() == 2 and s.shape[1] % 4 == 0
+        assert out is None or (out.shape == s.shape and out.dtype == bf16)
+        self._log("softmax_rows", rows=s.shape[0], n=s.shape[1], scale=scale)
+        return out if out is not None else torch.zeros(s.shape, dtype=bf16)
 
     def colsum(self, x, *, out=None):
         assert out is None or out.shape == (x.shape[1],)

@@ -150,3 +150,114 @@ def test_training_step_control_flow_with_fake_kernels():
     for p_, o in zip(opt.flat.params, opt.flat.offsets):
         assert o % 4 == 0 and p_.data_ptr() == opt.flat.data.data_ptr() + 4 * o
         assert p_.grad.data_ptr() == opt.flat.grad.data_ptr() + 4 * o
+
+
+def test_delta_checkpoint_round_trip(tmp_path):
+    """Delta-checkpoint key contract (main.py:611-625 save, sgm/util.py:225-237 load): pose weights and
+    `references` buffers, under `model.diffusion_model.*`, nothing else; loading restores them."""
+    from tests import test_train_step_gpu as G
+    from custom_diffusion360_b200.sgm import util as U
+    cfg = dict(O.TINY_CFG)
+    sd = O.synthetic_state_dict(cfg, seed=2)
+    eng = G._engine(cfg, sd, torch.device("cpu"))
+    unet = eng.model.diffusion_model
+    names = [n for n, _ in unet.pose_blocks()]
+    refs = {}
+    for n, m in unet.pose_blocks():
+        c = m.pose_emb_layers.weight.shape[0]
+        refs[n] = torch.randn(5, 16, c)
+    unet.register_references(refs)
+    path = tmp_path / "delta.ckpt"
+    U.save_delta_checkpoint(eng, path, embed=[torch.zeros(1, 8), torch.zeros(1, 8)])
+    ck = torch.load(path, weights_only=False)
+    delta = ck["delta_state_dict"]
+    keys = [k for k in delta if k != "embed"]
+    assert all(k.startswith("model.diffusion_model.") for k in keys)
+    assert all(("pose" in k and "raymarcher" not in k) or "references" in k for k in keys)
+    trainable = {"model.diffusion_model." + n for n, p in unet.named_parameters() if p.requires_grad}
+    assert trainable <= set(keys)
+    assert {f"model.diffusion_model.{n}.references" for n in names} <= set(keys)
+    eng2 = G._engine(cfg, O.synthetic_state_dict(cfg, seed=7), torch.device("cpu"))
+    base = {"model.diffusion_model." + k: v for k, v in O.synthetic_state_dict(cfg, seed=7).items()}
+    missing, unexpected = U.load_checkpoints(eng2, base, delta)
+    assert not missing and not unexpected
+    u2 = eng2.model.diffusion_model
+    for (n, p), (_, q) in zip(unet.named_parameters(), u2.named_parameters()):
+        if p.requires_grad:
+            assert torch.equal(p, q), n
+    for (n, m), (_, m2) in zip(unet.pose_blocks(), u2.pose_blocks()):
+        assert torch.equal(m.references, m2.references), n
+
+
+def test_camera_bin_loads_without_pytorch3d(tmp_path):
+    """camera.bin is a pickle of pytorch3d PerspectiveCameras lists (main.py:1025-1029); the loader
+    must read it with pytorch3d absent and return packed [N,16] rows."""
+    import sys
+    import types
+
+    from custom_diffusion360_b200.sgm import util as U
+    assert "pytorch3d" not in sys.modules
+    pkg = types.ModuleType("pytorch3d")
+    ren = types.ModuleType("pytorch3d.renderer")
+    cams = types.ModuleType("pytorch3d.renderer.cameras")
+
+    class PerspectiveCameras(torch.nn.Module):   # pickles like the real one: plain tensor attributes on an nn.Module
+        def __init__(self, R, T, focal_length, principal_point):
+            super().__init__()
+            self.R, self.T, self.focal_length, self.principal_point = R, T, focal_length, principal_point
+            self.in_ndc = True
+
+    PerspectiveCameras.__module__ = "pytorch3d.renderer.cameras"
+    PerspectiveCameras.__qualname__ = "PerspectiveCameras"
+    cams.PerspectiveCameras = PerspectiveCameras
+    sys.modules.update({"pytorch3d": pkg, "pytorch3d.renderer": ren, "pytorch3d.renderer.cameras": cams})
+    try:
+        g = torch.Generator().manual_seed(0)
+        mk = lambda: PerspectiveCameras(torch.randn(1, 3, 3, generator=g), torch.randn(1, 3, generator=g),
+                                        torch.rand(1, 2, generator=g) + 1, torch.zeros(1, 2))
+        val, train = [mk() for _ in range(3)], [mk() for _ in range(20)]
+        torch.save([val, train], tmp_path / "camera.bin")
+    finally:
+        for k in ("pytorch3d", "pytorch3d.renderer", "pytorch3d.renderer.cameras"):
+            sys.modules.pop(k)
+    cv, ct = U.load_camera_bin(tmp_path / "camera.bin")
+    assert "pytorch3d" not in sys.modules
+    assert cv.shape == (3, 16) and ct.shape == (20, 16)
+    assert torch.equal(ct[4, :9], train[4].R.reshape(-1)) and torch.equal(ct[4, 9:12], train[4].T[0])
+    assert torch.equal(cv[1, 12:14], val[1].focal_length[0])
+    choices = U.reference_choices(20, 8)
+    assert choices == [int(x) for x in torch.linspace(0, 20 - 20 / 8, 8)]       # sample.py:275-278
+    pose = U.sample_pose(cv, ct, 2, choices)
+    assert pose.shape == (9, 16) and torch.equal(pose[0], cv[2]) and torch.equal(pose[3], ct[choices[2]])
+
+
+def test_vae_decoder_host_logic_with_fake_kernels():
+    """First-stage decode: state-dict contract of the decode-only AutoencoderKL,
+    kernel-call sequence of one decode, and DiffusionEngine.decode_first_stage folding 1/scale_factor
+    into the post_quant_conv call."""
+    from collections import Counter
+
+    from oracle import vae_oracle as V
+    from custom_diffusion360_b200.sgm.models.autoencoder import AutoencoderKLInferenceWrapper
+    cfg = dict(V.TINY_VAE_CFG)
+    vae = AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=cfg, lossconfig={"target": "torch.nn.Identity"},
+                                        monitor="val/rec_loss").eval()
+    assert {k: tuple(v.shape) for k, v in vae.state_dict().items()} == V.param_shapes(cfg)
+    sd = V.synthetic_state_dict(cfg, seed=1)
+    missing, ignored = vae.load_decode_state_dict(dict(sd, **{"encoder.conv_in.bias": torch.zeros(3)}))
+    assert not missing and ignored == ["encoder.conv_in.bias"]
+    with pytest.raises(KeyError):
+        vae.load_decode_state_dict({"decoder.bogus": torch.zeros(1)})
+    with pytest.raises(NotImplementedError):
+        vae.encode(torch.zeros(1, 3, 64, 64))
+    with patched_ops() as fake:
+        img = vae.decode(torch.randn(2, 4, 16, 16), scale=1 / 0.13025)
+    assert img.shape == (2, 3, 128, 128)
+    calls = Counter(k for k, _ in fake.calls)
+    n_res = 2 + 3 * len(cfg["ch_mult"])
+    assert calls["conv3x3"] == 2 * n_res + (len(cfg["ch_mult"]) - 1) + 1      # res convs + upsample convs + conv_out
+    assert calls["softmax_rows"] == 2                                          # one hw x hw score matrix per image
+    pw = [kw for k, kw in fake.calls if k == "pointwise_conv"]
+    assert len(pw) == 1 and abs(pw[0]["scale"] - 1 / 0.13025) < 1e-9
+    sm = [kw for k, kw in fake.calls if k == "softmax_rows"][0]
+    assert sm["rows"] == sm["n"] == 256 and abs(sm["scale"] - (cfg["ch"] * cfg["ch_mult"][-1]) ** -0.5) < 1e-9

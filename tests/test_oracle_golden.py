@@ -127,3 +127,20 @@ def test_training_oracle_vs_reference_golden():
         scale = max(float(ref["sample"].abs().max()), 1e-3 * ref["norm"], 1e-9)
         assert float((smp - ref["sample"]).abs().max()) <= 2e-3 * scale, k
         assert abs(float(g.norm()) - ref["norm"]) <= 2e-3 * max(ref["norm"], 1e-9), k
+
+
+def test_vae_decoder_oracle_vs_reference_golden():
+    """oracle/vae_oracle.py against the output of the reference's own Decoder (+ post_quant_conv and
+    1/scale_factor) committed by tests/golden/make_vae_golden.py; the fixture is stored in fp16."""
+    import os
+
+    from oracle import vae_oracle as V
+    from tests.golden.make_vae_golden import latent
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vae_decoder_golden.pt"), weights_only=False)
+    cfg = dict(V.TINY_VAE_CFG)
+    sd = V.synthetic_state_dict(cfg, seed=g["seed_w"])
+    z = latent(g["seed_z"], g["batch"], g["latent"])
+    img = V.decode_first_stage(sd, cfg, z, g["scale_factor"])
+    ref = g["image"].float()
+    assert img.shape == ref.shape == (g["batch"], 3, 8 * g["latent"], 8 * g["latent"])
+    assert float((img - ref).abs().max()) <= 2e-3 * float(ref.abs().max())       # fp16 storage of the fixture

@@ -239,3 +239,27 @@ def test_training_step_vs_reference(ns, train_mode):
     for k, g in grads_ref.items():
         scale = max(float(g.abs().max()), 1e-6)
         assert float((grads[k] - g).abs().max()) <= 2e-3 * scale, (k, float((grads[k] - g).abs().max()), scale)
+
+
+def test_vae_decoder_oracle_vs_reference():
+    """oracle/vae_oracle.py against the reference's own Decoder module imported in place
+    (sgm/modules/diffusionmodules/model.py:604-757): parameter names / shapes and the output."""
+    import importlib
+
+    import torch.nn.functional as F
+
+    from oracle import vae_oracle as V
+    H.install()
+    m = importlib.import_module("sgm.modules.diffusionmodules.model")
+    cfg = dict(V.TINY_VAE_CFG)
+    dec = m.Decoder(**cfg).eval()
+    assert type(dec.mid.attn_1).__name__ == "MemoryEfficientAttnBlock"
+    ours = {k[len("decoder."):]: s for k, s in V.param_shapes(cfg).items() if k.startswith("decoder.")}
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == ours
+    sd = V.synthetic_state_dict(cfg, seed=4)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")})
+    z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = dec(F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+    out = V.autoencoder_decode(sd, cfg, z)
+    assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
