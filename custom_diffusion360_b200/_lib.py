@@ -60,7 +60,7 @@ SIGNATURES = {
     "cd360_upsample_nearest2x_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "cd360_cfg_euler_step": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _P]),
     "cd360_cfg_euler_step_dev": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _F, _F, _P]),
-    "cd360_nerf_points": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "cd360_nerf_points": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_combine": (C.c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),

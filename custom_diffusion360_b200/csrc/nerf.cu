@@ -86,7 +86,7 @@ __device__ __forceinline__ void pos_enc(const float (&v)[DIM], F&& emit) {
 __global__ void __launch_bounds__(128)
 nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
                    const float* __restrict__ depths, const float* __restrict__ w_nv_geo,
-                   float b_nv, __nv_bfloat16* __restrict__ pe, int* __restrict__ gidx,
+                   const float* __restrict__ b_nv, __nv_bfloat16* __restrict__ pe, int* __restrict__ gidx,
                    float* __restrict__ gwgt, float* __restrict__ vlogit, int nb, int n, int res,
                    int d, int kpe) {
   CD360_TL(16);  // tools/step_timeline.py; empty in the product build
@@ -128,7 +128,7 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
   // shared-over-views part of the logit: PE16(p in target view frame) (96) | p_tgt (3)
   float p_t[3];
   xform_point(tgt, pw, p_t);
-  float logit_pt = b_nv;
+  float logit_pt = b_nv != nullptr ? __ldg(b_nv) : 0.f;
   pos_enc<3, 16>(p_t, [&](int idx, float val) { logit_pt += s_w[idx] * val; });
 #pragma unroll
   for (int k = 0; k < 3; ++k) logit_pt += s_w[96 + k] * p_t[k];
@@ -367,7 +367,7 @@ nerf_volrender_kernel(const __nv_bfloat16* __restrict__ feats, const float* __re
 using namespace cd360;
 
 extern "C" int cd360_nerf_points(const float* cams, const float* xy, const float* depths,
-                                 const float* w_nv_geo, float b_nv, void* pe, int32_t* gidx,
+                                 const float* w_nv_geo, const float* b_nv, void* pe, int32_t* gidx,
                                  float* gwgt, float* vlogit, int32_t b, int32_t n, int32_t res,
                                  int32_t d, int32_t kpe, cd360_stream_t stream_) {
   if (!cams || !xy || !depths || !w_nv_geo || !pe || !gidx || !gwgt || !vlogit)

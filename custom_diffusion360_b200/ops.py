@@ -361,7 +361,7 @@ def nerf_points(cams, xy, depths, w_nv_geo, b_nv, b, n, res, d, kpe):
     gidx = torch.empty((b * n * hw * d, 4), device=dev, dtype=torch.int32)
     gwgt = torch.empty((b * n * hw * d, 4), device=dev, dtype=f32)
     vlogit = torch.empty((b, n, hw * d), device=dev, dtype=f32)
-    check(lib.cd360_nerf_points(_ptr(cams), _ptr(xy), _ptr(depths), _ptr(w_nv_geo), float(b_nv),
+    check(lib.cd360_nerf_points(_ptr(cams), _ptr(xy), _ptr(depths), _ptr(w_nv_geo), _ptr(b_nv),
                                 _ptr(pe), _ptr(gidx), _ptr(gwgt), _ptr(vlogit), b, n, res, d, kpe,
                                 _stream()), "cd360_nerf_points")
     return pe, gidx, gwgt, vlogit

@@ -224,6 +224,10 @@ class DiffusionEngine(nn.Module):
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             opt.attach_overlap(self.model.diffusion_model)
+        # the parameters were re-homed into the optimiser's flat buffer: packs built before hold views
+        # of / copies from the old storage
+        from ..modules.attention import invalidate_all_packed
+        invalidate_all_packed(self.model.diffusion_model, only_trainable=True, keep_buffers=False)
         return opt
 
     def _after_optimizer_step(self):
@@ -239,8 +243,10 @@ class GraphedTrainStep:
     the GPU.  Per call: the batch and the step's random draws (sigma indices from the reference's
     samplers, three noise tensors, stratified ray / depth variates) are written into static
     buffers, the graph replays, then the optimiser runs (gradient all-reduce + fused AdamW).
-    The bf16 operand packs of the TRAINABLE weights are rebuilt inside the graph from the fp32
-    masters, so every replay sees the previous optimiser update."""
+    The bf16 operand packs of the TRAINABLE weights live in persistent buffers that are refreshed in
+    place from the fp32 masters inside the graph (attention._Packed.mark_stale), so every replay sees
+    the previous optimiser update and the eager step shares the same buffers; the nviews bias is read
+    from device memory for the same reason."""
 
     def __init__(self, engine: "DiffusionEngine", opt, batch: dict):
         from ..modules.attention import invalidate_all_packed
@@ -276,7 +282,7 @@ class GraphedTrainStep:
         self._draw()
         self.opt.zero_grad()
         engine.shared_step(self._batch(), sync=False)              # warm-up: builds every frozen pack
-        invalidate_all_packed(unet, only_trainable=True)           # ... the trainable ones are rebuilt in the graph
+        invalidate_all_packed(unet, only_trainable=True)           # ... the trainable ones are refreshed IN PLACE inside the graph
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -48,7 +48,13 @@ def to_tokens(x: torch.Tensor) -> torch.Tensor:
 
 
 class _Packed:
-    """Lazily built bf16 / re-laid-out copies of a module's parameters (kernel operand layout)."""
+    """Lazily built bf16 / re-laid-out copies of a module's parameters (kernel operand layout).
+
+    Two ways to invalidate: `invalidate_packed()` drops the copies (rebuilt into NEW tensors on next
+    use); `mark_stale()` keeps the tensors and has the next `packed()` call refresh them IN PLACE
+    (`_refresh`) — what the training loop uses after every optimiser step, so that the addresses a
+    captured CUDA graph (GraphedTrainStep) and the eager step read never change and the refresh
+    itself is part of the graph."""
 
     def packed(self):
         dev = next(self.parameters()).device
@@ -57,21 +63,42 @@ class _Packed:
             p = self._pack(dev)
             p["dev"] = dev
             self.__dict__["_pk"] = p
+            self.__dict__["_pk_stale"] = False
+        elif self.__dict__.get("_pk_stale"):
+            self._refresh(p)
+            self.__dict__["_pk_stale"] = False
         return p
+
+    def _refresh(self, p):
+        fresh = self._pack(p["dev"])
+        for k, v in fresh.items():
+            if torch.is_tensor(v) and v.data_ptr() != p[k].data_ptr():
+                p[k].copy_(v)
 
     def invalidate_packed(self):
         self.__dict__["_pk"] = None
 
+    def mark_stale(self):
+        if self.__dict__.get("_pk") is not None:
+            self.__dict__["_pk_stale"] = True
 
-def invalidate_all_packed(root: nn.Module, only_trainable: bool = False):
-    """Drop the packed operand copies so they are rebuilt from the parameters.  only_trainable: just
-    those of the pose weights (after an optimiser step; the frozen packs stay)."""
+
+def invalidate_all_packed(root: nn.Module, only_trainable: bool = False, keep_buffers: bool = True):
+    """Make the packed operand copies follow the parameters again.  only_trainable: just those of the
+    pose weights (after an optimiser step; the frozen packs stay) — by default refreshed in place
+    (`keep_buffers`), see _Packed; otherwise every pack is dropped and rebuilt."""
     for m in root.modules():
         if only_trainable:
             if hasattr(m, "pose_emb_layers"):
-                m.pose_emb_layers.invalidate_packed()
-                m.pose_featurenerf.model._packed = None
-                m.__dict__.pop("_bwdpk_pose", None)
+                if keep_buffers:
+                    m.pose_emb_layers.mark_stale()
+                    m.pose_featurenerf.model.mark_stale()
+                    if m.__dict__.get("_bwdpk_pose") is not None:
+                        m.__dict__["_bwdpk_pose"]["stale"] = True
+                else:
+                    m.pose_emb_layers.invalidate_packed()
+                    m.pose_featurenerf.model._packed = None
+                    m.__dict__.pop("_bwdpk_pose", None)
             continue
         if isinstance(m, _Packed):
             m.invalidate_packed()
@@ -88,6 +115,11 @@ class Linear(nn.Linear, _Packed):
     def _pack(self, dev):
         return dict(w=self.weight.detach().to(bf16).contiguous(),
                     b=None if self.bias is None else self.bias.detach().float().contiguous())
+
+    def _refresh(self, p):
+        ops.cast_bf16(self.weight.detach().float().contiguous(), out=p["w"])
+        if self.bias is not None and p["b"].data_ptr() != self.bias.data_ptr():
+            p["b"].copy_(self.bias.detach())
 
     def tokens(self, x, **kw):
         p = self.packed()

@@ -71,36 +71,42 @@ class FeatureNeRFEncoding(nn.Module):
         self.decoder = nn.Linear(out_channels, 1 + (3 if rgb_predict else 0), bias=False)
         nn.init.zeros_(self.decoder.weight)  # zero_module, reference :49-51
         self._packed = None
+        self._stale = True
 
     def packed(self):
+        """bf16 operand packs of the (trainable) MLP; b1 / b2 / wnv_geo / bnv are live fp32 views of the
+        parameters.  After `mark_stale()` the bf16 copies are refreshed IN PLACE (fixed addresses:
+        CUDA-graph replays and the eager step share them, see attention._Packed)."""
         dev = self.nviews.weight.device
         p = self._packed
         if p is None or p["dev"] != dev:
             c = self.plane_coefs[2].weight.shape[0]
+            p = dict(dev=dev, c=c, wg=torch.zeros(c + 8, c, device=dev, dtype=torch.bfloat16),
+                     w1p=torch.zeros(c, KPE, device=dev, dtype=torch.bfloat16),
+                     w2=torch.empty(c, c, device=dev, dtype=torch.bfloat16),
+                     wd=torch.empty(self.decoder.weight.shape, device=dev, dtype=torch.bfloat16))
+            self._packed = p
+            self._stale = True
+        if self._stale:
+            c = p["c"]
             w1 = self.plane_coefs[0].weight.detach()
             wnv = self.nviews.weight.detach()
-            # G projection: rows [0,c) = feature columns of plane_coefs.0, row c = feature columns
-            # of nviews, zero rows up to c+8
-            wg = torch.zeros(c + 8, c, device=dev)
-            wg[:c] = w1[:, :c]
-            wg[c] = wnv[0, :c]
-            w1p = torch.zeros(c, KPE, device=dev)
-            w1p[:, :198] = w1[:, c:]
-            p = dict(dev=dev, c=c, wg=wg.to(torch.bfloat16).contiguous(),
-                     w1p=w1p.to(torch.bfloat16).contiguous(),
-                     b1=self.plane_coefs[0].bias.detach().float().contiguous(),
-                     w2=self.plane_coefs[2].weight.detach().to(torch.bfloat16).contiguous(),
+            # G projection: rows [0,c) = feature columns of plane_coefs.0, row c = feature columns of
+            # nviews, zero rows up to c+8
+            p["wg"][:c].copy_(w1[:, :c])
+            p["wg"][c].copy_(wnv[0, :c])
+            p["w1p"][:, :198].copy_(w1[:, c:])
+            p["w2"].copy_(self.plane_coefs[2].weight.detach())
+            p["wd"].copy_(self.decoder.weight.detach())
+            p.update(b1=self.plane_coefs[0].bias.detach().float().contiguous(),
                      b2=self.plane_coefs[2].bias.detach().float().contiguous(),
                      wnv_geo=wnv[0, c:].detach().float().contiguous(),
-                     # the bias shifts every view's logit alike (the view softmax ignores it); reading it
-                     # needs a host sync, which a CUDA-graph capture forbids: keep the last value there
-                     bnv=(self.__dict__.get("_bnv_host", 0.0)
-                          if (dev.type == "cuda" and torch.cuda.is_current_stream_capturing())
-                          else float(self.nviews.bias.detach().float().item())),
-                     wd=self.decoder.weight.detach().to(torch.bfloat16).contiguous())
-            self._packed = p
-            self.__dict__["_bnv_host"] = p["bnv"]
+                     bnv=self.nviews.bias.detach().float().contiguous())   # read on the device: no host sync
+            self._stale = False
         return p
+
+    def mark_stale(self):
+        self._stale = True
 
 
 class VolRender(nn.Module):

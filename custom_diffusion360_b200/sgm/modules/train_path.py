@@ -81,16 +81,21 @@ def pose_bwd_pack(block: BasicTransformerBlock) -> dict:
     step, unlike the frozen packs above)."""
     p = block.__dict__.get("_bwdpk_pose")
     dev = block.pose_emb_layers.weight.device
-    if p is not None and p["dev"] == dev:
-        return p
     c = block.pose_emb_layers.weight.shape[0]
+    if p is not None and p["dev"] == dev and not p.get("stale"):
+        return p
     wp = block.pose_emb_layers.packed()["w"]
     pk = block.pose_featurenerf.model.packed()
-    wd8 = torch.zeros(8, c, device=dev, dtype=bf16)
-    wd8[: pk["wd"].shape[0]] = pk["wd"]
-    p = dict(dev=dev, wp_x_t=transposed(wp[:, :c]), wp_r_t=transposed(wp[:, c:]),
-             w2n_t=transposed(pk["w2"]), wd_t8=transposed(wd8))
-    block.__dict__["_bwdpk_pose"] = p
+    if p is None or p["dev"] != dev:
+        p = dict(dev=dev, wp_x_t=torch.empty(c, c, device=dev, dtype=bf16), wp_r_t=torch.empty(c, c, device=dev, dtype=bf16),
+                 w2n_t=torch.empty(c, c, device=dev, dtype=bf16), wd_t8=torch.zeros(c, 8, device=dev, dtype=bf16))
+        block.__dict__["_bwdpk_pose"] = p
+    # refreshed in place after every optimiser step (fixed addresses, see attention._Packed)
+    p["wp_x_t"].copy_(wp[:, :c].t())
+    p["wp_r_t"].copy_(wp[:, c:].t())
+    p["w2n_t"].copy_(pk["w2"].t())
+    p["wd_t8"][:, : pk["wd"].shape[0]].copy_(pk["wd"].t())
+    p["stale"] = False
     return p
 
 

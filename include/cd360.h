@@ -203,9 +203,10 @@ int cd360_cfg_euler_step_dev(float* x, const float* eps, float* denoised_out, in
  *                                     gathered-feature term
  * depths: fp32 [hw, d] sample depths along each target ray (Raymarcher, :308-330);
  * xy: fp32 [hw, 2] NDC ray positions (get_patch_raybundle, utils_cameraray.py:103-158).
- * w_nv_geo: fp32 [198] the non-feature columns of nviews.weight, b_nv its bias. */
+ * w_nv_geo: fp32 [198] the non-feature columns of nviews.weight; b_nv: its bias, fp32 [1] in DEVICE
+ * memory (NULL = 0) so that a captured CUDA graph follows optimiser updates of the bias. */
 int cd360_nerf_points(const float* cams, const float* xy, const float* depths,
-                      const float* w_nv_geo, float b_nv, void* pe, int32_t* gidx, float* gwgt,
+                      const float* w_nv_geo, const float* b_nv, void* pe, int32_t* gidx, float* gwgt,
                       float* vlogit, int32_t b, int32_t n, int32_t res, int32_t d, int32_t kpe,
                       cd360_stream_t stream);
 /* Combine: for every (b, ray, sample): h_v = SiLU(hpre[b,v,p,:] + bilinear(G[b,v], gidx,gwgt)[:c]);

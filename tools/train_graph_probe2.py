@@ -41,8 +41,11 @@ invalidate_all_packed(unet, only_trainable=True)
 rand = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in gs.rand.items()}
 le = float(engine.training_step(dict(batch, rand=rand)))
 te = dict(engine.last_loss_dict)
-invalidate_all_packed(unet)
 le_all = float(engine.training_step(dict(batch, rand=rand)))
+gs.graph.replay()
+torch.cuda.synchronize()
+lg_again = float(gs.loss)
+tg_old = {k: round(float(v), 6) for k, v in gs.terms.items()}
 gs2 = GraphedTrainStep(engine, opt, batch)
 for k, v in gs.rand.items():
     if torch.is_tensor(v):
@@ -53,10 +56,8 @@ for a, b_ in zip(gs2.stratified or [], gs.stratified or []):
 gs2.graph.replay()
 torch.cuda.synchronize()
 lg_new = float(gs2.loss)
-gs.graph.replay()
-torch.cuda.synchronize()
-print("old graph %.6f (again %.6f) | eager %.6f | eager after full invalidate %.6f | fresh capture %.6f" % (
-    lg, float(gs.loss), le, le_all, lg_new))
-print("terms old graph", {k: round(float(v), 6) for k, v in gs.terms.items()})
+print("old graph %.6f (again %.6f) | eager %.6f | eager again %.6f | fresh capture %.6f" % (
+    lg, lg_again, le, le_all, lg_new))
+print("terms old graph", tg_old)
 print("terms eager    ", {k: round(float(v), 6) for k, v in te.items()})
 print("terms new graph", {k: round(float(v), 6) for k, v in gs2.terms.items()})
