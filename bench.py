@@ -33,6 +33,53 @@ METRIC = "denoising-steps/sec SDXL 1024^2 pose-cond"
 UNIT = "steps/s"
 
 
+def _hide_launch_latency(seconds: float):
+    """Queue a spin kernel ahead of the per-kernel pass: the host then enqueues the whole eager step
+    (launches + the CUDA events around them) while the GPU is still busy, so the event intervals are
+    back-to-back kernel durations, not host launch gaps (26 us per launch from Python)."""
+    torch.cuda._sleep(int(seconds * 1.9e9))
+
+
+def ncu_traffic(kernel: str):
+    """Average DRAM bytes (read + write) per launch of `kernel` in one steady-state step, from the
+    committed ncu launch list of this command (profiles/launches_r01_summary.json; dram__bytes_read.sum
+    + dram__bytes_write.sum per launch, tools/ncu_step_list.py).  None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "launches_r01_summary.json")
+    try:
+        with open(path) as f:
+            k = json.load(f)["kernels"]
+    except (OSError, ValueError, KeyError):
+        return None
+    for name, v in k.items():
+        if kernel in name:
+            return v.get("dram_bytes_per_launch")
+    return None
+
+
+def decode_timing(latent: int, dev, peaks, reps: int = 5):
+    """VAE decode of ONE image after the loop (DiffusionEngine.decode_first_stage, sample.py:194): the
+    shipped first-stage config, random weights, latent x latent -> 8x; CUDA events, 2 warm-up runs."""
+    from custom_diffusion360_b200 import synthetic as S
+    from custom_diffusion360_b200.sgm.models.autoencoder import AutoencoderKLInferenceWrapper
+    vae = AutoencoderKLInferenceWrapper(embed_dim=4, ddconfig=dict(S.SDXL_VAE_DDCONFIG),
+                                        lossconfig={"target": "torch.nn.Identity"}).eval().to(dev)
+    S.init_random_vae_weights_(vae, seed=5)
+    z = S.SDXL_SCALE_FACTOR * torch.randn(1, 4, latent, latent, device=dev)
+    for _ in range(2):
+        vae.decode(z, scale=1.0 / S.SDXL_SCALE_FACTOR)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        img = vae.decode(z, scale=1.0 / S.SDXL_SCALE_FACTOR)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = S.vae_decode_flops(vae, latent)
+    return {"ms_per_image": ms, "image": list(img.shape), "algorithmic_tflop": fl / 1e12, "tflops": fl / 1e9 / ms,
+            "frac_of_sustained_peak": fl / 1e9 / ms / peaks["sustained"], "cuda_graph": False}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -324,6 +371,7 @@ def run_train(args, world, rank, local_rank):
         return r
 
     ops.LaunchStats.hook = hook
+    _hide_launch_latency(0.25)
     eager_step(999)
     ops.LaunchStats.hook = None
     torch.cuda.synchronize()
@@ -356,8 +404,8 @@ def run_train(args, world, rank, local_rank):
                      "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None, "traffic": None,
                      "launches_per_step": gk.get("launches"), "launched_tflop_per_step": gk.get("launched_tflop"),
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
-        "kernels_note": "per-kernel times come from one extra EAGER step with CUDA events around every launch; that "
-                        "step is host-bound, so the intervals include launch gaps (upper bounds, shares only)",
+        "kernels_note": "per-kernel times come from one extra EAGER step with CUDA events around every launch, "
+                        "enqueued behind a spin kernel so that host launch latency does not enter the intervals",
         "kernels": kern, "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
         "loss_first_step": loss0, "loss_last_step": float(loss), "loss_terms_last_eager_step": engine.last_loss_dict, "clocks": clk,
         "trainable_values": opt.flat.numel, "allreduce_bytes_per_step": 4 * opt.flat.numel if world > 1 else 0,
@@ -480,6 +528,7 @@ def main():
 
         step.use_graph = False
         ops.LaunchStats.hook = hook
+        _hide_launch_latency(0.06)
         step(x, *sched(1))
         ops.LaunchStats.hook = None
         torch.cuda.synchronize()
@@ -508,7 +557,9 @@ def main():
         "config": workload_config(args),
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all linear + implicit-GEMM conv launches of one step)",
                      "bound": "tensor", "achieved": gk.get("tflops"), "peak": peaks["burst"], "unit": "TFLOP/s",
-                     "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None, "traffic": None,
+                     "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None,
+                     "traffic": ncu_traffic("gemm_bf16_tcgen05_kernel") if (args.latent == 128 and args.n_img == 1) else None,
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches)",
                      "launches_per_step": gk.get("launches"), "algorithmic_tflop_per_step": gk.get("algorithmic_tflop"),
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
         "roofline_step": {"bound": "tensor", "algorithmic_tflop_per_step": tflop_step,
@@ -521,6 +572,11 @@ def main():
         "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
         "cuda_graph": not args.no_graph, "clocks": clk,
     }
+    if world == 1:
+        try:
+            line["first_stage_decode"] = decode_timing(args.latent, dev, peaks)
+        except Exception as e:  # a reported extra, never part of the headline
+            line["first_stage_decode"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             base, _, _ = cpu_reference(1, 0, budget_s=30.0, latent=args.latent)

@@ -94,3 +94,45 @@ def make_references(model, latent: int, n_refs: int, device, seed: int = 0) -> d
         hw = (latent // ds) ** 2
         refs[name] = torch.randn(n_refs + 1, hw, c, device=device, generator=g)
     return refs
+
+
+# ---- first stage (VAE decode) ---------------------------------------------------
+# `first_stage_config.params.ddconfig` / `scale_factor` of configs/train_co3d_concept.yaml:5,104-115
+SDXL_VAE_DDCONFIG = dict(attn_type="vanilla-xformers", double_z=True, z_channels=4, resolution=256, in_channels=3,
+                         out_ch=3, ch=128, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+SDXL_SCALE_FACTOR = 0.13025
+
+
+@torch.no_grad()
+def init_random_vae_weights_(vae: torch.nn.Module, seed: int = 0) -> None:
+    """Decode-side weights with O(1) activations through the stack: convs ~ N(0, 1/fan_in), norm
+    gains 1 + 0.1 N, biases 0.05 N."""
+    g = torch.Generator(device=next(vae.parameters()).device)
+    g.manual_seed(seed)
+    for name, p in vae.named_parameters():
+        if p.dim() == 4:
+            p.normal_(0.0, 1.0 / math.sqrt(p[0].numel()), generator=g)
+        elif name.endswith("weight"):
+            p.normal_(1.0, 0.1, generator=g)
+        else:
+            p.normal_(0.0, 0.05, generator=g)
+
+
+def vae_decode_flops(vae, latent: int) -> float:
+    """2*MAC of one decode of a [1, 4, latent, latent] latent: every convolution at the resolution it
+    runs at + the single-head mid attention (4 * hw^2 * C)."""
+    dec = vae.decoder
+    n_levels = dec.num_resolutions
+    fl = 0.0
+    for name, m in dec.named_modules():
+        if not isinstance(m, torch.nn.Conv2d):
+            continue
+        r = latent
+        if name.startswith("up."):
+            lvl = int(name.split(".")[1])
+            r = latent * 2 ** (n_levels - 1 - lvl) * (2 if ".upsample." in name else 1)
+        elif name.startswith("conv_out"):
+            r = latent * 2 ** (n_levels - 1)
+        fl += 2.0 * r * r * m.out_channels * m.in_channels * m.kernel_size[0] * m.kernel_size[1]
+    c = dec.mid.attn_1.in_channels
+    return fl + 4.0 * float(latent * latent) ** 2 * c
