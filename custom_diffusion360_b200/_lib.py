@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
         ("conv", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
         ("act", C.c_int32), ("geglu", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_slabs", C.c_int32), ("ln_eps", C.c_float),
-        ("ln_colsum", C.c_void_p), ("stats_out", C.c_void_p),
+        ("ln_colsum", C.c_void_p), ("stats_out", C.c_void_p), ("k_splits", C.c_int32), ("split_stride", C.c_int64),
     ]
 
 
@@ -65,6 +65,8 @@ SIGNATURES = {
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
+    "cd360_splitk_slices": (C.c_int, [_I, _I, _I]),
+    "cd360_splitk_finish": (C.c_int, [_P, _L, _L, _I, _P, _P, _L, _P, _L, _I, _L, _I, _P]),
     "cd360_pointwise_conv_nchw_f32": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _L, C.c_float, _P]),
     "cd360_softmax_rows_f32_bf16": (C.c_int, [_P, _L, _P, _L, _L, _I, C.c_float, _P]),
     "cd360_nhwc_to_nchw_f32": (C.c_int, [_P, _I, _P, _I, _I, _I, _P]),

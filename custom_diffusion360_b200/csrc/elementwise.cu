@@ -372,6 +372,87 @@ extern "C" int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n,
   return CD360_OK;
 }
 
+namespace cd360 {
+// Finish of a split-K GEMM (cd360_gemm_bf16 with k_splits > 1): one thread per 4 columns, slices
+// summed in ascending order (deterministic).
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, long long ldw, long long split_stride, int slices,
+                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+                     long long ldr, void* __restrict__ out, long long ldo, int out_fp32, long long M,
+                     int N) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nv = N >> 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * nv) return;
+  const long long m = i / nv;
+  const int n = static_cast<int>(i - m * nv) * 4;
+  const float* src = ws + m * ldw + n;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 4 <= slices; s += 4) {  // four loads in flight
+    float4 t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = __ldcs(reinterpret_cast<const float4*>(src + (s + j) * split_stride));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v.x += t[j].x; v.y += t[j].y; v.z += t[j].z; v.w += t[j].w; }
+  }
+  for (; s < slices; ++s) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(src + s * split_stride));
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  if (bias != nullptr) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  }
+  if (residual != nullptr) {
+    const uint2 r = *reinterpret_cast<const uint2*>(residual + m * ldr + n);
+    const float2 r0 = unpack_bf16x2(r.x), r1 = unpack_bf16x2(r.y);
+    v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
+  }
+  if (out_fp32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * ldo + n) = v;
+  } else {
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * ldo + n) = o;
+  }
+}
+}  // namespace cd360
+
+extern "C" int cd360_splitk_slices(int32_t k0, int32_t k1, int32_t k_splits) {
+  const int nkb = (k0 + 63) / 64 + (k1 + 63) / 64;
+  if (nkb <= 0) return CD360_ERR_SHAPE;
+  if (k_splits <= 1 || nkb <= 1) return 1;
+  const int want = k_splits < nkb ? k_splits : nkb;
+  const int per = (nkb + want - 1) / want;
+  return (nkb + per - 1) / per;
+}
+
+extern "C" int cd360_splitk_finish(const float* ws, int64_t ldw, int64_t split_stride, int32_t slices,
+                                   const float* bias, const void* residual, int64_t ldr, void* out,
+                                   int64_t ldo, int32_t out_fp32, int64_t M, int32_t N,
+                                   cd360_stream_t stream_) {
+  if (!ws || !out) return CD360_ERR_NULL;
+  if (M <= 0 || N <= 0 || (N & 3) || ldw < N || ldo < N || slices <= 0) return CD360_ERR_SHAPE;
+  if ((ldw & 3) || (ldo & 3) || (split_stride & 3) || (residual && (ldr & 3)) ||
+      (reinterpret_cast<uintptr_t>(ws) & 15) ||
+      (reinterpret_cast<uintptr_t>(out) & (out_fp32 ? 15 : 7)) ||
+      (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) ||
+      (residual && (reinterpret_cast<uintptr_t>(residual) & 7)))
+    return CD360_ERR_ALIGN;
+  const long long total = static_cast<long long>(M) * (N >> 2);
+  if (launch_ex(cd360::splitk_finish_kernel, dim3(blocks_for(total, 256)), dim3(256), 0,
+                reinterpret_cast<cudaStream_t>(stream_), 1, ws, static_cast<long long>(ldw),
+                static_cast<long long>(split_stride), slices, bias,
+                reinterpret_cast<const __nv_bfloat16*>(residual), static_cast<long long>(ldr), out,
+                static_cast<long long>(ldo), out_fp32, static_cast<long long>(M), N) != cudaSuccess)
+    return CD360_ERR_LAUNCH;
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
 extern "C" int cd360_nhwc_to_nchw_f32(const void* x, int32_t x_is_fp32, float* out, int32_t batch,
                                       int32_t hw, int32_t c, cd360_stream_t stream_) {
   if (!x || !out) return CD360_ERR_NULL;

@@ -94,6 +94,12 @@ struct GemmKParams {
   const float* ln_colsum;  // [N]
   float* stats_out;        // [M, N_out/64, 2] partial (sum, sumsq) of the bf16 output rows, or NULL
   int stats_slabs;
+  // split-K (small-M GEMMs whose few tiles cannot pull the weights at HBM rate): tile index =
+  // ks * (m_blocks * n_blocks) + mn; split ks covers k-blocks [ks*kb_per, min(nkb, (ks+1)*kb_per));
+  // split ks stores its fp32 partial tile into slice ks of `out` ([ksplit][M][ldo] fp32, plain
+  // stores: deterministic), summed in fixed order by cd360_splitk_finish
+  int ksplit, kb_per;
+  long long split_stride;  // elements between the partial slices
 };
 
 template <int BN, int STAGES, int CG>
@@ -149,7 +155,7 @@ __device__ __forceinline__ void add_bias32_smem(float (&v)[32], const float* sb)
 
 // direct (row-per-thread) store path: fp32 outputs, odd leading dimensions, N tails < 8
 __device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams& p, long long row,
-                                              int ocol0, int nvalid) {
+                                              int ocol0, int nvalid, int ks = 0) {
   if (p.residual != nullptr) {
     const __nv_bfloat16* r = p.residual + row * p.ldr + ocol0;
     if (nvalid == 32) {
@@ -169,7 +175,7 @@ __device__ __forceinline__ void store_chunk32(float (&v)[32], const GemmKParams&
     }
   }
   if (p.out_fp32) {
-    float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + ocol0;
+    float* o = reinterpret_cast<float*>(p.out) + ks * p.split_stride + row * p.ldo + ocol0;
     if (nvalid == 32 && (p.ldo & 3) == 0) {
       float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
@@ -230,7 +236,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   const bool leader = rank == 0;
   const int unit = blockIdx.x / (CG * MC);   // cluster (or lone CTA) index
   const int num_units = gridDim.x / (CG * MC);
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int mn_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = mn_tiles * p.ksplit;
   const int nkb = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
   constexpr uint32_t TMEM_COLS = 2 * BN;
 
@@ -280,8 +287,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int ks = tile / mn_tiles;
+      const int mn = tile - ks * mn_tiles;
+      const int m_blk = mn % p.num_m_blocks;
+      const int n_blk = mn / p.num_m_blocks;
+      const int kb_begin = ks * p.kb_per;
+      const int kb_end = min(nkb, kb_begin + p.kb_per);
       const int m0 = ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM;
       const int n0 = n_blk * BN + static_cast<int>(rank) * L::BNC;
       int cb = 0, cy = 0, cx = 0;
@@ -292,7 +303,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         cy = rem / p.W;
         cx = rem - cy * p.W;
       }
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + A_TILE_BYTES;
@@ -328,8 +339,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         } else {
           tma_load_2d(sb, &tmB, fb, kb * BK, n0);
         }
-        if (tile == unit && kb == 0) CD360_TRACE(3);
-        if (tile + num_units >= num_tiles && kb == nkb - 1) CD360_TRACE(4);
+        if (tile == unit && kb == kb_begin) CD360_TRACE(3);
+        if (tile + num_units >= num_tiles && kb == kb_end - 1) CD360_TRACE(4);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -348,24 +359,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
-      for (int kb = 0; kb < nkb; ++kb) {
+      const int kb_begin = (tile / mn_tiles) * p.kb_per;
+      const int kb_end = min(nkb, kb_begin + p.kb_per);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (t == 0 && kb == 0) CD360_TRACE(5);
-        if (t == 0 && kb == 1) CD360_TRACE(6);
+        if (t == 0 && kb == kb_begin) CD360_TRACE(5);
+        if (t == 0 && kb == kb_begin + 1) CD360_TRACE(6);
         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
           const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
-          if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          const uint32_t accumulate = (kb != kb_begin || k != 0) ? 1u : 0u;
+          if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+          else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
         }
         // free the smem slot (in both CTAs) once these MMAs retire
         if (CG == 2) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>((1u << (CG * MC)) - 1u));
         else umma_commit(&empty_bar[stage]);
-        if (kb == nkb - 1) {
+        if (kb == kb_end - 1) {
           if (CG == 2) umma_commit_2sm(&tmem_full[buf], static_cast<uint16_t>(0x3u << (pr * 2)));
           else umma_commit(&tmem_full[buf]);
           if (tile + num_units >= num_tiles) CD360_TRACE(7);
@@ -405,8 +419,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      const int ks = tile / mn_tiles;   // split-K: partial tile ks of output tile mn
+      const int mn = tile - ks * mn_tiles;
+      const int m_blk = mn % p.num_m_blocks;
+      const int n_blk = mn / p.num_m_blocks;
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       const int row0 = ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM;
@@ -643,7 +659,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
               }
-              store_chunk32(v, p, row, col0, nvalid);
+              store_chunk32(v, p, row, col0, nvalid, ks);
             }
           }
         } else {
@@ -786,7 +802,7 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     }
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.ksplit;
   int units = max_units;
   if (max_ctas > 0 && max_ctas / CL >= 1 && max_ctas / CL < units) units = max_ctas / CL;
   if (tiles < units) units = tiles;
@@ -864,6 +880,17 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   p.act = a->act;
   p.geglu = a->geglu;
   if (a->row_bias != nullptr && a->geglu) return CD360_ERR_UNSUPPORTED;
+  p.ksplit = 1;
+  if (a->k_splits > 1) {
+    // partial tiles go to fp32 slices of `out`; everything an epilogue would apply (bias, residual,
+    // activation) belongs to cd360_splitk_finish
+    if (!a->out_fp32 || a->bias || a->row_bias || a->residual || a->geglu || a->ln_stats ||
+        a->stats_out || a->act != CD360_ACT_NONE || a->conv)
+      return CD360_ERR_UNSUPPORTED;
+    if (a->split_stride < static_cast<int64_t>(a->M) * a->ldo || (a->split_stride & 3))
+      return CD360_ERR_SHAPE;
+    p.split_stride = a->split_stride;
+  }
   if ((reinterpret_cast<uintptr_t>(a->a0) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15) ||
       (reinterpret_cast<uintptr_t>(a->out) & 15) ||
       (a->residual && (reinterpret_cast<uintptr_t>(a->residual) & 15)) ||
@@ -959,6 +986,15 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
       if (rc != CD360_OK) return rc;
     } else {
       tmA1 = tmA0;
+    }
+  }
+  {
+    const int nkb_host = p.conv ? 9 * p.cblocks : (p.kb0 + p.kb1);
+    p.kb_per = nkb_host;
+    if (a->k_splits > 1 && nkb_host > 1) {
+      const int want = a->k_splits < nkb_host ? a->k_splits : nkb_host;
+      p.kb_per = (nkb_host + want - 1) / want;
+      p.ksplit = (nkb_host + p.kb_per - 1) / p.kb_per;  // no empty split
     }
   }
   {

@@ -42,15 +42,57 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise Cd360Error(f"{name}: expected a contiguous tensor")
 
 
+import math as _math
+import os as _os
+
+# Split-K for small-M GEMMs (training step: M = 256 tokens against 13-26 MB of weights; weight
+# gradients with K ~ 10^5): on by default, CD360_SPLITK=0 disables it for A/B runs.
+SPLITK = _os.environ.get("CD360_SPLITK", "1") != "0"
+_splitk_ws: dict = {}
+
+
+def _splitk_plan(M, N, K, out, residual, bias, plain_epilogue):
+    """Number of K splits for cd360_gemm_bf16 (1 = none): only when the tile grid covers at most half
+    of the GPU, every split keeps >= 4 k-blocks, and the epilogue is something
+    cd360_splitk_finish can apply (bias, residual, conversion)."""
+    if not SPLITK or not plain_epilogue or (N & 3):
+        return 1
+    if out is not None and ((out.stride(0) & 3) or (out.data_ptr() & 15)):
+        return 1
+    if residual is not None and ((residual.stride(0) & 3) or (residual.data_ptr() & 7)):
+        return 1
+    if bias is not None and (bias.data_ptr() & 15):
+        return 1
+    pair = N > 128 and M > 128                       # pick_config of gemm_tcgen05.cu
+    units = _math.ceil(M / 256) * _math.ceil(N / 256) if pair else _math.ceil(M / 128) * _math.ceil(N / 128)
+    max_units = 74 if pair else 148
+    nkb = _math.ceil(K / 64)
+    if units * 2 > max_units or nkb < 16:
+        return 1
+    s = min(nkb // 4, max_units // units, (16 << 20) // max(M * N, 1))
+    return s if s >= 2 else 1
+
+
+def _splitk_workspace(numel: int, device) -> torch.Tensor:
+    """fp32 scratch for the partial tiles (fully overwritten by every split-K launch)."""
+    ws = _splitk_ws.get(str(device))
+    if ws is None or ws.numel() < numel:
+        ws = torch.empty(max(numel, 16 << 20), device=device, dtype=f32)
+        _splitk_ws[str(device)] = ws
+    return ws
+
+
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out=None,
          out_fp32=False, act=ACT_NONE, geglu=False, a1=None, block_n=0, max_ctas=0,
          lda=None, lda1=None, k0=None, k1=None, M=None, ln_stats=None, ln_colsum=None, ln_eps=1e-5,
-         stats_out=None):
+         stats_out=None, k_splits=None):
     """out = epilogue(A @ W^T).  a: bf16 [M, K0] (row stride `lda` if given), optional second
     K-segment a1 [M, K1]; w: bf16 [N, K0+K1].
     ln_stats / ln_colsum: LayerNorm of the A rows folded into the epilogue (w, bias pre-folded with
     gamma / beta, see include/cd360.h); stats_out: fp32 [M, N_out/64, 2] receives the per-slab
-    (sum, sumsq) of the output rows for the next folded LayerNorm."""
+    (sum, sumsq) of the output rows for the next folded LayerNorm.
+    k_splits: None = heuristic (`_splitk_plan`), 1 = off, n > 1 = split the K loop n ways (partials
+    accumulated in an fp32 scratch, bias / residual / conversion by cd360_splitk_finish)."""
     lib = _lib.load()
     _req(w, bf16, "w")
     M = a.shape[0] if M is None else M
@@ -65,6 +107,28 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out
     n_out = N // 2 if geglu else N
     if out is None:
         out = torch.empty((M, n_out), device=a.device, dtype=f32 if out_fp32 else bf16)
+    plain = (row_bias is None and act == ACT_NONE and not geglu and ln_stats is None and stats_out is None
+             and block_n == 0 and max_ctas == 0)
+    if k_splits is None:
+        k_splits = _splitk_plan(M, N, k0 + k1, out, residual, bias, plain)
+    elif k_splits > 1 and not plain:
+        raise Cd360Error("split-K GEMM supports only bias / residual epilogues")
+    if k_splits > 1:
+        slices = lib.cd360_splitk_slices(k0, k1, int(k_splits))
+        stride = (M * N + 3) // 4 * 4
+        ws = _splitk_workspace(slices * stride, a.device)
+        args = GemmArgs(
+            a0=_ptr(a), lda0=lda, k0=k0, a1=_ptr(a1), lda1=lda1, k1=k1, w=_ptr(w), bias=0, row_bias=0,
+            rows_per_group=0, ld_row_bias=0, residual=0, ldr=0, out=_ptr(ws), ldo=N, out_fp32=1, M=M, N=N,
+            conv=0, B=0, H=0, W=0, C=0, act=ACT_NONE, geglu=0, block_n=0, max_ctas=0, ln_stats=0, ln_slabs=0,
+            ln_eps=0.0, ln_colsum=0, stats_out=0, k_splits=int(k_splits), split_stride=stride)
+        _run("gemm", 2.0 * M * N * (k0 + k1),
+             lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(split-K)"))
+        _run("splitk_finish", 0.0, lambda: check(lib.cd360_splitk_finish(
+            _ptr(ws), N, stride, slices, _ptr(bias), _ptr(residual),
+            residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0),
+            int(out.dtype == f32), M, N, _stream()), "cd360_splitk_finish"))
+        return out
     args = GemmArgs(
         a0=_ptr(a), lda0=lda, k0=k0, a1=_ptr(a1), lda1=lda1, k1=k1, w=_ptr(w),
         bias=_ptr(bias), row_bias=_ptr(row_bias), rows_per_group=rows_per_group,
@@ -73,7 +137,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out
         out=_ptr(out), ldo=out.stride(0), out_fp32=int(out.dtype == f32), M=M, N=N,
         conv=0, B=0, H=0, W=0, C=0, act=act, geglu=int(geglu), block_n=block_n, max_ctas=max_ctas,
         ln_stats=_ptr(ln_stats), ln_slabs=(ln_stats.shape[1] if ln_stats is not None else 0),
-        ln_eps=float(ln_eps), ln_colsum=_ptr(ln_colsum), stats_out=_ptr(stats_out))
+        ln_eps=float(ln_eps), ln_colsum=_ptr(ln_colsum), stats_out=_ptr(stats_out), k_splits=0, split_stride=0)
     _run("gemm", 2.0 * M * N * (k0 + k1),
          lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16"))
     return out

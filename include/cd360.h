@@ -101,9 +101,27 @@ typedef struct cd360_gemm_args {
   float ln_eps;
   const float* ln_colsum; /* [N] fp32: sum_k w[n, k] of the bf16 weight actually multiplied */
   float* stats_out;
+  /* Split-K (0 / 1 = off; linear mode): the K loop of every output tile is divided among k_splits
+   * CTAs (or CTA pairs); split s stores its fp32 partial tile into out + s * split_stride (plain
+   * stores, so the result is deterministic) — `out` is an fp32 scratch [k_splits][M][ldo] and no
+   * epilogue operand may be set; cd360_splitk_finish sums the slices in order and applies bias /
+   * residual / conversion.  The number of slices actually written is
+   * ceil(nkb / ceil(nkb / k_splits)) with nkb = ceil(k0/64) + ceil(k1/64) (cd360_splitk_slices).
+   * For the small-M GEMMs of the training step (M = 256 tokens against 13-26 MB of weights: 10 CTAs
+   * cannot pull the weights at HBM rate, 140 can) and weight gradients (K = 10^5 rows). */
+  int32_t k_splits;
+  int64_t split_stride; /* elements, >= M * ldo */
 } cd360_gemm_args;
 
 int cd360_gemm_bf16(const cd360_gemm_args* args, cd360_stream_t stream);
+/* Slices a split-K launch writes for a contraction of `k0 + k1` and a requested `k_splits`. */
+int cd360_splitk_slices(int32_t k0, int32_t k1, int32_t k_splits);
+/* Finish a split-K GEMM: out[m, n] = sum_s ws[s][m][n] (s ascending) + bias[n] + residual[m, n]
+ * (bias / residual optional; out bf16 or fp32; row strides in elements; ws slices `split_stride`
+ * elements apart with row stride ldw). */
+int cd360_splitk_finish(const float* ws, int64_t ldw, int64_t split_stride, int32_t slices,
+                        const float* bias, const void* residual, int64_t ldr, void* out, int64_t ldo,
+                        int32_t out_fp32, int64_t M, int32_t N, cd360_stream_t stream);
 /* Rows of the interleave block used by the GEGLU epilogue for a given N (= BN/2). */
 int cd360_geglu_pack_block(int32_t n_total);
 

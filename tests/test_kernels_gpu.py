@@ -415,3 +415,45 @@ def test_cfg_euler_step():
                              denoised_out=den_out)
     assert (out - ref).abs().max() < 1e-4
     assert (den_out - D).abs().max() < 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("M,N,K,K1,splits", [
+    (256, 1280, 5120, 0, None),     # training-step FF2 of the level-2 main stream: heuristic must split
+    (256, 1280, 1280, 1280, 4),     # two K segments (pose_emb_layers: [x | rendered])
+    (200, 640, 4096, 0, 7),         # ragged M, split count that does not divide the k-blocks
+    (1288, 1280, 24576, 0, None),   # weight-gradient shape: K = rows of the sample batch
+    (256, 5120, 1280, 0, None),     # dX of FF2: 40 CTAs -> 3 splits
+    (96, 72, 2048, 0, 8),           # single-CTA config, N tail
+])
+def test_gemm_split_k(M, N, K, K1, splits):
+    """Split-K GEMM (partials in fp32 slices + cd360_splitk_finish) == the unsplit kernel up to the
+    final rounding, == torch; deterministic run to run (no atomics)."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(1)
+    dev = _dev()
+    a, af = _rt(torch.randn(M, K, device=dev))
+    w, wf = _rt(torch.randn(N, K + K1, device=dev) / math.sqrt(K + K1))
+    a1 = a1f = None
+    if K1:
+        a1, a1f = _rt(torch.randn(M, K1, device=dev))
+    bias = torch.randn(N, device=dev)
+    res, resf = _rt(torch.randn(M, N, device=dev))
+    ref = (torch.cat([af, a1f], 1) if K1 else af) @ wf.t()
+    if splits is None:
+        assert ops._splitk_plan(M, N, K + K1, None, res, bias, True) > 1
+    out = ops.gemm(a, w, a1=a1, bias=bias, residual=res, k_splits=splits)
+    _assert_close(out, ref + bias + resf, what="split-K gemm+bias+residual")
+    base = ops.gemm(a, w, a1=a1, bias=bias, residual=res, k_splits=1)
+    assert float((out.float() - base.float()).abs().max()) <= 2.0 ** -7 * float(base.float().abs().max())
+    out2 = ops.gemm(a, w, a1=a1, bias=bias, residual=res, k_splits=splits)
+    assert torch.equal(out, out2), "split-K must be deterministic"
+    # fp32 output into a strided view (weight gradients are written into the flat gradient buffer)
+    big = torch.zeros(M, N + 8, device=dev)
+    ops.gemm(a, w, a1=a1, out=big[:, :N], k_splits=splits)
+    _assert_close(big[:, :N], ref, rel=1e-4, abs_=1e-4, what="split-K fp32 strided out")
+    assert float(big[:, N:].abs().max()) == 0.0
+    # in-place residual
+    x = res.clone()
+    ops.gemm(a, w, a1=a1, residual=x, out=x, k_splits=splits)
+    _assert_close(x, ref + resf, what="split-K in-place residual")

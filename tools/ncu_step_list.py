@@ -7,7 +7,14 @@ launch index inside the step, kernel, grid, block, duration (ns) and DRAM bytes.
     python tools/ncu_step_list.py gpurun_out/ncu_launches_raw.csv profiles/launches_r01_step.csv
 
 A step starts at `timestep_embedding_kernel`; the last COMPLETE window without FeatureNeRF kernels is
-kept (step 0 of an image runs FeatureNeRF once)."""
+kept (step 0 of an image runs FeatureNeRF once).
+
+Training step (`--train`): windows are delimited by `adamw_kernel` (one per optimiser step) and the last
+complete one is kept, FeatureNeRF kernels included:
+
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:... -c 12000 --csv \
+        --log-file gpurun_out/ncu_train_raw.csv python bench.py --workload train --steps 1 --warmup 1 --no-graph
+    python tools/ncu_step_list.py --train gpurun_out/ncu_train_raw.csv profiles/launches_r01_train_step.csv"""
 import csv
 import io
 import json
@@ -15,7 +22,7 @@ import re
 import sys
 
 
-def main(src, dst):
+def main(src, dst, train=False):
     text = open(src, errors="replace").read()
     start = text.index('"ID"')
     rows = list(csv.DictReader(io.StringIO(text[start:])))
@@ -33,9 +40,13 @@ def main(src, dst):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
             d[name.split(".")[0]] = val * scale
     order = [launches[i] for i in sorted(launches)]
-    starts = [i for i, d in enumerate(order) if d["kernel"].startswith("timestep_embedding")]
-    windows = [order[a:b] for a, b in zip(starts, starts[1:])]
-    windows = [w for w in windows if not any(d["kernel"].startswith("nerf_") for d in w)]
+    if train:
+        ends = [i for i, d in enumerate(order) if d["kernel"].startswith("adamw")]
+        windows = [order[a + 1:b + 1] for a, b in zip(ends, ends[1:])]
+    else:
+        starts = [i for i, d in enumerate(order) if d["kernel"].startswith("timestep_embedding")]
+        windows = [order[a:b] for a, b in zip(starts, starts[1:])]
+        windows = [w for w in windows if not any(d["kernel"].startswith("nerf_") for d in w)]
     step = windows[-1]
     with open(dst, "w", newline="") as f:
         w = csv.writer(f)
@@ -56,4 +67,5 @@ def main(src, dst):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    argv = [a for a in sys.argv[1:] if a != "--train"]
+    main(argv[0], argv[1], train="--train" in sys.argv)
