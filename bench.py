@@ -371,7 +371,7 @@ def run_train(args, world, rank, local_rank):
         return r
 
     ops.LaunchStats.hook = hook
-    _hide_launch_latency(0.25)
+    _hide_launch_latency(0.8)
     eager_step(999)
     ops.LaunchStats.hook = None
     torch.cuda.synchronize()

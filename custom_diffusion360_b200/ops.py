@@ -48,6 +48,8 @@ import os as _os
 # Split-K for small-M GEMMs (training step: M = 256 tokens against 13-26 MB of weights; weight
 # gradients with K ~ 10^5): on by default, CD360_SPLITK=0 disables it for A/B runs.
 SPLITK = _os.environ.get("CD360_SPLITK", "1") != "0"
+# below ~2.5 k of K the fixed cost of a launch dominates and the extra finish launch does not pay
+SPLITK_MIN_KB = int(_os.environ.get("CD360_SPLITK_MIN_KB", "40"))
 _splitk_ws: dict = {}
 
 
@@ -67,7 +69,7 @@ def _splitk_plan(M, N, K, out, residual, bias, plain_epilogue):
     units = _math.ceil(M / 256) * _math.ceil(N / 256) if pair else _math.ceil(M / 128) * _math.ceil(N / 128)
     max_units = 74 if pair else 148
     nkb = _math.ceil(K / 64)
-    if units * 2 > max_units or nkb < 16:
+    if units * 2 > max_units or nkb < SPLITK_MIN_KB:
         return 1
     s = min(nkb // 4, max_units // units, (16 << 20) // max(M * N, 1))
     return s if s >= 2 else 1
@@ -75,10 +77,11 @@ def _splitk_plan(M, N, K, out, residual, bias, plain_epilogue):
 
 def _splitk_workspace(numel: int, device) -> torch.Tensor:
     """fp32 scratch for the partial tiles (fully overwritten by every split-K launch)."""
-    ws = _splitk_ws.get(str(device))
+    key = (str(device), torch.cuda.current_stream().cuda_stream)   # one per stream: streams may run concurrently
+    ws = _splitk_ws.get(key)
     if ws is None or ws.numel() < numel:
         ws = torch.empty(max(numel, 16 << 20), device=device, dtype=f32)
-        _splitk_ws[str(device)] = ws
+        _splitk_ws[key] = ws
     return ws
 
 
@@ -212,7 +215,7 @@ _gn_ws: dict = {}
 
 def groupnorm_workspace(batch: int, hw: int, device) -> torch.Tensor:
     n = _lib.load().cd360_groupnorm_workspace_floats(batch, hw)
-    key = (str(device), int(n))
+    key = (str(device), int(n), torch.cuda.current_stream().cuda_stream)   # one per stream (concurrent streams)
     ws = _gn_ws.get(key)
     if ws is None:
         ws = torch.empty(int(n), device=device, dtype=f32)

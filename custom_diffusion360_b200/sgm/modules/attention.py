@@ -87,6 +87,8 @@ def invalidate_all_packed(root: nn.Module, only_trainable: bool = False, keep_bu
     """Make the packed operand copies follow the parameters again.  only_trainable: just those of the
     pose weights (after an optimiser step; the frozen packs stay) — by default refreshed in place
     (`keep_buffers`), see _Packed; otherwise every pack is dropped and rebuilt."""
+    if not only_trainable:
+        root.__dict__["_packs_warm"] = False   # UNetModel.forward_train: next call builds packs serialised
     for m in root.modules():
         if only_trainable:
             if hasattr(m, "pose_emb_layers"):
@@ -295,7 +297,9 @@ class BasicTransformerBlock(nn.Module):
         real references.  bf16 [batch*n*hw, c]; cached (static across the sampling loop)."""
         live = self.__dict__.get("_live_ctxref")
         if live is not None:  # UNetModel.forward(input_ref=...): tokens of the live reference stream
-            tok, n = live
+            tok, n = live[:2]
+            if len(live) > 2 and live[2] is not None:   # produced on the side stream (forward_train)
+                torch.cuda.current_stream(tok.device).wait_event(live[2])
             assert tok.shape[0] % (batch * n) == 0
             self._ctxref_cache = (("live", tok.data_ptr()), tok, n)
             return tok
@@ -382,6 +386,10 @@ class BasicTransformerBlock(nn.Module):
         cap = self.__dict__.get("_capture")
         if cap is not None and self.image_cross:
             cap.append(x.clone())
+            if self.__dict__.get("_capture_events") and x.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(x.device))
+                self.__dict__["_capture_ev"] = ev
 
     # ---- token fast path with the three LayerNorms folded into the GEMMs -------------------------
     def ln_packed(self):

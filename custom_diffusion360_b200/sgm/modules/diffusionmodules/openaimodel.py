@@ -31,6 +31,12 @@ from ..utils_cameraray import pack_pose
 bf16 = torch.bfloat16
 
 
+# training step: run the no-grad reference stream on a side CUDA stream, concurrently with the taped
+# main stream (CD360_REF_OVERLAP=0 serialises them again, for A/B measurements)
+import os as _os
+OVERLAP_REF_STREAM = _os.environ.get("CD360_REF_OVERLAP", "1") != "0"
+
+
 class GroupNorm32(nn.GroupNorm):
     """Parameter holder; the arithmetic is cd360_groupnorm_silu_bf16 (fp32 statistics)."""
 
@@ -419,19 +425,46 @@ class UNetModel(nn.Module, _Packed):
             "context / y must hold the b target rows followed by the b*n reference rows"
         sig = sigmas_ref if sigmas_ref is not None else torch.zeros_like(timesteps)
         t_ref = sig.reshape(b, 1).expand(b, n).reshape(b * n)
-        with torch.no_grad():
-            caps = self.capture_references(input_ref.reshape(b * n, *input_ref.shape[2:]), t_ref,
-                                           context[b:], y[b:])
         blocks = dict(self.pose_blocks())
-        for name, m in blocks.items():
-            t = caps[name]
-            m.__dict__["_live_ctxref"] = (t.reshape(-1, t.shape[-1]), n)
-            m._ctxref_cache = None
+        # The reference stream is enqueued on a SIDE CUDA stream and the taped main stream on the
+        # current one: both are chains of small launches (M = 256 ... 4096 rows) that leave most SMs
+        # idle, so they overlap almost completely.  Each pose block of the main stream waits for the
+        # event recorded when the reference stream emitted that block's tokens; the side stream is
+        # joined before returning (a CUDA-graph capture records this as a fork / join).
+        x_ref = input_ref.reshape(b * n, *input_ref.shape[2:])
+        cur = side = None
+        # (the first call after the packs were (re)built runs serialised: operand packs are created
+        # lazily on whichever stream needs them first)
+        if x.is_cuda and OVERLAP_REF_STREAM and self.__dict__.get("_packs_warm"):
+            cur = torch.cuda.current_stream(x.device)
+            side = self.__dict__.get("_side_stream")
+            if side is None or side.device != x.device:
+                side = torch.cuda.Stream(device=x.device)
+                self.__dict__["_side_stream"] = side
+            side.wait_stream(cur)
+        for m in blocks.values():
+            m.__dict__["_capture_events"] = side is not None
         try:
-            return train_path.unet_forward(self, x, timesteps, context[:b], y[:b], pose, in_scale, jitter)
+            with torch.no_grad():
+                if side is not None:
+                    with torch.cuda.stream(side):
+                        caps = self.capture_references(x_ref, t_ref, context[b:], y[b:])
+                else:
+                    caps = self.capture_references(x_ref, t_ref, context[b:], y[b:])
+            for name, m in blocks.items():
+                t = caps[name]   # stays referenced (tape / caps) until after the join below
+                m.__dict__["_live_ctxref"] = (t.reshape(-1, t.shape[-1]), n, m.__dict__.pop("_capture_ev", None))
+                m._ctxref_cache = None
+            out = train_path.unet_forward(self, x, timesteps, context[:b], y[:b], pose, in_scale, jitter)
+            self.__dict__["_packs_warm"] = True
+            return out
         finally:
+            if side is not None:
+                cur.wait_stream(side)
             for m in blocks.values():
                 m.__dict__.pop("_live_ctxref", None)
+                m.__dict__.pop("_capture_events", None)
+                m.__dict__.pop("_capture_ev", None)
                 m._ctxref_cache = None
 
     def backward(self, tape, deps, daux_of=None):
