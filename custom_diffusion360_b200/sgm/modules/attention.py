@@ -89,6 +89,7 @@ def invalidate_all_packed(root: nn.Module, only_trainable: bool = False, keep_bu
     (`keep_buffers`), see _Packed; otherwise every pack is dropped and rebuilt."""
     if not only_trainable:
         root.__dict__["_packs_warm"] = False   # UNetModel.forward_train: next call builds packs serialised
+        root.__dict__["_bwd_warm"] = False
     for m in root.modules():
         if only_trainable:
             if hasattr(m, "pose_emb_layers"):

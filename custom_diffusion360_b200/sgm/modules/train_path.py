@@ -20,6 +20,7 @@ forward here (`UNetModel.capture_references`).
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from types import SimpleNamespace as NS
 from typing import Dict, List, Optional
@@ -35,6 +36,8 @@ from .utils_cameraray import patch_ray_xy
 
 bf16 = torch.bfloat16
 f32 = torch.float32
+# side stream of the current backward walk (unet_backward) and the tensors it still reads
+_BWD: dict = {"side": None, "keep": []}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -269,15 +272,24 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
     # ---- pose_emb_layers: x3 = [x2 | rendered] Wp^T
     if sv.nerf is not None:
         c = sv.x2.shape[1]
-        dwp = _grad_buf(block.pose_emb_layers.weight)                       # [c, 2c]
-        gt = ops.transpose_to_bf16(g)
-        ops.gemm(gt, ops.transpose_to_bf16(sv.x2), out=dwp[:, :c])
-        ops.gemm(gt, ops.transpose_to_bf16(sv.rendered), out=dwp[:, c:])
-        pp = pose_bwd_pack(block)
-        nerf_backward(block, sv.nerf, ops.gemm(g, pp["wp_r_t"]), daux)
-        ready = block.__dict__.get("_grads_ready")     # data-parallel: start this block's all-reduce now
-        if ready is not None:
-            ready()
+        pp = pose_bwd_pack(block)          # (refreshed on the current stream, before the fork)
+        # Everything that only produces WEIGHT gradients of this block — the pose_emb_layers dW GEMMs
+        # and the whole FeatureNeRF backward (its inputs are the no-grad reference tokens, so nothing
+        # flows on from it) — is off the critical dX chain: it runs on the side stream, concurrently
+        # with the rest of the walk, and is joined at the end of unet_backward.
+        side = _BWD.get("side")
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(g.device))
+            _BWD["keep"].append((g, sv, daux))   # read on the side stream: alive until the join
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            dwp = _grad_buf(block.pose_emb_layers.weight)                       # [c, 2c]
+            gt = ops.transpose_to_bf16(g)
+            ops.gemm(gt, ops.transpose_to_bf16(sv.x2), out=dwp[:, :c])
+            ops.gemm(gt, ops.transpose_to_bf16(sv.rendered), out=dwp[:, c:])
+            nerf_backward(block, sv.nerf, ops.gemm(g, pp["wp_r_t"]), daux)
+            ready = block.__dict__.get("_grads_ready")     # data-parallel: start this block's all-reduce now
+            if ready is not None:
+                ready()
         if stop_here:
             return None
         g = ops.gemm(g, pp["wp_x_t"])
@@ -454,6 +466,24 @@ def unet_backward(unet, fw, deps, daux_of: Dict[int, tuple]):
     """deps: bf16 [B*L*L, 64] gradient of the loss w.r.t. the UNet output tokens (columns >= 4
     zero); daux_of: {id(pose block): (dfg, dalphas, drgb)}.  Writes the gradients of every pose
     parameter into its `.grad` (fp32)."""
+    from .diffusionmodules.openaimodel import OVERLAP_REF_STREAM
+    side = None
+    if deps.is_cuda and OVERLAP_REF_STREAM and unet.__dict__.get("_packs_warm") and unet.__dict__.get("_bwd_warm"):
+        side = unet.__dict__.get("_side_stream")
+        if side is None or side.device != deps.device:
+            side = torch.cuda.Stream(device=deps.device)
+            unet.__dict__["_side_stream"] = side
+    _BWD["side"], _BWD["keep"] = side, []
+    try:
+        _unet_backward(unet, fw, deps, daux_of)
+        unet.__dict__["_bwd_warm"] = True     # the lazily built backward packs exist from now on
+    finally:
+        if side is not None:
+            torch.cuda.current_stream(deps.device).wait_stream(side)
+        _BWD["side"], _BWD["keep"] = None, []
+
+
+def _unet_backward(unet, fw, deps, daux_of):
     p = unet.packed()
     bp = bwd_pack(unet)
     b = fw.batch
