@@ -841,14 +841,19 @@ __device__ __forceinline__ void aa_window(int o, float scale, int in_size, int& 
   lo = max(static_cast<int>(center - support + 0.5f), 0);
   size = min(static_cast<int>(center + support + 0.5f), in_size) - lo;
 }
+// One WARP per output pixel: the window of a strong down-scale is large (512 -> 16: 64 x 64 taps) and
+// there are few outputs (3 planes x 256), so a thread per output left 3 CTAs working for 0.5 ms.
+// Lanes stride over the flattened window (x fastest: coalesced rows), fixed-order tree reduction.
 __global__ void __launch_bounds__(256)
 resize_bilinear_aa_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, int ih,
                           int iw, int oh, int ow, float out_scale, float out_shift) {
   pdl_wait();
   const long long total = static_cast<long long>(planes) * oh * ow;
   const float sy = static_cast<float>(ih) / oh, sx = static_cast<float>(iw) / ow;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long i = warp0; i < total; i += nwarps) {
     const int ox = static_cast<int>(i % ow);
     const int oy = static_cast<int>((i / ow) % oh);
     const long long pl = i / (static_cast<long long>(ow) * oh);
@@ -859,16 +864,18 @@ resize_bilinear_aa_kernel(const float* __restrict__ in, float* __restrict__ out,
     float wys = 0.f, wxs = 0.f;
     for (int j = 0; j < ysz; ++j) wys += fmaxf(0.f, 1.f - fabsf((j + ylo - yc + 0.5f) * yinv));
     for (int j = 0; j < xsz; ++j) wxs += fmaxf(0.f, 1.f - fabsf((j + xlo - xc + 0.5f) * xinv));
+    const float* base = in + (pl * ih + ylo) * iw + xlo;
+    const int taps = ysz * xsz;
     float acc = 0.f;
-    for (int jy = 0; jy < ysz; ++jy) {
-      const float wy = fmaxf(0.f, 1.f - fabsf((jy + ylo - yc + 0.5f) * yinv)) / wys;
-      const float* rowp = in + (pl * ih + ylo + jy) * iw + xlo;
-      float racc = 0.f;
-      for (int jx = 0; jx < xsz; ++jx)
-        racc = fmaf(fmaxf(0.f, 1.f - fabsf((jx + xlo - xc + 0.5f) * xinv)) / wxs, rowp[jx], racc);
-      acc = fmaf(wy, racc, acc);
+    for (int t = lane; t < taps; t += 32) {
+      const int jy = t / xsz, jx = t - jy * xsz;
+      const float wy = fmaxf(0.f, 1.f - fabsf((jy + ylo - yc + 0.5f) * yinv));
+      const float wx = fmaxf(0.f, 1.f - fabsf((jx + xlo - xc + 0.5f) * xinv));
+      acc = fmaf(wy * wx, __ldg(base + static_cast<long long>(jy) * iw + jx), acc);
     }
-    out[i] = fmaf(out_scale, acc, out_shift);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[i] = fmaf(out_scale, acc / (wys * wxs), out_shift);
   }
 }
 
@@ -1118,7 +1125,7 @@ extern "C" int cd360_resize_bilinear_aa(const float* in, float* out, int32_t pla
   if (!in || !out) return CD360_ERR_NULL;
   if (planes <= 0 || ih <= 0 || iw <= 0 || oh <= 0 || ow <= 0) return CD360_ERR_SHAPE;
   const long long items = static_cast<long long>(planes) * oh * ow;
-  launch_ex(resize_bilinear_aa_kernel, dim3(grid_for(items, 256)), dim3(256), 0,
+  launch_ex(resize_bilinear_aa_kernel, dim3(grid_for(items * 32, 256)), dim3(256), 0,
             reinterpret_cast<cudaStream_t>(stream_), 1, in, out, planes, ih, iw, oh, ow, out_scale, out_shift);
   CD360_CHECK_LAUNCH();
   return CD360_OK;

@@ -38,6 +38,9 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 # side stream of the current backward walk (unet_backward) and the tensors it still reads
 _BWD: dict = {"side": None, "keep": []}
+# FeatureNeRF results of the current taped forward that were enqueued ahead on their own stream:
+# id(block) -> (rendered, aux, saved, event)
+_FWD: dict = {}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,10 +247,15 @@ def block_forward(block: BasicTransformerBlock, x, batch, n, kv, nctx, cams=None
     aux = None
     x3 = x2
     if block.image_cross and cams is not None:
-        xref_tok = block.context_ref_tokens(batch)
-        n_views = block._ctxref_cache[2]
-        rendered, aux, sv.nerf = nerf_forward(block, cams, xref_tok, n_views, kv, nctx, batch, n,
-                                              next(jitter) if jitter is not None else None)
+        pre = _FWD.get(id(block))
+        if pre is not None:      # FeatureNeRF already enqueued on its own stream (unet_forward)
+            rendered, aux, sv.nerf, ev = pre
+            torch.cuda.current_stream(x.device).wait_event(ev)
+        else:
+            xref_tok = block.context_ref_tokens(batch)
+            n_views = block._ctxref_cache[2]
+            rendered, aux, sv.nerf = nerf_forward(block, cams, xref_tok, n_views, kv, nctx, batch, n,
+                                                  next(jitter) if jitter is not None else None)
         sv.rendered = rendered
         x3 = block.pose_emb_layers.tokens(x2, a1=rendered)
     sv.x3 = x3
@@ -437,28 +445,63 @@ def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=Non
                 raise TypeError(type(layer))
         return h, hh, ww
 
-    col = ops.im2col3x3_nchw(x.float().contiguous(), 64, scale=in_scale, batch=b)
-    h = ops.gemm(col, p["cin_w"], bias=p["cin_b"])
-    hs = [h]
-    tape.append(("push", 0))
-    for block in list(unet.input_blocks)[1:]:
-        h, hh, ww = run(block, h, hh, ww)
-        tape.append(("push", len(hs)))
-        hs.append(h)
-    h, hh, ww = run(unet.middle_block, h, hh, ww)
-    for block in unet.output_blocks:
-        tape.append(("pop", len(hs) - 1))
-        h, hh, ww = run(block, h, hh, ww, skip=hs.pop())
-    hn = ops.groupnorm(h, p["og"], p["ob"], b, hh * ww, eps=unet.out[0].eps, silu=True)
-    eps = ops.conv3x3(hn, p["cout_w"], b, hh, ww, bias=p["cout_b"], out_fp32=True)
+    # FeatureNeRF of every pose block depends on the reference tokens, the cameras and the weights —
+    # not on the main stream's activations: enqueue all of them on their own stream (each waits for
+    # the event of its block's reference tokens) so they run beside the main stream, which only waits
+    # for a block's event when it reaches that block's pose_emb_layers.
+    from .diffusionmodules.openaimodel import OVERLAP_REF_STREAM
+    nerf_stream = None
+    _FWD.clear()
+    if cams is not None and x.is_cuda and OVERLAP_REF_STREAM and unet.__dict__.get("_packs_warm"):
+        nerf_stream = unet.__dict__.get("_nerf_stream")
+        if nerf_stream is None or nerf_stream.device != dev:
+            nerf_stream = torch.cuda.Stream(device=dev)
+            unet.__dict__["_nerf_stream"] = nerf_stream
+        nerf_stream.wait_stream(torch.cuda.current_stream(dev))      # kv_all, cams
+        with torch.cuda.stream(nerf_stream):
+            for block in pose_blocks_in_order(unet):
+                c = block.pose_emb_layers.weight.shape[0]
+                res = x.shape[-1] // (c // unet.model_channels)
+                off, width = block.__dict__["_kv_slice"]
+                xref_tok = block.context_ref_tokens(b)                # waits for the reference stream's event
+                n_views = block._ctxref_cache[2]
+                rendered, a, saved = nerf_forward(block, cams, xref_tok, n_views, kv_all[:, off:off + width], nctx,
+                                                  b, res * res, next(jitter) if jitter is not None else None)
+                ev = torch.cuda.Event()
+                ev.record(nerf_stream)
+                _FWD[id(block)] = (rendered, a, saved, ev)
+    try:
+        col = ops.im2col3x3_nchw(x.float().contiguous(), 64, scale=in_scale, batch=b)
+        h = ops.gemm(col, p["cin_w"], bias=p["cin_b"])
+        hs = [h]
+        tape.append(("push", 0))
+        for block in list(unet.input_blocks)[1:]:
+            h, hh, ww = run(block, h, hh, ww)
+            tape.append(("push", len(hs)))
+            hs.append(h)
+        h, hh, ww = run(unet.middle_block, h, hh, ww)
+        for block in unet.output_blocks:
+            tape.append(("pop", len(hs) - 1))
+            h, hh, ww = run(block, h, hh, ww, skip=hs.pop())
+        hn = ops.groupnorm(h, p["og"], p["ob"], b, hh * ww, eps=unet.out[0].eps, silu=True)
+        eps = ops.conv3x3(hn, p["cout_w"], b, hh, ww, bias=p["cout_b"], out_fp32=True)
+    finally:
+        if nerf_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(nerf_stream)
+        _FWD.clear()
     return eps, aux, NS(tape=tape, h_last=h, batch=b, hh=hh, ww=ww)
+
+
+def pose_blocks_in_order(unet) -> List[BasicTransformerBlock]:
+    """Pose blocks in the order the forward pass executes them."""
+    return [m for blk in list(unet.input_blocks) + [unet.middle_block] + list(unet.output_blocks)
+            for layer in blk if isinstance(layer, SpatialTransformer) and layer.image_cross
+            for i, m in enumerate(layer.transformer_blocks) if m.image_cross and i % layer.poscontrol_interval == 0]
 
 
 def first_pose_block(unet) -> Optional[BasicTransformerBlock]:
     """The pose block that runs first in the forward pass: the backward walk ends there."""
-    order = [m for blk in list(unet.input_blocks) + [unet.middle_block] + list(unet.output_blocks)
-             for layer in blk if isinstance(layer, SpatialTransformer)
-             for m in layer.transformer_blocks if m.image_cross]
+    order = pose_blocks_in_order(unet)
     return order[0] if order else None
 
 
