@@ -423,7 +423,7 @@ def test_cfg_euler_step():
     (256, 1280, 1280, 1280, 4),     # two K segments (pose_emb_layers: [x | rendered])
     (200, 640, 4096, 0, 7),         # ragged M, split count that does not divide the k-blocks
     (1288, 1280, 24576, 0, None),   # weight-gradient shape: K = rows of the sample batch
-    (256, 5120, 1280, 0, None),     # dX of FF2: 40 CTAs -> 3 splits
+    (256, 5120, 1280, 0, 3),        # dX of FF2: 40 CTAs, K below the heuristic threshold
     (96, 72, 2048, 0, 8),           # single-CTA config, N tail
 ])
 def test_gemm_split_k(M, N, K, K1, splits):
