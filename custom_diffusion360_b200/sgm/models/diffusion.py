@@ -281,6 +281,8 @@ class GraphedTrainStep:
                                "leaves the fg / bg terms out of the total (diffusion.py:225)")
         self._draw()
         self.opt.zero_grad()
+        # no collectives inside the captured step: the bucket all-reduces run after each replay (opt.step)
+        self.opt.suspend_overlap = True
         engine.shared_step(self._batch(), sync=False)              # warm-up: builds every frozen pack
         invalidate_all_packed(unet, only_trainable=True)           # ... the trainable ones are refreshed IN PLACE inside the graph
         torch.cuda.synchronize()

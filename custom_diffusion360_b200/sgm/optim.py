@@ -78,6 +78,9 @@ class PoseAdamW:
         self.buckets = self.flat.buckets_by_prefix()
         self._pending: list = []
         self._comm_stream = None
+        # True while the step runs as a CUDA-graph replay (GraphedTrainStep): the per-block callbacks of
+        # the backward walk do nothing and `step()` all-reduces every bucket after the replay
+        self.suspend_overlap = False
         self.on_step = None
         self.param_groups = [{"lr": lr, "params": self.flat.params}]
 
@@ -85,11 +88,11 @@ class PoseAdamW:
     def _world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def reduce_bucket(self, i: int):
+    def reduce_bucket(self, i: int, force: bool = False):
         """Start the (sum) all-reduce of bucket i of the flat gradient buffer.  On CUDA the
         collective runs on a side stream ordered after the kernels already queued on the current
         stream, so it overlaps whatever the backward launches next."""
-        if self._world() == 1:
+        if self._world() == 1 or (self.suspend_overlap and not force):
             return
         lo, hi = self.buckets[i]
         g = self.flat.grad[lo:hi]
@@ -119,7 +122,7 @@ class PoseAdamW:
 
     def reduce_all(self):
         for i in range(len(self.buckets)):
-            self.reduce_bucket(i)
+            self.reduce_bucket(i, force=True)
 
     def wait_reduce(self):
         for w in self._pending:

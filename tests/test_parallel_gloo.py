@@ -84,6 +84,17 @@ def _train_worker(rank, world, port, q):
         opt.wait_reduce()
         tot = sum(r + 1 for r in range(world))
         ok = all(bool((p.grad == float(tot * (k + 1))).all()) for k, (_, p) in enumerate(named))
+        # graph mode (GraphedTrainStep): the callbacks are suspended, step() reduces everything afterwards
+        opt.suspend_overlap = True
+        for k, (_, p) in enumerate(named):
+            p.grad.fill_(float((rank + 1) * (k + 1)))
+        for blk in reversed(blocks):
+            blk.__dict__["_grads_ready"]()
+        assert not opt._pending
+        ok = ok and all(bool((p.grad == float((rank + 1) * (k + 1))).all()) for k, (_, p) in enumerate(named))
+        opt.reduce_all()
+        opt.wait_reduce()
+        ok = ok and all(bool((p.grad == float(tot * (k + 1))).all()) for k, (_, p) in enumerate(named))
         # views survive: parameters and grads still alias the flat buffers
         alias = all(p.data_ptr() == opt.flat.data.data_ptr() + 4 * o for p, o in zip(opt.flat.params, opt.flat.offsets))
         q.put((rank, ok, alias, len(opt.buckets), opt.flat.numel))
