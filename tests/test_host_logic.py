@@ -261,3 +261,19 @@ def test_vae_decoder_host_logic_with_fake_kernels():
     assert len(pw) == 1 and abs(pw[0]["scale"] - 1 / 0.13025) < 1e-9
     sm = [kw for k, kw in fake.calls if k == "softmax_rows"][0]
     assert sm["rows"] == sm["n"] == 256 and abs(sm["scale"] - (cfg["ch"] * cfg["ch_mult"][-1]) ** -0.5) < 1e-9
+
+
+def test_splitk_plan_heuristic():
+    """Split-K dispatch (ops._splitk_plan): never for the sampling step's shapes (M >= 3072 rows: the
+    tile grid already covers the GPU), on for the training step's small-M / large-K GEMMs and weight
+    gradients, off below K = 2560 and for epilogues the finish kernel cannot apply."""
+    from custom_diffusion360_b200 import ops
+    plan = lambda M, N, K, plain=True: ops._splitk_plan(M, N, K, None, None, None, plain)
+    for M, N, K in ((3072, 1280, 1280), (3072, 1280, 5120), (3072, 10240, 1280), (12288, 640, 2560), (49152, 320, 2880)):
+        assert plan(M, N, K) == 1, (M, N, K)
+    assert plan(256, 1280, 5120) == 14          # FF2 of the level-2 main stream: 5 pairs -> 70 pairs
+    assert plan(256, 1280, 10240) == 14         # dX of FF1
+    assert plan(1288, 1280, 24576) == 2         # weight gradient [c + 8, c] over 24 576 sample rows
+    assert plan(256, 1280, 1280) == 1           # fixed launch cost dominates below K = 2560
+    assert plan(256, 1280, 5120, plain=False) == 1
+    assert plan(256, 1282, 5120) == 1           # finish kernel works on 4-column vectors

@@ -185,3 +185,33 @@ def test_graphed_training_step_equals_eager():
         assert err <= 1e-4 * float(g_eager.abs().max()), (it, err, float(g_eager.abs().max()))
         opt.step()                       # second iteration: both paths must see the updated pose weights
     _record("graphed_vs_eager", max_abs_grad_diff=err, loss=float(loss_e))
+
+
+@gpu
+def test_multi_stream_step_equals_serial(monkeypatch):
+    """The training step with the reference stream / FeatureNeRF forward / pose-weight gradient branch
+    on side CUDA streams (default) against the same step fully serialised on one stream: identical
+    loss, gradients equal up to the order of the fp32 atomics of the scatter / column-sum kernels."""
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules import openaimodel as U
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    sd = O.synthetic_state_dict(cfg, seed=3)
+    batch = _to_engine_batch(T.synthetic_train_batch(cfg, 16, n_views=3, b=2, seed=9, image=32, jitter=True), dev)
+    engine = _engine(cfg, sd, dev)
+    engine.global_step = 1
+    opt = engine.configure_optimizers()
+    unet = engine.model.diffusion_model
+    out = {}
+    for mode in ("warm-up", "overlap", "serial"):
+        monkeypatch.setattr(U, "OVERLAP_REF_STREAM", mode != "serial")
+        opt.zero_grad()
+        loss = float(engine.training_step(dict(batch)))
+        torch.cuda.synchronize()
+        out[mode] = (loss, opt.flat.grad.clone())
+    assert unet.__dict__.get("_packs_warm") and unet.__dict__.get("_bwd_warm")
+    assert unet.__dict__.get("_side_stream") is not None and unet.__dict__.get("_nerf_stream") is not None
+    (l1, g1), (l0, g0) = out["overlap"], out["serial"]
+    assert l1 == l0 == out["warm-up"][0], (l1, l0, out["warm-up"][0])
+    err = float((g1 - g0).abs().max())
+    assert err <= 1e-4 * float(g0.abs().max()), (err, float(g0.abs().max()))
+    _record("multi_stream_vs_serial", loss=l1, max_abs_grad_diff=err)
