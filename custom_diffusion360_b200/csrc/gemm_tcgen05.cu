@@ -835,6 +835,19 @@ static int pick_config(int M, int N, int geglu, int requested) {
   if (requested == 256 || requested == 512) return 512;
   if (requested == 1024) return 1024;
   if (N <= 128 || M <= 128 || !pair_ok) return (geglu && (N % 256) == 0) ? 512 : 128;
+  {
+    // small problems (training step at batch 1: M = 256 ... 1024 rows): when 128x128 tiles fill at most
+    // half a wave of single CTAs, twice as many CTAs pull the operands and the epilogue tail of each is half
+    // as long as a CTA pair's 128x256 share (CD360_GEMM_SMALL=0 keeps the pair tiles, for A/B runs)
+    static int small_ok = -1;
+    if (small_ok < 0) {
+      const char* e = getenv("CD360_GEMM_SMALL");
+      small_ok = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const long long single_tiles =
+        static_cast<long long>((M + BM - 1) / BM) * static_cast<long long>((N + 127) / 128);
+    if (small_ok && !geglu && single_tiles <= num_sms() / 2) return 128;  // (leaves room for split-K)
+  }
   const int pair_blocks = (M + 2 * BM - 1) / (2 * BM);
   return (mc_ok && pair_blocks >= 2 && (pair_blocks & 1) == 0) ? 1024 : 512;
 }

@@ -49,6 +49,7 @@ import os as _os
 # gradients with K ~ 10^5): on by default, CD360_SPLITK=0 disables it for A/B runs.
 SPLITK = _os.environ.get("CD360_SPLITK", "1") != "0"
 # below ~2.5 k of K the fixed cost of a launch dominates and the extra finish launch does not pay
+GEMM_SMALL = _os.environ.get("CD360_GEMM_SMALL", "1") != "0"   # mirrors pick_config's small-problem rule
 SPLITK_MIN_KB = int(_os.environ.get("CD360_SPLITK_MIN_KB", "40"))
 _splitk_ws: dict = {}
 
@@ -65,8 +66,9 @@ def _splitk_plan(M, N, K, out, residual, bias, plain_epilogue):
         return 1
     if bias is not None and (bias.data_ptr() & 15):
         return 1
-    pair = N > 128 and M > 128                       # pick_config of gemm_tcgen05.cu
-    units = _math.ceil(M / 256) * _math.ceil(N / 256) if pair else _math.ceil(M / 128) * _math.ceil(N / 128)
+    singles = _math.ceil(M / 128) * _math.ceil(N / 128)
+    pair = N > 128 and M > 128 and not (GEMM_SMALL and singles <= 74)     # pick_config of gemm_tcgen05.cu
+    units = _math.ceil(M / 256) * _math.ceil(N / 256) if pair else singles
     max_units = 74 if pair else 148
     nkb = _math.ceil(K / 64)
     if units * 2 > max_units or nkb < SPLITK_MIN_KB:

@@ -271,8 +271,8 @@ def test_splitk_plan_heuristic():
     plan = lambda M, N, K, plain=True: ops._splitk_plan(M, N, K, None, None, None, plain)
     for M, N, K in ((3072, 1280, 1280), (3072, 1280, 5120), (3072, 10240, 1280), (12288, 640, 2560), (49152, 320, 2880)):
         assert plan(M, N, K) == 1, (M, N, K)
-    assert plan(256, 1280, 5120) == 14          # FF2 of the level-2 main stream: 5 pairs -> 70 pairs
-    assert plan(256, 1280, 10240) == 14         # dX of FF1
+    assert plan(256, 1280, 5120) == 7           # FF2 of the level-2 main stream: 20 single CTAs -> 140
+    assert plan(256, 1280, 10240) == 7          # dX of FF1
     assert plan(1288, 1280, 24576) == 2         # weight gradient [c + 8, c] over 24 576 sample rows
     assert plan(256, 1280, 1280) == 1           # fixed launch cost dominates below K = 2560
     assert plan(256, 1280, 5120, plain=False) == 1
