@@ -39,3 +39,29 @@ def gather_images(x_local: torch.Tensor, n_images: int, group: Optional[dist.Pro
             out[idx] = bufs[r][: len(idx)]
     assert len(image_shard(n_images, rank, world)) == x_local.shape[0]
     return out
+
+
+def gather_references(unet, captured: dict, null_row: Optional[dict] = None,
+                      group: Optional[dist.ProcessGroup] = None) -> dict:
+    """Validation-epoch reference capture across ranks (reference main.py:594-602): every rank ran
+    `UNetModel.capture_references` on ITS share of the validation views (`captured`: {pose block
+    name: [r, hw, c]}, the same r on every rank); per pose block the shards are all-gathered,
+    interleaved rank-minor like the reference's `rearrange(stack(output_list).transpose(0, 1),
+    "b n ... -> (b n) ...")` (view j of rank k lands at row j * world + k), optionally followed by an
+    explicit 'null' row — sampling uses `references[-1]` as the null reference of the unconditional CFG
+    row (sample.py:92,96), i.e. whatever was captured last — and registered as that block's
+    `references` buffer.
+    Returns {name: references tensor}."""
+    out = {}
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    for name, _ in unet.pose_blocks():
+        t = captured[name].contiguous()
+        if world > 1:
+            bufs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(bufs, t, group=group)
+            t = torch.stack(bufs).transpose(0, 1).reshape(-1, *t.shape[1:])
+        if null_row is not None:
+            t = torch.cat([t, null_row[name].to(t).reshape(1, *t.shape[1:])], 0)
+        out[name] = t
+    unet.register_references(out)
+    return out

@@ -116,3 +116,45 @@ def test_gradient_allreduce_buckets_two_ranks():
         assert p.exitcode == 0
     for rank, ok, alias, nb, numel in results:
         assert ok and alias and nb == 9 and numel > 0
+
+
+def _refs_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import sgm_oracle as O
+        from custom_diffusion360_b200.parallel import gather_references
+        from custom_diffusion360_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+        unet = UNetModel(**dict(O.TINY_CFG))
+        caps, null = {}, {}
+        for name, m in unet.pose_blocks():
+            c = m.pose_emb_layers.weight.shape[0]
+            # view j of rank k is filled with 10 * j + k
+            caps[name] = torch.stack([torch.full((4, c), 10.0 * j + rank) for j in range(3)])
+            null[name] = torch.full((4, c), -1.0)
+        refs = gather_references(unet, caps, null_row=null)
+        ok = True
+        for name, m in unet.pose_blocks():
+            r = m.references
+            expect = [10.0 * j + k for j in range(3) for k in range(world)] + [-1.0]   # main.py:601 ordering
+            ok = ok and r.shape[0] == 3 * world + 1 and r[:, 0, 0].tolist() == expect and r is refs[name]
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_validation_reference_gather_two_ranks():
+    """per-pose-block all_gather of the captured reference tokens, interleaved like
+    main.py:600-601, registered as `references`."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_refs_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results)
