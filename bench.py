@@ -526,6 +526,28 @@ def main():
         step0_warm_ms = ea.elapsed_time(eb)
         step(x, *sched(1))          # back to the steady state for the per-kernel pass
         torch.cuda.synchronize()
+        # the same step-0 once more with CUDA events around every launch: where FeatureNeRF's time goes
+        rec0 = {}
+
+        def hook0(name, flops, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            rec0.setdefault(name, []).append((flops, a, b))
+            return r
+
+        net.clear_rendered_feat()
+        ops.LaunchStats.hook = hook0
+        _hide_launch_latency(0.12)
+        step(x, float(sigmas[0]), float(sigmas[1]))
+        ops.LaunchStats.hook = None
+        torch.cuda.synchronize()
+        step0_kernels = {name: {"launches": len(items), "ms": sum(a.elapsed_time(b) for _, a, b in items),
+                                "launched_tflop": sum(f for f, _, _ in items) / 1e12}
+                         for name, items in rec0.items()}
+        step(x, *sched(1))
+        torch.cuda.synchronize()
         # ---- per-kernel pass for the roofline: CUDA events around every tensor-core launch of one
         #      eager steady-state step (same stream, after the timed region) ----
         rec = {}
@@ -579,6 +601,7 @@ def main():
                           "frac": step_tflops / peaks["sustained"],
                           "peak_source": peaks["source"] + " sustained (kernel inside a long step)"},
         "kernels": kern, "first_call_ms": step0_ms, "step0_featurenerf_ms": step0_warm_ms,
+        "step0_kernels": step0_kernels,
         "step0_note": "first_call_ms = first step of the process (builds every bf16 weight pack, loads modules); "
                       "step0_featurenerf_ms = first step of the NEXT image: FeatureNeRF of all 12 pose blocks + one eager guided step",
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": lat_bytes + 4 * (2 * 3 * args.n_img + 4),
