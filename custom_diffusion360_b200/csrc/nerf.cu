@@ -82,8 +82,12 @@ __device__ __forceinline__ void pos_enc(const float (&v)[DIM], F&& emit) {
   }
 }
 
-// One thread per (b, ray, sample); loops over the n reference views.
-__global__ void __launch_bounds__(128)
+// One thread per (b, ray, sample); loops over the n reference views.  The 198 positional features of a
+// point are staged in shared memory ([128 points][kpe] bf16, the block's rows are contiguous in `pe`)
+// and written with coalesced 16-byte stores: a thread storing its own 400-byte row two bytes at a
+// time touched 32 sectors per store instruction and left the kernel at a few hundred GB/s.
+constexpr int NP_THREADS = 128;
+__global__ void __launch_bounds__(NP_THREADS)
 nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
                    const float* __restrict__ depths, const float* __restrict__ w_nv_geo,
                    const float* __restrict__ b_nv, __nv_bfloat16* __restrict__ pe, int* __restrict__ gidx,
@@ -92,8 +96,9 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
   CD360_TL(16);  // tools/step_timeline.py; empty in the product build
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float s_w[];  // w_nv_geo[198] | per-view origin logit [n]
+  extern __shared__ __align__(16) float s_w[];  // w_nv_geo[198] | per-view origin logit [16] | pe tile
   float* s_ol = s_w + 200;
+  __nv_bfloat16* s_pe = reinterpret_cast<__nv_bfloat16*>(s_w + 200 + 16);  // [NP_THREADS][kpe]
   const int hw = res * res;
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 198; i += blockDim.x) s_w[i] = w_nv_geo[i];
@@ -114,8 +119,10 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
   }
   __syncthreads();
 
-  const int pid = blockIdx.x * blockDim.x + threadIdx.x;  // ray * d + sample
-  if (pid >= hw * d) return;
+  const int pid0 = blockIdx.x * blockDim.x;                // first point of this block
+  const bool valid = pid0 + static_cast<int>(threadIdx.x) < hw * d;
+  const int pid = valid ? pid0 + threadIdx.x : hw * d - 1;  // ray * d + sample (tail threads idle along)
+  const int rows_here = min(static_cast<int>(blockDim.x), hw * d - pid0);
   const int ray = pid / d;
   const float depth = depths[pid];
   const float x = xy[ray * 2], y = xy[ray * 2 + 1];
@@ -163,12 +170,14 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
         gip[a * 2 + c] = in ? ys[a] * res + xs[c] : -1;
         gwp[a * 2 + c] = in ? wy[a] * wx[c] : 0.f;
       }
-    *reinterpret_cast<int4*>(gidx + point * 4) = gi;
-    *reinterpret_cast<float4*>(gwgt + point * 4) = gw;
-    vlogit[point] = logit_pt + s_ol[v];
+    if (valid) {
+      *reinterpret_cast<int4*>(gidx + point * 4) = gi;
+      *reinterpret_cast<float4*>(gwgt + point * 4) = gw;
+      vlogit[point] = logit_pt + s_ol[v];
+    }
 
     // ---- the 198 positional features of plane_coefs' input ----
-    __nv_bfloat16* row = pe + point * kpe;
+    __nv_bfloat16* row = s_pe + static_cast<int>(threadIdx.x) * kpe;
     // PE16(p_view) 96 | p_view 3
     pos_enc<3, 16>(pv, [&](int idx, float val) { row[idx] = __float2bfloat16_rn(val); });
 #pragma unroll
@@ -185,6 +194,15 @@ nerf_points_kernel(const float* __restrict__ cams, const float* __restrict__ xy,
 #pragma unroll
     for (int k = 0; k < 3; ++k) row[195 + k] = __float2bfloat16_rn(dv[k]);
     for (int k = 198; k < kpe; ++k) row[k] = __float2bfloat16_rn(0.f);
+    __syncthreads();
+    {  // coalesced copy-out of the block's rows_here x kpe tile (kpe % 8 == 0: whole 16-byte vectors)
+      const long long first = ((static_cast<long long>(b) * n + v) * hw) * d + pid0;
+      uint4* dst = reinterpret_cast<uint4*>(pe + first * kpe);
+      const uint4* src = reinterpret_cast<const uint4*>(s_pe);
+      const int nvec = rows_here * (kpe >> 3);
+      for (int i = threadIdx.x; i < nvec; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();  // the tile is rewritten for the next view
   }
 }
 
@@ -377,10 +395,18 @@ extern "C" int cd360_nerf_points(const float* cams, const float* xy, const float
   if ((reinterpret_cast<uintptr_t>(gidx) & 15) || (reinterpret_cast<uintptr_t>(gwgt) & 15) ||
       (reinterpret_cast<uintptr_t>(pe) & 15))
     return CD360_ERR_ALIGN;
+  if (kpe > 256) return CD360_ERR_SHAPE;
   const int pts = res * res * d;
-  dim3 grid((pts + 127) / 128, b);
-  const size_t smem = (200 + NERF_MAX_VIEWS) * sizeof(float);
-  launch_ex(nerf_points_kernel, dim3(grid), dim3(128), smem, reinterpret_cast<cudaStream_t>(stream_), 1, 
+  dim3 grid((pts + NP_THREADS - 1) / NP_THREADS, b);
+  const size_t smem = (200 + 16) * sizeof(float) + static_cast<size_t>(NP_THREADS) * kpe * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(nerf_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (200 + 16) * 4 + NP_THREADS * 256 * 2) != cudaSuccess)
+      return CD360_ERR_LAUNCH;
+    attr_set = true;
+  }
+  launch_ex(nerf_points_kernel, dim3(grid), dim3(NP_THREADS), smem, reinterpret_cast<cudaStream_t>(stream_), 1, 
       cams, xy, depths, w_nv_geo, b_nv, reinterpret_cast<__nv_bfloat16*>(pe), gidx, gwgt, vlogit, b,
       n, res, d, kpe);
   CD360_CHECK_LAUNCH();
