@@ -29,7 +29,8 @@ class Denoiser(nn.Module):
 
     def __call__(self, network, input, sigma, cond, sigmas_ref=None, **kwargs):
         if sigmas_ref is not None or kwargs.get("input_ref") is not None:
-            raise NotImplementedError("reference-image noising (training path) is a later row of SURVEY §8f")
+            raise NotImplementedError("the training-time call with reference latents is Denoiser.train_forward "
+                                      "(taped forward + explicit backward; there is no autograd through __call__)")
         sigma = self.possibly_quantize_sigma(sigma)
         sigma_shape = sigma.shape
         sigma = append_dims(sigma, input.ndim)
