@@ -63,6 +63,7 @@ SIGNATURES = {
     "cd360_nerf_points": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_combine": (C.c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cd360_nerf_mask_ref": (C.c_int, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
     "cd360_splitk_slices": (C.c_int, [_I, _I, _I]),

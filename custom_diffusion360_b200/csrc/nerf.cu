@@ -13,6 +13,8 @@
 // coordinates), the 4-tap gather of G, SiLU, the softmax over views and the volume-rendering scan.
 // Camera conventions follow PyTorch3D (row vectors, X_cam = X_world R + T, NDC +X left / +Y up;
 // SURVEY.md §8c restates the pinned-dependency semantics).
+#include <algorithm>
+
 #include "cd360_common.cuh"
 
 namespace cd360 {
@@ -382,9 +384,58 @@ nerf_volrender_kernel(const __nv_bfloat16* __restrict__ feats, const float* __re
   }
 }
 
+// Reference padding masks (FeatureNeRFEncoding.forward, nerfsd_pytorch3d.py:61-70):
+//   mask = F.interpolate(mask_ref[(b n), 1, H, W], size=[res, res], mode="nearest");  xref = xref * mask
+// One pass over the reference tokens: row (bn, y, x) is scaled by mask[bn, floor(y*H/res), floor(x*W/res)]
+// (torch's legacy "nearest": src = min(floor(dst * scale), in - 1) with scale = in / out in fp32).
+__global__ void __launch_bounds__(256)
+nerf_mask_ref_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask,
+                     __nv_bfloat16* __restrict__ out, long long rows, int res, int mh, int mw, int c) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nvec = c >> 3;
+  const long long total = rows * nvec;
+  const float sy = static_cast<float>(mh) / static_cast<float>(res);
+  const float sx = static_cast<float>(mw) / static_cast<float>(res);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / nvec;
+    const int hw = res * res;
+    const long long bn = row / hw;
+    const int pix = static_cast<int>(row - bn * hw);
+    const int y = pix / res, xx = pix - y * res;
+    const int my = min(static_cast<int>(floorf(static_cast<float>(y) * sy)), mh - 1);
+    const int mx = min(static_cast<int>(floorf(static_cast<float>(xx) * sx)), mw - 1);
+    const float m = __ldg(mask + (bn * mh + my) * mw + mx);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    uint4 o;
+    o.x = pack_bf16x2(a.x * m, a.y * m);
+    o.y = pack_bf16x2(b.x * m, b.y * m);
+    o.z = pack_bf16x2(cc.x * m, cc.y * m);
+    o.w = pack_bf16x2(d.x * m, d.y * m);
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
 }  // namespace cd360
 
 using namespace cd360;
+
+extern "C" int cd360_nerf_mask_ref(const void* x, const float* mask, void* out, int64_t bn, int32_t res,
+                                   int32_t mh, int32_t mw, int32_t c, cd360_stream_t stream_) {
+  if (!x || !mask || !out) return CD360_ERR_NULL;
+  if (bn <= 0 || res <= 0 || mh <= 0 || mw <= 0 || c <= 0 || (c & 7)) return CD360_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return CD360_ERR_ALIGN;
+  const long long rows = static_cast<long long>(bn) * res * res;
+  const long long total = rows * (c >> 3);
+  const unsigned blocks = static_cast<unsigned>(std::min<long long>((total + 255) / 256, 148LL * 16));
+  launch_ex(nerf_mask_ref_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1,
+            reinterpret_cast<const __nv_bfloat16*>(x), mask, reinterpret_cast<__nv_bfloat16*>(out), rows, res,
+            mh, mw, c);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
 
 extern "C" int cd360_nerf_points(const float* cams, const float* xy, const float* depths,
                                  const float* w_nv_geo, const float* b_nv, void* pe, int32_t* gidx,

@@ -448,6 +448,21 @@ def nerf_combine(g, hpre, gidx, gwgt, vlogit, b, n, hw, d, c):
 
 
 @_op("nerf")
+def nerf_mask_ref(xref_tok, mask_ref, bn, res, *, out=None):
+    """xref_tok bf16 [bn*res*res, c] scaled row-wise by the nearest-resized padding masks
+    mask_ref fp32 [bn, (1,) mh, mw] (nerfsd_pytorch3d.py:61-70)."""
+    lib = _lib.load()
+    _req(xref_tok, bf16, "xref_tok")
+    m = mask_ref.reshape(bn, mask_ref.shape[-2], mask_ref.shape[-1])
+    _req(m, f32, "mask_ref")
+    if out is None:
+        out = torch.empty_like(xref_tok)
+    check(lib.cd360_nerf_mask_ref(_ptr(xref_tok), _ptr(m), _ptr(out), bn, res, m.shape[-2], m.shape[-1],
+                                  xref_tok.shape[-1], _stream()), "cd360_nerf_mask_ref")
+    return out
+
+
+@_op("nerf")
 def nerf_volrender(feats, raw, dists, b, hw, d, c):
     lib = _lib.load()
     dev = feats.device

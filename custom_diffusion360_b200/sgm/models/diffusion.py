@@ -51,6 +51,15 @@ class DiffusionEngine(nn.Module):
         super().__init__()
         if use_ema:
             raise NotImplementedError("use_ema=True is unused by the shipped config")
+        if trainkeys != "pose":
+            # 'poseattn' / 'all' would hand frozen SDXL weights to AdamW with zero gradients (the explicit
+            # backward only produces pose + conditioning gradients): decoupled weight decay would then
+            # shrink them every step.  The shipped config trains `pose` (train_co3d_concept.yaml:8).
+            raise NotImplementedError(f"trainkeys={trainkeys!r}: only 'pose' (the shipped config) is built")
+        if ckpt_path is not None:
+            raise NotImplementedError("ckpt_path: load checkpoints with sgm.util.load_checkpoints(engine, base_sd, delta_sd)")
+        if scheduler_config is not None:
+            raise NotImplementedError("scheduler_config is None in the shipped config; LR schedules are not built")
         self.log_keys = log_keys
         self.input_key = input_key
         self.trainkeys = trainkeys
@@ -77,10 +86,7 @@ class DiffusionEngine(nn.Module):
         self.first_stage_model = None
         # trainable set by parameter name (reference :119-147)
         for name, p in self.model.diffusion_model.named_parameters():
-            if trainkeys == "pose":
-                p.requires_grad = "pose" in name
-            elif trainkeys == "all":
-                p.requires_grad = True
+            p.requires_grad = "pose" in name
         self._fused: Optional[FusedGuidedStep] = None
 
     @property
@@ -255,7 +261,7 @@ class GraphedTrainStep:
         unet = engine.model.diffusion_model
         dev = engine.device
         k = engine.input_key
-        self.keys = [key for key in (k, k + "_ref", "mask", "depth", "rgb", "drop_im") if torch.is_tensor(batch.get(key))]
+        self.keys = [key for key in (k, k + "_ref", "mask", "mask_ref", "depth", "rgb", "drop_im") if torch.is_tensor(batch.get(key))]
         self.static = {key: batch[key].to(dev).clone() for key in self.keys}
         self.static["pose"] = pack_pose(batch["pose"], dev).clone()
         self.static_cond = {n: t.to(dev).clone() for n, t in batch["cond"].items()}

@@ -320,12 +320,16 @@ class BasicTransformerBlock(nn.Module):
         self._ctxref_cache = (key, tok, n)
         return tok
 
-    def reference_tokens(self, cams, xref_tok, n, kv, nkv, batch, hw):
+    def reference_tokens(self, cams, xref_tok, n, kv, nkv, batch, hw, mask_ref=None):
         """reference_attn (reference :571-598) in token layout -> (rendered bf16 [batch*hw, c],
-        fg [batch,hw], alphas [batch,hw,d], rgb [batch,hw,3])."""
+        fg [batch,hw], alphas [batch,hw,d], rgb [batch,hw,3]).  mask_ref: padding masks of the
+        reference views [batch, n, 1, H, W] (None at inference); UNetModel.forward installs the
+        call's masks as `_mask_ref` on every pose block."""
         nerf = self.pose_featurenerf
         d = nerf.raymarcher.num_samples
-        feats, raw, dists, _ = nerf.encode_tokens(cams, xref_tok, batch, n, hw)
+        if mask_ref is None:
+            mask_ref = self.__dict__.get("_mask_ref")
+        feats, raw, dists, _ = nerf.encode_tokens(cams, xref_tok, batch, n, hw, mask_ref=mask_ref)
         # feats += attn2(norm2(feats), context): the block's own norm2 / attn2 over every sample
         fn = self.norm2.tokens(feats)
         feats = self.attn2.tokens(fn, batch, hw * d, kv=kv, nkv=nkv, residual=feats, out=feats)
@@ -338,13 +342,11 @@ class BasicTransformerBlock(nn.Module):
 
     def reference_attn(self, x, context_ref, context, pose, prev_weights, mask_ref):
         """Reference-signature variant: context_ref [b, n, hw, c], context [b, 77, ctx]."""
-        if mask_ref is not None:
-            raise NotImplementedError("mask_ref is not supported on the inference path")
         b, n, hw, c = context_ref.shape
         cams = pack_pose(pose, x.device)
         kv = self.attn2.project_context(to_tokens(context))
         rendered, fg, alphas, rgb = self.reference_tokens(cams, to_tokens(context_ref), n, kv,
-                                                          context.shape[1], b, hw)
+                                                          context.shape[1], b, hw, mask_ref=mask_ref)
         d = alphas.shape[-1]
         return (ops.cast_f32(rendered).view(b, hw, c), fg.view(b, hw, 1), None,
                 alphas.view(b, hw, d, 1), rgb if self.rgb_predict else None)
@@ -491,11 +493,15 @@ class BasicTransformerBlock(nn.Module):
                                    residual=xt, out=xt)
             nv = context_ref.shape[0] // b
             rendered, fg, alphas, rgb = self.reference_tokens(cams, to_tokens(context_ref), nv, kv,
-                                                              context.shape[1], b, n)
+                                                              context.shape[1], b, n, mask_ref=mask_ref)
             xt = self.pose_emb_layers.tokens(xt, a1=rendered)
             xt = self.ff.tokens(self.norm3.tokens(xt), residual=xt, out=xt)
         else:
-            xt, aux = self.tokens(xt, b, n, ctx_tok, context.shape[1], cams)
+            self.__dict__["_mask_ref"] = mask_ref
+            try:
+                xt, aux = self.tokens(xt, b, n, ctx_tok, context.shape[1], cams)
+            finally:
+                self.__dict__.pop("_mask_ref", None)
             if aux is not None:
                 fg, alphas, rgb = aux
         if fg is not None:
@@ -587,8 +593,14 @@ class SpatialTransformer(nn.Module, _Packed):
         b, c, h, w = x.shape
         aux: list = []
         cams = pack_pose(pose, x.device) if pose is not None else None
-        y = self.tokens(ops.nchw_to_nhwc_bf16(x.float().contiguous()), b, h * w, to_tokens(context),
-                        context.shape[1], cams, aux)
+        for blk in self.transformer_blocks:
+            blk.__dict__["_mask_ref"] = mask_ref
+        try:
+            y = self.tokens(ops.nchw_to_nhwc_bf16(x.float().contiguous()), b, h * w, to_tokens(context),
+                            context.shape[1], cams, aux)
+        finally:
+            for blk in self.transformer_blocks:
+                blk.__dict__.pop("_mask_ref", None)
         out = ops.nhwc_to_nchw_f32(y, b, h * w, c).view(b, c, h, w)
         if aux:
             d = aux[0][1].shape[-1]

@@ -49,8 +49,6 @@ class StandardDiffusionLossImgRef(nn.Module):
     # ---- forward: noising, denoiser / UNet (taped), loss values -------------------------------------
     def __call__(self, network, denoiser, conditioner, input, input_rgb, input_ref, pose, mask, mask_ref,
                  opacity, batch):
-        if mask_ref is not None:
-            raise NotImplementedError("mask_ref (masked reference features) is not built")
         cond = conditioner(batch) if conditioner is not None else batch["cond"]
         rnd = batch.get("rand", {}) if isinstance(batch, dict) else {}
         dev = input.device
@@ -68,7 +66,7 @@ class StandardDiffusionLossImgRef(nn.Module):
                 input_ref = input_ref + nr * append_dims(sigmas_ref, input_ref.ndim)   # loss.py:163-170
         eps_tok, aux, tape, sigma_q = denoiser.train_forward(
             network, noised_input, sigmas, cond, sigmas_ref=sigmas_ref, input_ref=input_ref, pose=pose,
-            noise_ref2=rnd.get("noise_ref2"), jitter=rnd.get("jitter"))
+            noise_ref2=rnd.get("noise_ref2"), jitter=rnd.get("jitter"), mask_ref=mask_ref)
         self.last = NS(network=network, eps=eps_tok, aux=aux, tape=tape, sigma=sigma_q.float().contiguous(),
                        x_noisy=noised_input, target=input.float().contiguous(),
                        mask=None if mask is None else mask.float().contiguous())

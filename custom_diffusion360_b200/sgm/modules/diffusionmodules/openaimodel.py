@@ -369,9 +369,16 @@ class UNetModel(nn.Module, _Packed):
     def forward(self, x, timesteps=None, context=None, y=None, timesteps2=None, **kwargs):
         """x [B,4,L,L] fp32, timesteps [B], context [B,77,ctx], y [B,adm] ->
         (eps [B,4,L,L] fp32, fg_mask_list, alphas_list, predicted_rgb_list)."""
-        if kwargs.get("mask_ref") is not None:
-            raise NotImplementedError("mask_ref is not supported on the inference path")
         assert (y is not None), "must specify y: the model is class-conditional (num_classes='sequential')"
+        mask_ref = kwargs.get("mask_ref")
+        if mask_ref is not None:       # padding masks of the reference views (nerfsd_pytorch3d.py:61-70)
+            for _, m in self.pose_blocks():
+                m.__dict__["_mask_ref"] = mask_ref
+            try:
+                return self.forward(x, timesteps, context, y, timesteps2, **{k: v for k, v in kwargs.items() if k != "mask_ref"})
+            finally:
+                for _, m in self.pose_blocks():
+                    m.__dict__.pop("_mask_ref", None)
         # (CPU tensors are rejected by the first kernel wrapper: there is no CPU path)
         xr = kwargs.get("input_ref")
         if xr is None:
@@ -413,7 +420,7 @@ class UNetModel(nn.Module, _Packed):
 
     # ---- training step (explicit backward) ------------------------------------------
     def forward_train(self, x, timesteps=None, context=None, y=None, *, pose=None, input_ref=None,
-                      sigmas_ref=None, in_scale=None, jitter=None, **_ignored):
+                      sigmas_ref=None, in_scale=None, jitter=None, mask_ref=None, **_ignored):
         """The training-time call of the reference (openaimodel.py:1008-1093 with `input_ref`):
         the reference latents input_ref [b, n, 4, L, L] run as the no-grad reference stream
         (timesteps `sigmas_ref` broadcast over the views; second halves of context / y), the main
@@ -444,6 +451,7 @@ class UNetModel(nn.Module, _Packed):
             side.wait_stream(cur)
         for m in blocks.values():
             m.__dict__["_capture_events"] = side is not None
+            m.__dict__["_mask_ref"] = mask_ref       # reference padding masks (nerfsd_pytorch3d.py:61-70)
         try:
             with torch.no_grad():
                 if side is not None:
@@ -465,6 +473,7 @@ class UNetModel(nn.Module, _Packed):
                 m.__dict__.pop("_live_ctxref", None)
                 m.__dict__.pop("_capture_events", None)
                 m.__dict__.pop("_capture_ev", None)
+                m.__dict__.pop("_mask_ref", None)
                 m._ctxref_cache = None
 
     def backward(self, tape, deps, daux_of=None):

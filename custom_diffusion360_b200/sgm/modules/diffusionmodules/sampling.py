@@ -126,13 +126,22 @@ class FusedGuidedStep:
         self.n_steady = 0
         self.launches_per_step = None
 
+    @staticmethod
+    def quantize(table: torch.Tensor, sigma: float):
+        """(table index, quantised σ, c_in) of one σ of the schedule — `DiscreteDenoiser.sigma_to_idx`
+        / `possibly_quantize_sigma` (reference denoiser.py:65-75: argmin |σ − table| over the fp32
+        table, first minimum wins) and `EpsScaling.c_in` (denoiser_scaling.py:26-31).  Integer work:
+        tests/test_host_logic.py pins the index bit-exactly against the reference-generated golden."""
+        idx = int((torch.tensor(sigma, dtype=table.dtype) - table).abs().argmin())
+        sigma_q = float(table[idx])
+        return idx, sigma_q, 1.0 / (sigma_q ** 2 + 1.0) ** 0.5
+
     def _set_scalars(self, sigma: float, sigma_next: float):
-        idx = int((self.table - sigma).abs().argmin())      # DiscreteDenoiser.sigma_to_idx
-        sigma_q = float(self.table[idx])                     # possibly_quantize_sigma
+        idx, sigma_q, c_in = self.quantize(self.table, sigma)
         B = self.B
         h = self.scal_host
         h[:B] = float(idx)                                   # quantised c_noise -> table index
-        h[B:2 * B] = 1.0 / (sigma_q ** 2 + 1.0) ** 0.5       # EpsScaling.c_in
+        h[B:2 * B] = c_in                                    # EpsScaling.c_in
         h[2 * B], h[2 * B + 1], h[2 * B + 2] = sigma_q, sigma, sigma_next
         self.scal.copy_(h, non_blocking=True)
 

@@ -4,9 +4,11 @@ reference (sgm/modules/nerfsd_pytorch3d.py:23-464); the arithmetic is restructur
 csrc/nerf.cu (first Linear hoisted through the bilinear gather, second Linear applied after the
 view-weighted sum) and runs on tensor cores + fused geometry kernels.
 
-Scope: the inference flow the reference actually executes — deterministic depth bins, no
-importance sampling (`prev_weights` is never forwarded to the raymarcher), no
-reference mask (`mask_ref=None`, sample.py:181).  Requests outside it raise.
+Scope: the flow the reference actually executes — deterministic depth bins at inference, injected
+stratified variates in training (train_path.nerf_bins), no importance sampling (`prev_weights` is
+never forwarded to the raymarcher); the reference padding masks `mask_ref`
+(None at inference, sample.py:181; always present in training, data_co3d.py:485) are applied by
+`apply_mask_ref` (nerfsd_pytorch3d.py:61-70).  Requests outside it raise.
 """
 from __future__ import annotations
 
@@ -141,12 +143,25 @@ class NerfSDModule(nn.Module):
         self.model = self.MODES[mode](out_channels, out_channels, far_plane=near_plane + far_plane,
                                       rgb_predict=rgb_predict, average=average, num_freqs=num_freqs)
 
+    @staticmethod
+    def apply_mask_ref(xref_tok: torch.Tensor, mask_ref, b: int, n: int, hw: int) -> torch.Tensor:
+        """FeatureNeRFEncoding.forward step 1 (reference :61-70): `xref * nearest_resize(mask_ref)`.
+        mask_ref [b, n, 1, H, W] (or [b*n, 1, H, W] / [b*n, H, W]); xref_tok bf16 [b*n*hw, c] -> new tensor."""
+        if mask_ref is None:
+            return xref_tok
+        res = int(math.sqrt(hw))
+        m = mask_ref.reshape(b * n, mask_ref.shape[-2], mask_ref.shape[-1])
+        m = m.to(device=xref_tok.device, dtype=torch.float32).contiguous()
+        return ops.nerf_mask_ref(xref_tok, m, b * n, res)
+
     # ---- token-layout fast path -------------------------------------------------------------
-    def encode_tokens(self, cams: torch.Tensor, xref_tok: torch.Tensor, b: int, n: int, hw: int):
+    def encode_tokens(self, cams: torch.Tensor, xref_tok: torch.Tensor, b: int, n: int, hw: int, mask_ref=None):
         """cams fp32 [b, n+1, 16]; xref_tok bf16 [b*n*hw, c] -> plane_features_final bf16
         [b*hw*d, c], raw fp32 [b*hw*d, 4|1], dists [hw, d], view softmax fp32 [b, n, hw*d]."""
         if self.training and self.raymarcher.stratified:
-            raise NotImplementedError("stratified training-time jitter is outside the inference path built here")
+            raise NotImplementedError("stratified jitter needs injected variates: the training step goes through "
+                                      "train_path.nerf_forward (UNetModel.forward_train)")
+        xref_tok = self.apply_mask_ref(xref_tok, mask_ref, b, n, hw)
         pk = self.model.packed()
         c = pk["c"]
         d = self.raymarcher.num_samples
@@ -170,13 +185,11 @@ class NerfSDModule(nn.Module):
     def forward(self, pose, xref=None, mask_ref=None, prev_weights=None, imp_sample_next_step=False):
         """Reference contract (:434-464): xref [b, n, hw, c] -> (features [b,hw,d,c], sigma_raw
         [b,hw,d,1], dists [1,hw,d,1], view softmax [b,n,hw,d,1], rgb_raw | None, None, None)."""
-        if mask_ref is not None:
-            raise NotImplementedError("mask_ref is not supported (the sampling path passes None)")
         b, n, hw, c = xref.shape
         cams = pack_pose(pose, xref.device)
         tok = xref.reshape(b * n * hw, c)
         tok = tok if tok.dtype == torch.bfloat16 else ops.cast_bf16(tok.float().contiguous())
-        final, raw, dists, vsm = self.encode_tokens(cams, tok.contiguous(), b, n, hw)
+        final, raw, dists, vsm = self.encode_tokens(cams, tok.contiguous(), b, n, hw, mask_ref=mask_ref)
         d = self.raymarcher.num_samples
         feats = ops.cast_f32(final).view(b, hw, d, c)
         raw = raw.view(b, hw, d, -1)

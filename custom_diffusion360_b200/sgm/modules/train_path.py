@@ -166,6 +166,8 @@ def nerf_forward(block: BasicTransformerBlock, cams, xref_tok, n, kv, nkv, batch
     res = int(math.sqrt(hw))
     dev = xref_tok.device
     xy, depths, dists = nerf_bins(nerf, hw, dev, jitter)
+    # reference padding masks (nerfsd_pytorch3d.py:61-70); the masked tokens are also what dWg reads
+    xref_tok = nerf.apply_mask_ref(xref_tok, block.__dict__.get("_mask_ref"), batch, n, hw)
     g = ops.gemm(xref_tok, pk["wg"])
     pe, gidx, gwgt, vlogit = ops.nerf_points(cams, xy, depths, pk["wnv_geo"], pk["bnv"], batch, n, res, d, KPE)
     hpre = ops.gemm(pe, pk["w1p"], bias=pk["b1"])

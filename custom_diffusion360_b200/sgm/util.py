@@ -83,23 +83,34 @@ def append_zero(x):
 def delta_state_dict(engine, embed=None) -> dict:
     """What the reference's `CUDACallback.on_save_checkpoint` keeps (main.py:611-625): every
     state-dict entry whose key contains `pose` (but not `raymarcher`) or `references`, under the
-    Lightning module's key names (`model.diffusion_model.<name>`), plus `embed` — the two trained
-    token rows of the text encoders, which belong to the conditioner (outside this build) and are
-    passed through when the caller has them."""
+    Lightning module's key names (`model.diffusion_model.<name>`), plus `embed` — the trained
+    `<new1>` token rows of the two text encoders, `[clip_l_row, open_clip_row]`.  `embed` defaults to
+    the engine's own conditioner (`engine.conditioner.modifier_token_rows()`) when it has one."""
     st = engine.state_dict()
     out = {k: v.detach().clone() for k, v in st.items()
            if ("pose" in k and "raymarcher" not in k) or "references" in k}
+    if embed is None:
+        cond = getattr(engine, "conditioner", None)
+        if cond is not None and hasattr(cond, "modifier_token_rows"):
+            embed = cond.modifier_token_rows()
     if embed is not None:
-        out["embed"] = list(embed)
+        out["embed"] = [e.detach().clone() for e in embed]
     return out
 
 
 def save_delta_checkpoint(engine, path, embed=None, **extra):
     """`torch.save({'delta_state_dict': …})` — the file `sample.py --custom_model_dir` reads back
-    through `load_model_from_config`'s delta branch (sgm/util.py:225-237)."""
+    through `load_model_from_config`'s delta branch (sgm/util.py:225-237).  That loader indexes
+    `sd_delta['embed'][0]` and `[1]` unconditionally, so a checkpoint without the two token rows is
+    unreadable by the reference: `embed` is required (from the argument or the engine's conditioner)."""
     import torch
 
-    torch.save({"delta_state_dict": delta_state_dict(engine, embed), **extra}, path)
+    delta = delta_state_dict(engine, embed)
+    if "embed" not in delta or len(delta["embed"]) != 2:
+        raise ValueError("save_delta_checkpoint needs `embed` = [clip_l_token_row, open_clip_token_row] "
+                         "(the reference loader reads sd_delta['embed'][0] and [1], sgm/util.py:225-228); "
+                         "pass it or attach a conditioner that provides modifier_token_rows()")
+    torch.save({"delta_state_dict": delta, **extra}, path)
 
 
 class _CameraShell:

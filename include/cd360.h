@@ -244,6 +244,13 @@ int cd360_nerf_volrender(const void* feats, const float* raw, const float* dists
                          float* fg, float* alphas, float* rgb, int32_t b, int32_t hw, int32_t d,
                          int32_t c, cd360_stream_t stream);
 
+/* Reference padding masks (FeatureNeRFEncoding.forward step 1, nerfsd_pytorch3d.py:61-70; supplied by every
+ * training batch, data_co3d.py:485): out[(bn, y, x), :] = x[(bn, y, x), :] * mask[bn, floor(y*mh/res),
+ * floor(x*mw/res)] — F.interpolate(mask_ref, [res, res], mode="nearest") fused with the multiply.
+ * x / out bf16 [bn*res*res, c] (may alias), mask fp32 [bn, mh, mw]. */
+int cd360_nerf_mask_ref(const void* x, const float* mask, void* out, int64_t bn, int32_t res,
+                        int32_t mh, int32_t mw, int32_t c, cd360_stream_t stream);
+
 /* Utility: fp32 -> bf16 and bf16 -> fp32 contiguous conversion (weight prepack, I/O). */
 int cd360_cast_f32_to_bf16(const float* x, void* out, int64_t n, cd360_stream_t stream);
 int cd360_cast_bf16_to_f32(const void* x, float* out, int64_t n, cd360_stream_t stream);

@@ -305,7 +305,7 @@ class _TruncExp(torch.autograd.Function):
 
 def feature_nerf_encoding(sd, p: str, cams: Tensor, xref: Tensor, num_samples: int, far: float,
                           near: float = 0.0, num_freqs: int = 16, rgb_predict: bool = True,
-                          jitter: Optional[dict] = None):
+                          jitter: Optional[dict] = None, mask_ref: Optional[Tensor] = None):
     """Raymarcher.forward (eval, prev_weights=None; nerfsd_pytorch3d.py:332-394) +
     FeatureNeRFEncoding.forward (:53-161) + the split in NerfSDModule.forward (:443-449).
     cams [b, n+1, 16] (index 0 = target), xref [b, n, hw, c].
@@ -314,6 +314,11 @@ def feature_nerf_encoding(sd, p: str, cams: Tensor, xref: Tensor, num_samples: i
     b, n, hw, c = xref.shape
     res = int(math.sqrt(hw))
     d = num_samples
+    if mask_ref is not None:
+        # :61-70 — padding mask of every reference view [b, n, 1, H, W], nearest-resized to the block's
+        # resolution, zeroes the reference tokens that lie in the padded border
+        m = F.interpolate(mask_ref.reshape(b * n, *mask_ref.shape[2:]).float(), size=[res, res], mode="nearest")
+        xref = xref * m.reshape(b, n, -1, 1)
     xy = patch_ray_xy(res) if jitter is None else stratified_ray_xy(res, *jitter["xy_rand"])
     centers = camera_centers(cams)                                   # [b, n+1, 3]
     dirs = unproject_ndc_depth1_dirs(cams, xy)                       # [b, n+1, hw, 3]
@@ -382,7 +387,7 @@ def reference_attn(sd, p: str, cams: Tensor, xref: Tensor, context: Tensor, head
     feats, rgb_raw, sigma_raw, dists, _ = feature_nerf_encoding(
         sd, p + "pose_featurenerf.model.", cams, xref, cfg["num_samples"], cfg.get("far", 2.0),
         cfg.get("near_plane", 0.0), cfg.get("num_freqs", 16), cfg.get("rgb_predict", True),
-        jitter=next(jit) if jit is not None else None)
+        jitter=next(jit) if jit is not None else None, mask_ref=cfg.get("_mask_ref"))
     b, hw, d, c = feats.shape
     f2 = feats.reshape(b, hw * d, c)
     f2 = cross_attention(sd, p + "attn2.", layer_norm(sd, p + "norm2.", f2), context, heads) + f2

@@ -76,7 +76,7 @@ def training_loss(sd: Dict[str, Tensor], cfg: dict, batch: dict, *, global_step:
                   lambdas=(10.0, 10.0, 5.0), rgb: bool = True, rgb_predict: bool = True):
     """One training-step loss.  batch: x [b,4,L,L], x_ref [b,n,4,L,L], cams [b,n+1,16], crossattn
     [b+b*n,77,ctx], vector [b+b*n,adm], mask [b,1,L,L] | None, opacity [b,1,H,W], rgb [b,3,H,W] |
-    None, drop_im [b], rand = {sigma_idx [b], sigma_ref_idx [b], noise, noise_ref, noise_ref2,
+    None, mask_ref [b,n,1,H,W] | None (padding masks of the reference views), drop_im [b], rand = {sigma_idx [b], sigma_ref_idx [b], noise, noise_ref, noise_ref2,
     jitter | None}.  Returns (total loss, dict of the terms)."""
     x, x_ref = batch["x"], batch["x_ref"]
     b, n = x_ref.shape[:2]
@@ -99,7 +99,8 @@ def training_loss(sd: Dict[str, Tensor], cfg: dict, batch: dict, *, global_step:
     c_in = 1 / (sigma_q ** 2 + 1.0) ** 0.5
     c_noise = den.sigma_to_idx(sigma_q)
     jit = rnd.get("jitter")            # list of per-pose-block variates, in execution order
-    cfg_run = dict(cfg, _jitter=iter(jit) if jit else None, _probe=batch.get("_probe"), _probe_h=batch.get("_probe_h"))
+    cfg_run = dict(cfg, _jitter=iter(jit) if jit else None, _probe=batch.get("_probe"), _probe_h=batch.get("_probe_h"),
+                   _mask_ref=batch.get("mask_ref"))          # loss.py:154 -> nerfsd_pytorch3d.py:61-70
     (eps, aux), _ = O.unet_forward_with_reference_stream(
         sd, cfg_run, noised * O.append_dims(c_in, x.ndim), c_noise, batch["crossattn"][:b], batch["vector"][:b],
         batch["cams"], xr, t_ref, batch["crossattn"][b:], batch["vector"][b:])
@@ -147,7 +148,7 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=1e-4, b
 
 
 def synthetic_train_batch(cfg: dict, latent: int, n_views: int = 4, b: int = 1, seed: int = 0, image: int = 64,
-                          jitter: bool = False) -> dict:
+                          jitter: bool = False, mask_ref: bool = False) -> dict:
     """Seeded training batch of the shapes of config 4 (train_co3d_concept.yaml: 1 target + n refs)."""
     import numpy as np
 
@@ -165,6 +166,16 @@ def synthetic_train_batch(cfg: dict, latent: int, n_views: int = 4, b: int = 1, 
                   noise=f(b, cfg["in_channels"], latent, latent),
                   noise_ref=f(b, n_views, cfg["in_channels"], latent, latent),
                   noise_ref2=f(b, n_views, cfg["in_channels"], latent, latent)))
+    if mask_ref:  # data_co3d.py:485 `masks_padding[1:]`: non-square images padded to a square -> border bands of 0
+        m = torch.ones(b, n_views, 1, image, image)
+        for i in range(b):
+            for v in range(n_views):
+                w = int(rs.randint(image // 16, image // 4))
+                if (i + v) % 2:
+                    m[i, v, :, :w, :] = 0; m[i, v, :, image - w:, :] = 0
+                else:
+                    m[i, v, :, :, :w] = 0; m[i, v, :, :, image - w:] = 0
+        batch["mask_ref"] = m
     if jitter:   # one independent draw per pose block, in execution order (each Raymarcher call draws anew)
         jit = []
         for _, c, ds in O.pose_block_prefixes(cfg):

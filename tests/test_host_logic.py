@@ -168,6 +168,8 @@ def test_delta_checkpoint_round_trip(tmp_path):
         refs[n] = torch.randn(5, 16, c)
     unet.register_references(refs)
     path = tmp_path / "delta.ckpt"
+    with pytest.raises(ValueError, match="embed"):      # the reference loader indexes embed[0] / embed[1]
+        U.save_delta_checkpoint(eng, path)
     U.save_delta_checkpoint(eng, path, embed=[torch.zeros(1, 8), torch.zeros(1, 8)])
     ck = torch.load(path, weights_only=False)
     delta = ck["delta_state_dict"]
@@ -277,3 +279,18 @@ def test_splitk_plan_heuristic():
     assert plan(256, 1280, 1280) == 1           # fixed launch cost dominates below K = 2560
     assert plan(256, 1280, 5120, plain=False) == 1
     assert plan(256, 1282, 5120) == 1           # finish kernel works on 4-column vectors
+
+
+def test_engine_rejects_unbuilt_training_options():
+    """Options whose silent acceptance would corrupt training: any trainkeys other than
+    'pose' would put frozen SDXL weights under AdamW weight decay with zero gradients."""
+    from tests import test_train_step_gpu as G
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    cfg = dict(O.TINY_CFG)
+    base = G._engine_config(cfg) if hasattr(G, "_engine_config") else None
+    if base is None:
+        pytest.skip("engine config helper not available")
+    for bad in ({"trainkeys": "all"}, {"trainkeys": "poseattn"}, {"ckpt_path": "x.ckpt"},
+                {"scheduler_config": {"target": "x"}}, {"use_ema": True}):
+        with pytest.raises(NotImplementedError):
+            DiffusionEngine(**{**base, **bad})

@@ -457,3 +457,23 @@ def test_gemm_split_k(M, N, K, K1, splits):
     x = res.clone()
     ops.gemm(a, w, a1=a1, residual=x, out=x, k_splits=splits)
     _assert_close(x, ref + resf, what="split-K in-place residual")
+
+
+@gpu
+def test_nerf_mask_ref_nearest_resize_multiply():
+    """cd360_nerf_mask_ref == `xref * F.interpolate(mask_ref, [res, res], mode="nearest")`
+    (nerfsd_pytorch3d.py:61-70), incl. non-integer scale factors and non-square masks; 0/1 masks
+    (what data_co3d.py produces) are exact in bf16."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    for bn, res, mh, mw, c in ((6, 8, 48, 48, 64), (3, 16, 50, 37, 128), (2, 32, 32, 32, 640), (4, 8, 5, 7, 64)):
+        x = torch.randn(bn * res * res, c, generator=g).to(torch.bfloat16)
+        m = (torch.rand(bn, 1, mh, mw, generator=g) > 0.3).float()
+        ref = x.float().view(bn, res * res, c) * F.interpolate(m, size=[res, res], mode="nearest").reshape(bn, -1, 1)
+        out = ops.nerf_mask_ref(x.to(dev), m.to(dev), bn, res)
+        assert torch.equal(out.float().cpu().view(bn, res * res, c), ref), (bn, res, mh, mw, c)
+        soft = torch.rand(bn, 1, mh, mw, generator=g)
+        ref = x.float().view(bn, res * res, c) * F.interpolate(soft, size=[res, res], mode="nearest").reshape(bn, -1, 1)
+        out = ops.nerf_mask_ref(x.to(dev), soft.to(dev), bn, res).float().cpu().view(bn, res * res, c)
+        assert float((out - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())

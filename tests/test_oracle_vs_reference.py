@@ -188,7 +188,7 @@ def _reference_training_step(ns, cfg, sd, batch, seed, train_mode):
     conditioner = lambda bt: {"crossattn": batch["crossattn"], "vector": batch["vector"]}
     torch.manual_seed(seed)
     loss, loss_fg, loss_bg, loss_rgb = loss_fn(net, denoiser, conditioner, batch["x"], batch["rgb"], batch["x_ref"],
-                                               pose, batch["mask"], None, batch["opacity"], {})
+                                               pose, batch["mask"], batch.get("mask_ref"), batch["opacity"], {})
     # DiffusionEngine.forward (diffusion.py:221-236) with the yaml's lambdas, global_step > 0
     drop = batch["drop_im"]
     total = loss.mean()
@@ -219,16 +219,18 @@ def _reference_training_step(ns, cfg, sd, batch, seed, train_mode):
     return total.detach(), terms, grads, rand
 
 
-@pytest.mark.parametrize("train_mode", [False, True])
-def test_training_step_vs_reference(ns, train_mode):
+@pytest.mark.parametrize("train_mode,mask_ref", [(False, False), (True, False), (True, True)])
+def test_training_step_vs_reference(ns, train_mode, mask_ref):
     """The training oracle (oracle/train_oracle.py) against the reference's own training code:
     loss terms and the gradient of every trainable ('pose') parameter.  train_mode=True runs the
-    reference UNet in .train() — stratified ray / depth jitter on (yaml: stratified: True)."""
+    reference UNet in .train() — stratified ray / depth jitter on (yaml: stratified: True);
+    mask_ref=True passes the padding masks of the reference views (data_co3d.py:485 ->
+    loss.py:154 -> nerfsd_pytorch3d.py:61-70), as every reference training batch does."""
     from oracle import train_oracle as T
     cfg = dict(O.TINY_CFG)
     L, n = 16, 3
     sd = O.synthetic_state_dict(cfg, seed=2)
-    batch = T.synthetic_train_batch(cfg, L, n_views=n, b=1, seed=5, image=48)
+    batch = T.synthetic_train_batch(cfg, L, n_views=n, b=1, seed=5, image=48, mask_ref=mask_ref)
     total_ref, terms_ref, grads_ref, rand = _reference_training_step(ns, cfg, sd, batch, seed=11, train_mode=train_mode)
     batch = dict(batch, rand=rand)
     total, terms, grads = T.training_gradients(sd, cfg, batch)
@@ -239,6 +241,10 @@ def test_training_step_vs_reference(ns, train_mode):
     for k, g in grads_ref.items():
         scale = max(float(g.abs().max()), 1e-6)
         assert float((grads[k] - g).abs().max()) <= 2e-3 * scale, (k, float((grads[k] - g).abs().max()), scale)
+    if mask_ref:   # the masks must matter, or this case pins nothing
+        with torch.no_grad():
+            total_nomask, _ = T.training_loss(sd, cfg, {k: v for k, v in batch.items() if k != "mask_ref"})
+        assert abs(float(total_nomask) - float(total)) > 1e-3 * abs(float(total))
 
 
 def test_vae_decoder_oracle_vs_reference():

@@ -30,10 +30,9 @@ P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
 METRICS = {}
 
 
-def _engine(cfg, sd, dev):
-    from custom_diffusion360_b200.sgm.util import instantiate_from_config
+def _engine_config(cfg):
     disc = {"target": P + "discretizer.LegacyDDPMDiscretization"}
-    engine = instantiate_from_config({"target": "custom_diffusion360_b200.sgm.models.diffusion.DiffusionEngine", "params": dict(
+    return dict(
         network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
         denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
             "num_idx": 1000, "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
@@ -43,7 +42,13 @@ def _engine(cfg, sd, dev):
                                      "params": {"num_idx": 1000, "discretization_config": disc}},
             "sigma_sampler_config_ref": {"target": P + "sigma_sampling.DiscreteSampling",
                                          "params": {"num_idx": 50, "discretization_config": disc}}}},
-        trainkeys="pose", loss_rgb_lambda=5, loss_fg_lambda=10, loss_bg_lambda=10)})
+        trainkeys="pose", loss_rgb_lambda=5, loss_fg_lambda=10, loss_bg_lambda=10)
+
+
+def _engine(cfg, sd, dev, **extra):
+    from custom_diffusion360_b200.sgm.util import instantiate_from_config
+    engine = instantiate_from_config({"target": "custom_diffusion360_b200.sgm.models.diffusion.DiffusionEngine",
+                                      "params": {**_engine_config(cfg), **extra}})
     unet = engine.model.diffusion_model
     missing, unexpected = unet.load_state_dict(sd, strict=False)
     assert not unexpected and all("raymarcher" in m for m in missing)
@@ -58,10 +63,13 @@ def _to_engine_batch(batch, dev):
     rand["sigma_idx"], rand["sigma_ref_idx"] = r["sigma_idx"], r["sigma_ref_idx"]   # index the host tables
     if "jitter" in r:
         rand["jitter"] = r["jitter"]
-    return {"jpg": batch["x"].to(dev), "jpg_ref": batch["x_ref"].to(dev), "pose": batch["cams"].to(dev),
-            "mask": batch["mask"].to(dev), "depth": batch["opacity"].to(dev), "rgb": batch["rgb"].to(dev),
-            "drop_im": batch["drop_im"].to(dev),
-            "cond": {"crossattn": batch["crossattn"].to(dev), "vector": batch["vector"].to(dev)}, "rand": rand}
+    out = {"jpg": batch["x"].to(dev), "jpg_ref": batch["x_ref"].to(dev), "pose": batch["cams"].to(dev),
+           "mask": batch["mask"].to(dev), "depth": batch["opacity"].to(dev), "rgb": batch["rgb"].to(dev),
+           "drop_im": batch["drop_im"].to(dev),
+           "cond": {"crossattn": batch["crossattn"].to(dev), "vector": batch["vector"].to(dev)}, "rand": rand}
+    if batch.get("mask_ref") is not None:      # data_co3d.py:485: every reference training batch carries it
+        out["mask_ref"] = batch["mask_ref"].to(dev)
+    return out
 
 
 def _record(name, **kw):
@@ -73,13 +81,13 @@ def _record(name, **kw):
 
 
 @gpu
-@pytest.mark.parametrize("jitter,b", [(False, 1), (True, 2)])
-def test_training_step_gradients_vs_oracle(jitter, b):
+@pytest.mark.parametrize("jitter,b,mask_ref", [(False, 1, False), (True, 2, False), (True, 2, True)])
+def test_training_step_gradients_vs_oracle(jitter, b, mask_ref):
     dev = torch.device("cuda:0")
     cfg = dict(O.TINY_CFG)
     L, n = 16, 3
     sd = O.synthetic_state_dict(cfg, seed=2)
-    batch = T.synthetic_train_batch(cfg, L, n_views=n, b=b, seed=5, image=48, jitter=jitter)
+    batch = T.synthetic_train_batch(cfg, L, n_views=n, b=b, seed=5, image=48, jitter=jitter, mask_ref=mask_ref)
     if b > 1:
         batch["drop_im"] = torch.tensor([1.0, 0.0])[:b]     # second sample: reference images dropped
     total_ref, terms_ref, grads_ref = T.training_gradients(sd, cfg, _oracle_batch(batch))
@@ -110,13 +118,13 @@ def test_training_step_gradients_vs_oracle(jitter, b):
         rel = err / float(g_ref.norm())
         cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm()).clamp_min(1e-30))
         bn = block_norm[block_of(k)] ** 0.5
-        _record(f"jitter={jitter}/b={b}/{k}", rel_rms=rel, cosine=cos, ref_norm=float(g_ref.norm()), err_over_block=err / bn)
+        _record(f"jitter={jitter}/b={b}/mask_ref={mask_ref}/{k}", rel_rms=rel, cosine=cos, ref_norm=float(g_ref.norm()), err_over_block=err / bn)
         minor = float(g_ref.norm()) < 0.1 * bn
         assert (rel <= 0.12 and cos >= 0.99) or (minor and err <= 0.012 * bn), \
             f"{k}: rel_rms {rel:.4g}, cosine {cos:.5f}, err / block norm {err / bn:.4g}"
         worst = max(worst, (rel, k))
     gcos = dot / (n1 * n2) ** 0.5
-    _record(f"jitter={jitter}/b={b}/summary", loss=float(loss), loss_oracle=float(total_ref), worst_rel_rms=worst[0],
+    _record(f"jitter={jitter}/b={b}/mask_ref={mask_ref}/summary", loss=float(loss), loss_oracle=float(total_ref), worst_rel_rms=worst[0],
             worst_tensor=worst[1], tensors=len(grads_ref), global_cosine=gcos)
     assert gcos >= 0.998, gcos
     # optimiser: one fused AdamW step over the flat buffer == torch.optim.AdamW semantics on the same gradients

@@ -194,6 +194,21 @@ def test_forward_with_input_ref_vs_oracle(gold):
         _check(f"input_ref_fg_{i}", f, f2.reshape(f.shape), rel_tol=2e-2)
     # the stream leaves no state behind: stored references drive the next call again
     assert all(m.rendered_feat is None and "_live_ctxref" not in m.__dict__ for _, m in model.pose_blocks())
+    # with the padding masks of the reference views (mask_ref, nerfsd_pytorch3d.py:61-70)
+    mref = torch.ones(b, n, 1, 40, 40)
+    mref[:, ::2, :, :9, :] = 0
+    mref[:, 1::2, :, :, 28:] = 0
+    with torch.no_grad():
+        (ref_m, aux_m), _ = O.unet_forward_with_reference_stream(sd, dict(cfg, _mask_ref=mref), x, t, ctx, y, cams,
+                                                                 xr, sig, ctxr, yr)
+        eps_m, fg_m, _, _ = model(x.to(dev), timesteps=t.to(dev), context=torch.cat([ctx, ctxr]).to(dev),
+                                  y=torch.cat([y, yr]).to(dev), input_ref=xr.to(dev), sigmas_ref=sig.to(dev),
+                                  pose=cams.to(dev), mask_ref=mref.to(dev))
+    assert float((ref_m - ref).abs().max()) > 1e-3 * float(ref.abs().max())      # the masks matter
+    _check("input_ref_mask_ref_forward_eps", eps_m, ref_m)
+    for i, (f, (f2, a2, r2)) in enumerate(zip(fg_m, aux_m)):
+        _check(f"input_ref_mask_ref_fg_{i}", f, f2.reshape(f.shape), rel_tol=2e-2)
+    assert all("_mask_ref" not in m.__dict__ for _, m in model.pose_blocks())
 
 
 @gpu
