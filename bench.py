@@ -130,28 +130,39 @@ class ClockSampler:
 # reference arm / cpu_baseline: the oracle (restatement of the reference algorithm) on host cores
 # ------------------------------------------------------------------------------------------------
 
-def _oracle_forward_seconds(O, sd, cfg, latent, cache_feats, threads):
+def _oracle_step_seconds(O, sd, cfg, latent, threads, state=None):
+    """ONE guided denoising step of one image on the host, as the reference runs it in steady state
+    (sample.py / sampling.py:96-110): CFG rows (uc, uc, c) -> c_in -> UNet forward at batch 3 with the
+    pose blocks reading their cached rendered features (sample.py:123-133) -> c_out / c_skip -> CFG
+    combine (guiders.py:111-114) -> Euler update.  Nothing is extrapolated: the timed region is the
+    whole batch-3 step."""
     torch.set_num_threads(threads)
-    x = torch.randn(1, 4, latent, latent)
-    ctx = torch.randn(1, 77, cfg["context_dim"])
-    y = torch.randn(1, cfg["adm_in_channels"])
-    cache = {p: torch.randn(1, (latent // ds) ** 2, c) for p, c, ds in O.pose_block_prefixes(cfg)} if cache_feats else None
-    cams = torch.zeros(1, 9, 16) if cache_feats else None
+    if state is None:
+        g = torch.Generator().manual_seed(latent)
+        state = dict(
+            x=torch.randn(1, 4, latent, latent, generator=g) * 14.6,
+            ctx=torch.cat([torch.zeros(2, 77, cfg["context_dim"]), torch.randn(1, 77, cfg["context_dim"], generator=g)]),
+            y=torch.randn(1, cfg["adm_in_channels"], generator=g).expand(3, -1).contiguous(),
+            cache={p: torch.randn(3, (latent // ds) ** 2, c, generator=g) for p, c, ds in O.pose_block_prefixes(cfg)},
+            cams=torch.zeros(3, 9, 16), table=O.legacy_ddpm_sigmas(1000, do_append_zero=False, flip=True),
+            sig=O.legacy_ddpm_sigmas(50), i=1)
+    st = state
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.unet_forward(sd, cfg, x, torch.tensor([500]), ctx, y, cams=cams, choices=list(range(8)), cache=cache)
-    return time.perf_counter() - t0
+        s, s_next = st["sig"][st["i"]], st["sig"][st["i"] + 1]
+        idx = (s - st["table"]).abs().argmin()
+        sq = st["table"][idx]
+        x3 = torch.cat([st["x"]] * 3)
+        eps, _ = O.unet_forward(sd, cfg, x3 / (sq ** 2 + 1.0) ** 0.5, idx.reshape(1).expand(3), st["ctx"], st["y"],
+                                cams=st["cams"], choices=list(range(8)), cache=st["cache"])
+        d_u, d_ic, d_c = (eps * (-sq) + x3).chunk(3)
+        den = d_u + 7.5 * (d_c - d_ic) + 3.5 * (d_ic - d_u)
+        st["x"] = st["x"] + (st["x"] - den) / s * (s_next - s)
+    st["i"] = 1 + st["i"] % 48
+    return time.perf_counter() - t0, state
 
 
-def cpu_reference(steps: int, warmup: int, budget_s: float, latent: int = 128):
-    """Times the oracle's UNet forward for ONE CFG row (batch 1) with the pose blocks in their
-    steady state (cached rendered features -> pose_emb_layers only), fp32, all host threads;
-    a guided step is 3 such rows (CPU time is linear in batch).  Picks the largest latent
-    (128 preferred, else 64 scaled by the algorithmic FLOP ratio) that fits the time budget."""
-    from oracle import sgm_oracle as O
-    from custom_diffusion360_b200.synthetic import UNET_TFLOP_PER_ROW
-    threads = os.cpu_count() or 1
-    cfg = dict(O.SDXL_CFG)
+def _oracle_weights(O, cfg):
     g = torch.Generator().manual_seed(0)
     sd = {}
     for name, shape in O.param_shapes(cfg).items():
@@ -159,35 +170,44 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, latent: int = 128):
             sd[name] = (torch.ones(shape) if name.endswith("weight") else torch.zeros(shape))
         else:
             sd[name] = torch.randn(shape, generator=g) / math.sqrt(float(torch.tensor(shape[1:]).prod()))
-    _oracle_forward_seconds(O, sd, cfg, 32, True, threads)   # thread-pool / allocator warm-up
+    return sd
+
+
+def cpu_reference(steps: int, warmup: int, latent: int = 128):
+    """The reference algorithm on the host cores: `warmup` + `steps` REAL guided steps (batch 3, the
+    benchmark's latent size) of the oracle — the fp32 torch-CPU restatement of the reference's UNet,
+    pinned against the reference's own modules (tests/test_oracle_vs_reference.py); the reference
+    itself cannot be installed here.  Returns (cpu_baseline dict, mean seconds per
+    step, timed steps)."""
+    from oracle import sgm_oracle as O
+    threads = os.cpu_count() or 1
+    cfg = dict(O.SDXL_CFG)
+    sd = _oracle_weights(O, cfg)
+    _oracle_step_seconds(O, sd, cfg, 16, threads)   # thread-pool / allocator warm-up
     # torch's CPU kernels stop scaling (and can regress) far below the core count of a big host:
-    # keep the thread count that is actually fastest on a small calibration run
+    # keep the thread count that is actually fastest on a small calibration step
     cand = sorted({threads, min(threads, 64), min(threads, 32), min(threads, 16)}, reverse=True)
-    timing = {c: _oracle_forward_seconds(O, sd, cfg, 32, True, c) for c in cand}
+    timing = {c: _oracle_step_seconds(O, sd, cfg, 16, c)[0] for c in cand}
     threads = min(timing, key=timing.get)
-    t32 = timing[threads]
-    n = max(1, steps + warmup)
-    est128 = t32 * 17.0
-    use = 128 if (latent == 128 and est128 * n <= budget_s) else 64
-    if use == 64 and t32 * 4.1 * n > budget_s:
-        n = max(1, int(budget_s / (t32 * 4.1)))
-    times = [_oracle_forward_seconds(O, sd, cfg, use, True, threads) for _ in range(n)]
-    timed = times[min(warmup, len(times) - 1):] or times
-    t_row = sum(timed) / len(timed)
-    scale = UNET_TFLOP_PER_ROW[latent] / UNET_TFLOP_PER_ROW[use]
-    t_step = 3.0 * t_row * scale
-    sample = (f"oracle (fp32 torch CPU restatement of the reference UNet) forward of 1 of the 3 CFG rows at "
-              f"{use}x{use} latents, pose blocks in cached steady state, {len(timed)} timed evaluation(s); "
-              f"step time = 3 rows x {t_row:.2f} s" + (f" x FLOP ratio {scale:.3f} ({use}->{latent})" if use != latent else ""))
+    state = None
+    times = []
+    for _ in range(warmup + steps):
+        t, state = _oracle_step_seconds(O, sd, cfg, latent, threads, state)
+        times.append(t)
+    timed = times[warmup:]
+    t_step = sum(timed) / len(timed)
+    sample = (f"oracle (fp32 torch-CPU restatement of the reference UNet, kind=port) running {len(timed)} timed + {warmup} "
+              f"warm-up REAL guided steps: UNet batch 3 at {latent}x{latent} latents, pose blocks in cached steady state, "
+              f"c_in / c_out / CFG combine / Euler included; {threads} threads; nothing extrapolated")
     return dict(value=1.0 / t_step, unit=UNIT, cores=threads, kind="port", sample=sample), t_step, len(timed)
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    base, t_step, n_timed = cpu_reference(args.steps, args.warmup, budget_s=200.0, latent=args.latent)
+    base, t_step, n_timed = cpu_reference(args.steps, args.warmup, latent=args.latent)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+            "steps": n_timed, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -256,6 +276,20 @@ def make_step(latent, n_img, dev, rank=0, use_graph=True):
 # training step (BASELINE configs[3]: main.py train_co3d_concept.yaml fine-tune step, DDP)
 # ------------------------------------------------------------------------------------------------
 
+def _padding_masks(b, n_views, img, dev):
+    """masks_padding of the reference views (data_co3d.py:485): non-square images padded to a square."""
+    m = torch.ones(b, n_views, 1, img, img, device=dev)
+    for v in range(n_views):
+        w = img // 16 * (1 + v % 3)
+        if v % 2:
+            m[:, v, :, :w, :] = 0
+            m[:, v, :, img - w:, :] = 0
+        else:
+            m[:, v, :, :, :w] = 0
+            m[:, v, :, :, img - w:] = 0
+    return m
+
+
 def make_train(latent, n_views, dev, rank=0):
     from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
     from custom_diffusion360_b200 import synthetic as S
@@ -288,26 +322,26 @@ def make_train(latent, n_views, dev, rank=0):
              "pose": S.lookat_cameras(n_views, seed=rank)[None].to(dev),
              "mask": (u(b, 1, latent, latent) > 0.25).float(), "depth": (u(b, 1, img, img) > 0.5).float(),
              "rgb": u(b, 3, img, img) * 2 - 1, "drop_im": torch.ones(b, device=dev),
+             "mask_ref": _padding_masks(b, n_views, img, dev),
              "cond": {"crossattn": r(b + b * n_views, 77, cfg["context_dim"]),
                       "vector": r(b + b * n_views, cfg["adm_in_channels"])}}
     return engine, net, batch
 
 
-def run_train(args, world, rank, local_rank):
+def train_measure(args, world, rank, local_rank, steps, warmup, per_kernel=True):
     """One optimisation step per "step": reference stream (n_views rows, no grad) + taped main
-    stream + loss + explicit backward to the pose weights + gradient all-reduce + fused AdamW.
-    64x64 latents (512^2 images), 1 sample (1 target + 4 reference views) per GPU — the shipped
-    train_co3d_concept.yaml; stratified ray / depth jitter on."""
+    stream + loss + explicit backward to the pose weights (and to the conditioning) + gradient
+    all-reduce + fused AdamW.  64x64 latents (512^2 images), 1 sample (1 target + 4 reference views)
+    per GPU — the shipped train_co3d_concept.yaml; stratified ray / depth jitter on; mask_ref supplied
+    like every reference batch does.  The process group (world > 1) must already exist.
+    Returns the record on every rank (timings are max over ranks)."""
     import torch.distributed as dist
     from custom_diffusion360_b200 import ops
     from custom_diffusion360_b200 import synthetic as S
 
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    latent, n_views = args.latent, 4
+    latent, n_views = (64 if args.latent == 128 else args.latent), 4
     engine, net, batch = make_train(latent, n_views, dev, rank)
     opt = engine.configure_optimizers()
     d = S.SDXL_CFG["num_samples"]
@@ -334,69 +368,86 @@ def run_train(args, world, rank, local_rank):
     loss0 = float(one_step(0))
     launches_per_step = ops.LaunchStats.launches - n0
     eager_step = one_step
+    gs = None
     if not args.no_graph:
         # the step replayed from a CUDA graph (sgm/models/diffusion.py: GraphedTrainStep); the random
         # draws (sigma, noise, stratified variates) are renewed on the device before every replay
         from custom_diffusion360_b200.sgm.models.diffusion import GraphedTrainStep
         gs = GraphedTrainStep(engine, opt, batch)
         one_step = lambda i: gs(batch)
-    for i in range(1, max(args.warmup, 3)):
+    for i in range(1, max(warmup, 3)):
         one_step(i)
     torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks.start()
-    e0.record()
-    for i in range(args.steps):
-        loss = one_step(100 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    clk = clocks.stop()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
-    # per-kernel pass (eager, CUDA events around each launch)
-    rec = {}
 
-    def hook(name, flops, fn):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = fn()
-        b.record()
-        rec.setdefault(name, []).append((flops, a, b))
-        return r
-
-    ops.LaunchStats.hook = hook
-    _hide_launch_latency(0.8)
-    eager_step(999)
-    ops.LaunchStats.hook = None
-    torch.cuda.synchronize()
-    kern = {}
-    for name, items in rec.items():
-        fl = sum(f for f, _, _ in items)
-        tt = sum(a.elapsed_time(b) for _, a, b in items)
-        kern[name] = {"launches": len(items), "launched_tflop": fl / 1e12, "ms": tt,
-                      "tflops": fl / 1e9 / tt if tt > 0 and fl > 0 else None}
-    if rank != 0:
+    def timed(fn, k):
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            out = fn(100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t), out
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms, loss = timed(one_step, steps)
+    clk = clocks.stop()
+    # exposed gradient-exchange time: the same step with the all-reduces switched off (every rank then
+    # applies only its own gradient — measurement only, after the timed region)
+    exposed_ms = allreduce_alone_ms = None
+    if world > 1:
+        opt.comm_enabled = False
+        ms_nocomm, _ = timed(one_step, max(3, steps // 2))
+        opt.comm_enabled = True
+        exposed_ms = ms / steps - ms_nocomm / max(3, steps // 2)
+        def only_reduce(i):
+            opt.reduce_all()
+            opt.wait_reduce()
+        only_reduce(0)
+        t_ar, _ = timed(only_reduce, 5)
+        allreduce_alone_ms = t_ar / 5
+    kern = {}
+    if per_kernel:
+        rec = {}
+
+        def hook(name, flops, fn):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            rec.setdefault(name, []).append((flops, a, b))
+            return r
+
+        ops.LaunchStats.hook = hook
+        _hide_launch_latency(0.8)
+        eager_step(999)
+        ops.LaunchStats.hook = None
+        torch.cuda.synchronize()
+        for name, items in rec.items():
+            fl = sum(f for f, _, _ in items)
+            tt = sum(a.elapsed_time(b) for _, a, b in items)
+            kern[name] = {"launches": len(items), "launched_tflop": fl / 1e12, "ms": tt,
+                          "tflops": fl / 1e9 / tt if tt > 0 and fl > 0 else None}
     gk = kern.get("gemm", {})
     line = {
-        "metric": "training-steps/sec SDXL 512^2 pose fine-tune (train_co3d_concept.yaml)", "value": world * args.steps / (ms / 1e3),
-        "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": "training-steps/sec SDXL 512^2 pose fine-tune (train_co3d_concept.yaml)", "value": world * steps / (ms / 1e3),
+        "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 (fp32 loss / weight gradients / AdamW)",
         "data": "synthetic (random-init SDXL-shaped weights, seeded latents / embeddings / cameras / masks)",
         "config": {"workload": f"main.py train_co3d_concept.yaml step: {latent}x{latent} latents, 1 sample per GPU = 1 target + "
-                               f"{n_views} reference views (reference stream no-grad), FeatureNeRF in all 12 pose blocks with "
-                               f"stratified jitter, l2 + fg/bg/rgb losses, backward to the pose weights, DDP all-reduce, AdamW",
-                   "parallelism": f"data-parallel x{world} (bucketed all-reduce of {opt.flat.numel} fp32 gradients "
-                                  f"overlapped with the backward walk when eager, after the graph replay otherwise)",
+                               f"{n_views} reference views (reference stream no-grad), mask_ref padding masks, FeatureNeRF in all 12 pose "
+                               f"blocks with stratified jitter, l2 + fg/bg/rgb losses, backward to the pose weights and to the "
+                               f"conditioning (crossattn / vector), DDP all-reduce, AdamW",
+                   "parallelism": f"data-parallel x{world} (bucketed all-reduce of {opt.flat.numel} fp32 gradients, "
+                                  + ("captured inside the step's CUDA graph on a side stream, overlapped with the backward walk"
+                                     if getattr(gs, "comm_in_graph", False) else "on a side stream, overlapped with the backward walk when eager") + ")",
                    "cuda_graph": not args.no_graph,
                    "l2": "inputs larger than L2: ~5 GB of bf16 weights + ~5 GB of transposed packs stream per step"},
         "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (forward, dX and dW launches of one training step)", "bound": "tensor",
@@ -406,13 +457,102 @@ def run_train(args, world, rank, local_rank):
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
         "kernels_note": "per-kernel times come from one extra EAGER step with CUDA events around every launch, "
                         "enqueued behind a spin kernel so that host launch latency does not enter the intervals",
-        "kernels": kern, "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
+        "kernels": kern, "gpu_launches": launches_per_step * steps * world, "launches_per_step": launches_per_step,
         "loss_first_step": loss0, "loss_last_step": float(loss), "loss_terms_last_eager_step": engine.last_loss_dict, "clocks": clk,
         "trainable_values": opt.flat.numel, "allreduce_bytes_per_step": 4 * opt.flat.numel if world > 1 else 0,
+        "exposed_allreduce_ms_per_step": exposed_ms, "allreduce_alone_ms": allreduce_alone_ms,
+        "exposed_note": "exposed = step time - time of the same step with the all-reduces switched off; "
+                        "allreduce_alone_ms = all buckets reduced back to back on an otherwise idle GPU",
     }
-    print(json.dumps(line))
+    del gs, engine, net, opt
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_train(args, world, rank, local_rank):
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = train_measure(args, world, rank, local_rank, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sub_records(args, world, rank, dev, engine, net, sigmas):
+    """Sub-records of the headline line (same process, same network, after the headline's timed
+    region), every rank runs them, times are max over ranks:
+      config3_n_img4 — BASELINE configs[2] per GPU: 4 images per GPU, UNet batch 12, steady-state steps;
+      config5_sweep  — BASELINE configs[4]: one sweep unit = ONE target pose x 4 prompts in one batch,
+                       all 50 steps incl. the step-0 FeatureNeRF; per-pose latency and aggregate steps/s."""
+    import torch.distributed as dist
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    from custom_diffusion360_b200 import synthetic as S
+    cfg = dict(S.SDXL_CFG)
+    n4 = 4
+    latent = args.latent
+    nsig = len(sigmas) - 1
+
+    def tmax(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    net.clear_rendered_feat()
+    cond, uc = S.make_conditioning(cfg, n4, dev, seed=rank + 17)
+    poses = [S.lookat_cameras(8, seed=rank * 100 + i, target_azimuth=0.35 + 0.5 * i) for i in range(n4)]
+    step4 = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, cond, uc, pose=poses, n_img=n4,
+                            latent_shape=(4, latent, latent), use_graph=not args.no_graph)
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    x_init = torch.randn(n4, 4, latent, latent, device=dev, generator=g) * float(torch.sqrt(1.0 + sigmas[0] ** 2))
+    x = x_init.clone()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step4(x, float(sigmas[0]), float(sigmas[1]))
+    for i in range(1, 5):                       # eager steady step + graph capture + 2 replays
+        step4(x, float(sigmas[i]), float(sigmas[i + 1]))
+    k = max(5, args.steps // 2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(k):
+        j = 5 + i % (nsig - 5)
+        step4(x, float(sigmas[j]), float(sigmas[j + 1]))
+    e1.record()
+    torch.cuda.synchronize()
+    ms4 = tmax(e0.elapsed_time(e1))
+    rec3 = {"workload": "BASELINE configs[2] per GPU: 4 images per GPU (UNet batch 12), steady-state guided steps",
+            "n_img_per_gpu": n4, "steps": k, "ms_per_step": ms4 / k, "value": world * n4 * k / (ms4 / 1e3), "unit": UNIT,
+            "tflops_per_gpu": 3 * n4 * S.UNET_TFLOP_PER_ROW.get(latent, float("nan")) * k / (ms4 / 1e3)}
+    # ---- sweep: two sweep units (poses), each = set_pose + 50 steps of a 4-prompt batch ----
+    lat = []
+    n_pose = 2
+    for pi in range(n_pose):
+        tgt = [S.lookat_cameras(8, seed=rank * 100, target_azimuth=math.radians(10.0 * (pi + 1)))] * n4
+        x.copy_(x_init)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        step4.set_pose(tgt)
+        for i in range(nsig):
+            step4(x, float(sigmas[i]), float(sigmas[i + 1]))
+        e1.record()
+        torch.cuda.synchronize()
+        lat.append(tmax(e0.elapsed_time(e1)))
+    per_pose = sum(lat) / len(lat)
+    rec5 = {"workload": "BASELINE configs[4] sweep unit: 1 target pose x 4 prompts in one batch (UNet batch 12), all 50 steps "
+                        "incl. step-0 FeatureNeRF of the 12 pose blocks; 36 poses x 4 prompts = 36 such units, 36 / n_gpus per GPU",
+            "poses_timed": n_pose, "per_pose_latency_ms": per_pose, "per_pose_latency_ms_each": lat,
+            "images_per_pose": n4, "value": world * n4 * nsig / (per_pose / 1e3), "unit": UNIT,
+            "sweep_36_poses_s_estimate": per_pose / 1e3 * math.ceil(36 / world),
+            "note": "value = aggregate guided steps/s over all GPUs with step 0 inside the timed region"}
+    del step4
+    net.clear_rendered_feat()
+    return {"config3_n_img4": rec3, "config5_sweep": rec5}
 
 
 def main():
@@ -427,6 +567,7 @@ def main():
     ap.add_argument("--n-img", dest="n_img", type=int, default=1, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the configs[2] / [3] / [4] sub-records")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -573,6 +714,22 @@ def main():
             kern[name] = {"launches": len(items), "algorithmic_tflop": fl / 1e12, "ms": tt,
                           "tflops": fl / 1e9 / tt if tt > 0 else None}
 
+        step.use_graph = not args.no_graph
+        # ---- BASELINE configs[2] (4 images per GPU, UNet batch 12) and configs[4] (360-degree sweep: one
+        #      target pose x 4 prompts per batch, per-pose latency incl. step-0 FeatureNeRF) ----
+        sub = {}
+        if not args.no_sub and args.n_img == 1:
+            sub = sub_records(args, world, rank, dev, engine, net, sigmas)
+    train_rec = None
+    if not args.no_sub and args.n_img == 1:
+        del step
+        net.clear_rendered_feat()
+        torch.cuda.empty_cache()
+        try:
+            train_rec = train_measure(args, world, rank, local_rank, steps=max(5, args.steps // 2), warmup=3,
+                                      per_kernel=(world == 1))
+        except Exception as e:      # reported extras never break the headline line
+            train_rec = {"error": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -609,6 +766,9 @@ def main():
         "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,
         "cuda_graph": not args.no_graph, "clocks": clk,
     }
+    line.update(sub)
+    if train_rec is not None:
+        line["train_step"] = train_rec
     if world == 1:
         try:
             line["first_stage_decode"] = decode_timing(args.latent, dev, peaks)
@@ -616,7 +776,7 @@ def main():
             line["first_stage_decode"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            base, _, _ = cpu_reference(1, 0, budget_s=30.0, latent=args.latent)
+            base, _, _ = cpu_reference(1, 0, latent=args.latent)
             line["cpu_baseline"] = base
         except Exception as e:  # the baseline is a reported extra, never the thing measured
             line["cpu_baseline"] = {"error": repr(e)}

@@ -126,6 +126,29 @@ class FusedGuidedStep:
         self.n_steady = 0
         self.launches_per_step = None
 
+    def set_pose(self, pose):
+        """New target / reference cameras for the NEXT image(s) (the 360-degree sweep of BASELINE
+        configs[4]: same prompts, another target camera).  The packed cameras are overwritten IN PLACE
+        and the rendered-feature caches dropped: the next call runs FeatureNeRF eagerly (step 0 of the
+        image), later calls replay the already captured graph, which reads the same buffers."""
+        cams = pack_pose(pose, self.dev).repeat(self.rows, 1, 1).contiguous()
+        if self.cams is None or self.cams.shape != cams.shape:
+            raise ValueError("set_pose: camera batch shape differs from the one this step was built with")
+        self.cams.copy_(cams)
+        self.net.clear_rendered_feat()
+
+    def set_cond(self, cond: dict, uc: dict):
+        """New prompts (text / vector conditioning) for the next image(s), written in place into the
+        buffers the captured graph reads.  K/V of the text context are re-projected inside every step,
+        FeatureNeRF's attn2-over-samples depends on them too: the caches are dropped."""
+        x0 = torch.zeros(self.n_img, 1, device=self.dev)
+        _, _, c_all = self.guider.prepare_inputs(x0, torch.ones(self.n_img, device=self.dev),
+                                                 {k: v.to(self.dev) for k, v in cond.items()},
+                                                 {k: v.to(self.dev) for k, v in uc.items()})
+        self.ctx_tok.copy_(to_tokens(c_all["crossattn"][: self.B].float().contiguous()))
+        self.y.copy_(c_all["vector"][: self.B].float())
+        self.net.clear_rendered_feat()
+
     @staticmethod
     def quantize(table: torch.Tensor, sigma: float):
         """(table index, quantised σ, c_in) of one σ of the schedule — `DiscreteDenoiser.sigma_to_idx`

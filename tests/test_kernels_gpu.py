@@ -465,6 +465,7 @@ def test_nerf_mask_ref_nearest_resize_multiply():
     (nerfsd_pytorch3d.py:61-70), incl. non-integer scale factors and non-square masks; 0/1 masks
     (what data_co3d.py produces) are exact in bf16."""
     import torch.nn.functional as F
+    from custom_diffusion360_b200 import ops
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(0)
     for bn, res, mh, mw, c in ((6, 8, 48, 48, 64), (3, 16, 50, 37, 128), (2, 32, 32, 32, 640), (4, 8, 5, 7, 64)):

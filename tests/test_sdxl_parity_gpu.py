@@ -1,0 +1,216 @@
+"""Parity of the CUDA path on the configuration that is BENCHMARKED (BASELINE.json configs[1] / [2]):
+the full SDXL-width UNet (c = 320 / 640 / 1280, 70 transformer blocks) with FeatureNeRF ON
+(12 pose blocks, n = 8 reference views, d = 24 depth samples), UNet batch 3 (one CFG triple), at
+64x64 and 128x128 latents — against the fp32 oracle (oracle/sgm_oracle.py, the unhoisted restatement
+pinned to the reference's own modules) evaluated ON THE GPU in strict fp32 (TF32 off): the CPU cannot
+finish this size in test time (19 TFLOP of FeatureNeRF MLP per batch row at 128x128).
+
+Tolerances (stated per tensor): ~300 sequential bf16 roundings of the residual stream
+-> eps rel_rms <= 6e-2, max_abs <= 0.25 max|ref|; per pose block fg / alphas / rgb (fp32 geometry,
+one bf16 MLP) rel_rms <= 2e-2.  Measured values -> gpurun_out/parity_sdxl_metrics.json
+(copied to profiles/parity_r02.json).
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import sgm_oracle as O
+
+gpu = pytest.mark.gpu
+METRICS = {}
+P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+
+
+def _record(name, ours, ref):
+    ours, ref = ours.detach().float().cpu(), ref.detach().float().cpu()
+    rel = float((ours - ref).norm() / ref.norm().clamp_min(1e-12))
+    mx = float((ours - ref).abs().max())
+    METRICS[name] = dict(rel_rms=rel, max_abs=mx, ref_max=float(ref.abs().max()))
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_sdxl_metrics.json"), "w") as f:
+        json.dump(METRICS, f, indent=1)
+    return rel, mx, float(ref.abs().max())
+
+
+def _check(name, ours, ref, rel_tol, max_frac):
+    rel, mx, refmax = _record(name, ours, ref)
+    assert rel <= rel_tol, f"{name}: rel_rms {rel:.4g} > {rel_tol}"
+    assert mx <= max_frac * refmax + 1e-3, f"{name}: max_abs {mx:.4g} vs ref max {refmax:.4g}"
+
+
+@pytest.fixture(scope="module")
+def sdxl():
+    """The SDXL-width pose-conditioned UNet with seeded random weights, built ONCE on the GPU (2.6 B
+    parameters): (model, fp32 state dict on the device for the oracle)."""
+    from custom_diffusion360_b200 import synthetic as S
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    dev = torch.device("cuda:0")
+    cfg = dict(S.SDXL_CFG)
+    with torch.device("meta"):
+        model = UNetModel(**cfg)
+    model = model.to_empty(device=dev)
+    for m in model.modules():      # buffers of the raymarcher were created on `meta`: rebuild them
+        if m.__class__.__name__ == "Raymarcher":
+            fresh = type(m)(num_samples=m.num_samples, far_plane=m.far_plane, stratified=m.stratified,
+                            imp_sampling_percent=m.imp_sampling_percent, near_plane=m.near_plane)
+            for k, v in fresh.named_buffers():
+                getattr(m, k).copy_(v)
+    S.init_random_weights_(model, seed=0)
+    model.eval()
+    sd = {k: v.detach() for k, v in model.state_dict().items() if "raymarcher" not in k}
+    return model, sd, cfg, dev
+
+
+def _strict_fp32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@gpu
+@pytest.mark.parametrize("L", [64, 128])
+def test_sdxl_pose_on_batch3_vs_oracle(sdxl, L):
+    """One guided UNet evaluation exactly as the benchmark step runs it: CFG triple (uc, uc, c), stored
+    `references` + `choices` of 8 views, FeatureNeRF computed in this call; then the cached second call
+    at another sigma (sample.py:123-133: rendered_feat reused)."""
+    from custom_diffusion360_b200 import synthetic as S
+    model, sd, cfg, dev = sdxl
+    _strict_fp32()
+    nv = 8
+    refs = S.make_references(model, L, nv, dev, seed=L)
+    model.register_references(refs)
+    model.set_reference_choices(list(range(nv)))
+    model.clear_rendered_feat()
+    cond, uc = S.make_conditioning(cfg, 1, dev, seed=L)
+    g = torch.Generator(device=dev).manual_seed(30)
+    x = torch.randn(1, 4, L, L, device=dev, generator=g)
+    x3 = torch.cat([x] * 3)
+    ctx3 = torch.cat([uc["crossattn"], uc["crossattn"], cond["crossattn"]])
+    y3 = torch.cat([uc["vector"], uc["vector"], cond["vector"]])
+    t3 = torch.tensor([500, 500, 500], device=dev)
+    cams = S.lookat_cameras(nv, seed=3).to(dev)[None].expand(3, -1, -1).contiguous()
+    sd_o = dict(sd)
+    for name, r in refs.items():
+        sd_o[name + ".references"] = r
+    cache = {}
+    with torch.no_grad():
+        eps, fg, al, rgb = model(x3, timesteps=t3, context=ctx3, y=y3, pose=cams)
+        eps2, fg2, _, _ = model(0.9 * x3, timesteps=t3 - 100, context=ctx3, y=y3, pose=cams)
+        torch.cuda.synchronize()
+        with torch.device(dev):
+            ref, aux = O.unet_forward(sd_o, cfg, x3, t3, ctx3, y3, cams=cams, choices=list(range(nv)), cache=cache)
+            ref2, aux2 = O.unet_forward(sd_o, cfg, 0.9 * x3, t3 - 100, ctx3, y3, cams=cams,
+                                        choices=list(range(nv)), cache=cache)
+    model.clear_rendered_feat()
+    assert len(fg) == len(aux) == 12 and fg2 == [] and aux2 == []
+    tag = f"sdxl_pose_on_B3_L{L}"
+    for i, (f, a, r, (f_o, a_o, r_o)) in enumerate(zip(fg, al, rgb, aux)):
+        _check(f"{tag}/block{i}/fg", f, f_o.reshape(f.shape), 2e-2, 0.1)
+        _check(f"{tag}/block{i}/alphas", a, a_o.reshape(a.shape), 2e-2, 0.1)
+        _check(f"{tag}/block{i}/rgb", r, r_o.reshape(r.shape), 2e-2, 0.1)
+    _check(f"{tag}/eps", eps, ref, 6e-2, 0.25)
+    _check(f"{tag}/eps_cached_step", eps2, ref2, 6e-2, 0.25)
+
+
+@gpu
+def test_sdxl_fused_step_vs_oracle_step(sdxl):
+    """The benchmarked callable itself — FusedGuidedStep (c_in folded into the input load, CFG rows
+    replicated on load, UNet, c_out / CFG combine / Euler in one kernel, CUDA-graph replay) — against
+    the oracle's denoiser + guider + Euler update (oracle DiscreteDenoiserOracle / guider_combine,
+    sampling.py:96-110) over 3 sigmas of the 50-step schedule at 64x64 latents."""
+    from custom_diffusion360_b200 import synthetic as S
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.guiders import ScheduledCFGImgTextRef
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    model, sd, cfg, dev = sdxl
+    _strict_fp32()
+    L, nv, steps = 64, 8, 3
+    refs = S.make_references(model, L, nv, dev, seed=5)
+    model.register_references(refs)
+    model.set_reference_choices(list(range(nv)))
+    model.clear_rendered_feat()
+    cond, uc = S.make_conditioning(cfg, 1, dev, seed=5)
+    cams = S.lookat_cameras(nv, seed=3).to(dev)
+    den = DiscreteDenoiser(weighting_config={"target": P + "denoiser_weighting.EpsWeighting"},
+                           scaling_config={"target": P + "denoiser_scaling.EpsScaling"}, num_idx=1000,
+                           discretization_config={"target": P + "discretizer.LegacyDDPMDiscretization"})
+    guider = ScheduledCFGImgTextRef(scale=7.5, scale_im=3.5)
+    step = FusedGuidedStep(model, den, guider, cond, uc, pose=cams[None], n_img=1, latent_shape=(4, L, L))
+    sig = O.legacy_ddpm_sigmas(50)
+    g = torch.Generator(device=dev).manual_seed(30)
+    x0 = torch.randn(1, 4, L, L, device=dev, generator=g) * float((1.0 + sig[0] ** 2) ** 0.5)
+    x = x0.clone()
+    for i in range(steps):
+        step(x, float(sig[i]), float(sig[i + 1]))
+    torch.cuda.synchronize()
+    model.clear_rendered_feat()
+    # oracle: same loop, fp32 on the device
+    sd_o = dict(sd)
+    for name, r in refs.items():
+        sd_o[name + ".references"] = r
+    cams3 = cams[None].expand(3, -1, -1).contiguous()
+    cache = {}
+    xo = x0.clone()
+    with torch.no_grad(), torch.device(dev):
+        table = O.legacy_ddpm_sigmas(1000, do_append_zero=False, flip=True).to(dev)
+        for i in range(steps):
+            s, s_next = sig[i].to(dev), sig[i + 1].to(dev)
+            idx = (s - table).abs().argmin()
+            sq = table[idx]
+            c_in = 1.0 / (sq ** 2 + 1.0) ** 0.5
+            x3 = torch.cat([xo] * 3)
+            ctx3 = torch.cat([uc["crossattn"], uc["crossattn"], cond["crossattn"]])
+            y3 = torch.cat([uc["vector"], uc["vector"], cond["vector"]])
+            eps, _ = O.unet_forward(sd_o, cfg, x3 * c_in, idx.reshape(1).expand(3), ctx3, y3, cams=cams3,
+                                    choices=list(range(nv)), cache=cache)
+            den3 = eps * (-sq) + x3
+            d_u, d_ic, d_c = den3.chunk(3)
+            denoised = d_u + 7.5 * (d_c - d_ic) + 3.5 * (d_ic - d_u)       # guiders.py:111-114
+            xo = xo + (xo - denoised) / s * (s_next - s)                    # sampling.py:103-106
+    # 3 guided steps with CFG 7.5 amplify the per-evaluation error (~1.5e-2) by ~(1 + scale)
+    _check("sdxl_fused_step_3steps_L64", x, xo, 8e-2, 0.3)
+
+
+@gpu
+def test_sdxl_four_images_equal_four_single_runs(sdxl):
+    """BASELINE configs[2] per GPU: 4 images in one batch (UNet batch 12) produce, per image, the
+    trajectory of that image sampled alone — at SDXL width, through the engine's public `sample`."""
+    from custom_diffusion360_b200 import synthetic as S
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    model, sd, cfg, dev = sdxl
+    L, nv, steps, n_img = 64, 8, 2, 4
+    disc = {"target": P + "discretizer.LegacyDDPMDiscretization"}
+    with torch.device("meta"):
+        engine = DiffusionEngine(
+            network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+            denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+                "num_idx": 1000, "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+                "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"}, "discretization_config": disc}},
+            sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+                "num_steps": steps, "discretization_config": disc,
+                "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef",
+                                  "params": {"scale": 7.5, "scale_im": 3.5}}}})
+    engine.model.diffusion_model = model            # reuse the 2.6 B-parameter network of the fixture
+    engine.denoiser = engine.denoiser.to_empty(device=dev)
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.discretizer import LegacyDDPMDiscretization
+    engine.denoiser.sigmas = LegacyDDPMDiscretization()(1000, do_append_zero=False, flip=True).to(dev)
+    refs = S.make_references(model, L, nv, dev, seed=9)
+    model.register_references(refs)
+    engine.set_reference_choices(list(range(nv)))
+    cond, uc = S.make_conditioning(cfg, n_img, dev, seed=9)
+    g = torch.Generator(device=dev).manual_seed(31)
+    noise = torch.randn(n_img, 4, L, L, device=dev, generator=g)
+    poses = [S.lookat_cameras(nv, seed=3, target_azimuth=0.35 + 0.9 * i).to(dev) for i in range(n_img)]
+    sub = lambda d, i: {k: v[i:i + 1] for k, v in d.items()}
+    alone = []
+    for i in range(n_img):
+        alone.append(engine.sample(sub(cond, i), uc=sub(uc, i), batch_size=1, num_steps=steps,
+                                   noise=noise[i:i + 1].clone(), pose=[poses[i]] * 3))
+        engine.clear_rendered_feat()
+    both = engine.sample(cond, uc=uc, batch_size=n_img, num_steps=steps, noise=noise.clone(),
+                         pose=poses * 3)
+    engine.clear_rendered_feat()
+    for i in range(n_img):
+        _check(f"sdxl_n_img4_image{i}_vs_alone", both[i:i + 1], alone[i], 2e-2, 0.1)
