@@ -402,10 +402,18 @@ def train_measure(args, world, rank, local_rank, steps, warmup, per_kernel=True)
     # applies only its own gradient — measurement only, after the timed region)
     exposed_ms = allreduce_alone_ms = None
     if world > 1:
-        opt.comm_enabled = False
-        ms_nocomm, _ = timed(one_step, max(3, steps // 2))
-        opt.comm_enabled = True
-        exposed_ms = ms / steps - ms_nocomm / max(3, steps // 2)
+        from custom_diffusion360_b200.sgm.models.diffusion import GraphedTrainStep
+        k2 = max(3, steps // 2)
+        if args.no_graph:
+            nocomm = lambda i: (opt.zero_grad(), setattr(opt, "suspend_overlap", True), engine.training_step(fresh_batch(i)),
+                                opt.step(reduce=False), setattr(opt, "suspend_overlap", False))[2]
+        else:
+            gs0 = GraphedTrainStep(engine, opt, batch, comm="none")
+            nocomm = lambda i: gs0(batch)
+        nocomm(0)
+        ms_nocomm, _ = timed(nocomm, k2)
+        exposed_ms = ms / steps - ms_nocomm / k2
+
         def only_reduce(i):
             opt.reduce_all()
             opt.wait_reduce()

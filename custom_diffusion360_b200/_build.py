@@ -25,6 +25,7 @@ SOURCES = [
     "attention_bwd.cu",
     "train.cu",
     "vae.cu",
+    "conditioner.cu",
 ]
 
 NVCC_FLAGS = [

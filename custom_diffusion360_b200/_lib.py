@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcd360.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "cd360.h")
 
 OK = 0
-ACT_NONE, ACT_SILU = 0, 1
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_QUICK_GELU = 0, 1, 2, 3
 
 
 class Cd360Error(RuntimeError):
@@ -64,6 +64,9 @@ SIGNATURES = {
     "cd360_nerf_combine": (C.c_int, [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "cd360_nerf_volrender": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "cd360_nerf_mask_ref": (C.c_int, [_P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "cd360_embed_tokens": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "cd360_attention_causal_bf16": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P]),
+    "cd360_gather_rows_bf16_f32": (C.c_int, [_P, _L, _P, _P, _I, _I, _L, _P]),
     "cd360_cast_f32_to_bf16": (C.c_int, [_P, _P, _L, _P]),
     "cd360_cast_bf16_to_f32": (C.c_int, [_P, _P, _L, _P]),
     "cd360_splitk_slices": (C.c_int, [_I, _I, _I]),

@@ -406,6 +406,17 @@ __device__ __forceinline__ float erf_as_f(float x) {
 __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f));
 }
+// quick_gelu of the CLIP-L text tower (HF CLIPTextModel, hidden_act "quick_gelu"): x * sigmoid(1.702 x)
+__device__ __forceinline__ float quick_gelu_f(float x) { return x * rcp_approx_f(1.0f + __expf(-1.702f * x)); }
+// epilogue activation selected by CD360_ACT_* (include/cd360.h)
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case CD360_ACT_SILU: return silu_f(x);
+    case CD360_ACT_GELU: return gelu_erf_f(x);
+    case CD360_ACT_QUICK_GELU: return quick_gelu_f(x);
+    default: return x;
+  }
+}
 
 // host-side: launch with optional cluster dimension and programmatic dependent launch
 // (PDL on by default; CD360_PDL=0 disables it for A/B measurements)

@@ -517,9 +517,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
                 if (p.bias != nullptr) add_bias32_smem(vv, s_bias + (c0 + h) * 32);
                 if (rb != nullptr) load_bias32(vv, rb, col0, nvalid);
               }
-              if (p.act == CD360_ACT_SILU) {
+              if (p.act != CD360_ACT_NONE) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) vv[j] = silu_f(vv[j]);
+                for (int j = 0; j < 32; ++j) vv[j] = apply_act(vv[j], p.act);
               }
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[h * 32 + j] = vv[j];
@@ -655,9 +655,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
               if (p.bias != nullptr) add_bias32_smem(v, s_bias + c * 32);
               if (rb != nullptr) load_bias32(v, rb, col0, nvalid);
-              if (p.act == CD360_ACT_SILU) {
+              if (p.act != CD360_ACT_NONE) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
               }
               store_chunk32(v, p, row, col0, nvalid, ks);
             }

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SILU, Cd360Error, GemmArgs, check
+from ._lib import ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, Cd360Error, GemmArgs, check
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -474,6 +474,51 @@ def nerf_volrender(feats, raw, dists, b, hw, d, c):
                                    _ptr(alphas), _ptr(rgb), b, hw, d, c, _stream()),
           "cd360_nerf_volrender")
     return rendered, fg, alphas, rgb
+
+
+# ------------------------------------------------------------------------------------------------
+# text conditioner (csrc/conditioner.cu)
+# ------------------------------------------------------------------------------------------------
+@_op("conditioner")
+def embed_tokens(ids, tok_emb, pos_emb):
+    """ids int32 [B, ctx] (device); tok_emb fp32 [V, w]; pos_emb fp32 [ctx, w] -> bf16 [B*ctx, w]."""
+    lib = _lib.load()
+    _req(ids, torch.int32, "ids")
+    _req(tok_emb, f32, "tok_emb")
+    _req(pos_emb, f32, "pos_emb")
+    b, ctx = ids.shape
+    vocab, w = tok_emb.shape
+    if pos_emb.shape[0] < ctx:
+        raise Cd360Error(f"embed_tokens: {ctx} tokens per sequence but only {pos_emb.shape[0]} positions")
+    out = torch.empty((b * ctx, w), device=ids.device, dtype=bf16)
+    check(lib.cd360_embed_tokens(_ptr(ids), _ptr(tok_emb), _ptr(pos_emb), _ptr(out), b * ctx, ctx, w, vocab,
+                                 _stream()), "cd360_embed_tokens")
+    return out
+
+
+@_op("conditioner")
+def attention_causal(q, k, v, batch, heads, n, *, out=None):
+    """Causal softmax(QK^T/8)V, head dim 64; q/k/v 2-D bf16 views (row strides from the views)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((batch * n, heads * 64), device=q.device, dtype=bf16)
+    check(lib.cd360_attention_causal_bf16(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
+                                          _ptr(out), out.stride(0), batch, heads, n, _stream()),
+          "cd360_attention_causal_bf16")
+    return out
+
+
+@_op("conditioner")
+def gather_rows(x, idx):
+    """x bf16 [R, c] (row stride from the view), idx int32 [B] -> fp32 [B, c]."""
+    lib = _lib.load()
+    _req(idx, torch.int32, "idx")
+    if x.dtype != bf16 or not x.is_cuda:
+        raise Cd360Error("gather_rows: expected a CUDA bf16 tensor")
+    out = torch.empty((idx.shape[0], x.shape[1]), device=x.device, dtype=f32)
+    check(lib.cd360_gather_rows_bf16_f32(_ptr(x), x.stride(0), _ptr(idx), _ptr(out), idx.shape[0], x.shape[1],
+                                         x.shape[0], _stream()), "cd360_gather_rows_bf16_f32")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

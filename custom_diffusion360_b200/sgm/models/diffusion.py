@@ -3,9 +3,9 @@
 Kept: constructor config keys, `.model` (OpenAIWrapper) / `.model.diffusion_model`, `.denoiser`,
 `.sampler`, `sample(cond, uc, batch_size, num_steps, randn, shape, **kwargs)`,
 `clear_rendered_feat()`, trainable-parameter selection by name (`trainkeys`).
-Out of scope here: the text conditioner and the VAE first stage
-are not instantiated — callers feed `cond` / `uc` embeddings and receive latents; Lightning is
-not required (plain nn.Module).
+The text conditioner (sgm/modules/encoders/modules.py) and the decode-only first stage are built
+when their `target:` names this package; otherwise callers feed `cond` / `uc` embeddings and receive
+latents.  Lightning is not required (plain nn.Module).
 
 Training (`training_step`, reference :221-272): there is no autograd on this path — `forward`
 evaluates the loss through the taped UNet forward and immediately runs the explicit backward
@@ -82,7 +82,12 @@ class DiffusionEngine(nn.Module):
         self.scheduler_config = scheduler_config
         self.learning_rate = 1.0e-4   # base_learning_rate of the shipped yaml; main.py:1019-1050 overrides
         self.global_step = 0
+        # the conditioner of THIS package (text towers on the CUDA kernels) is built when
+        # its target names it; with the reference's own `sgm.modules.GeneralConditioner` target the caller
+        # keeps the reference object and assigns it to `.conditioner`
         self.conditioner = None
+        if conditioner_config is not None and str(conditioner_config.get("target", "")).startswith("custom_diffusion360_b200."):
+            self.conditioner = instantiate_from_config(conditioner_config)
         self.first_stage_model = None
         # trainable set by parameter name (reference :119-147)
         for name, p in self.model.diffusion_model.named_parameters():
@@ -254,7 +259,13 @@ class GraphedTrainStep:
     the previous optimiser update and the eager step shares the same buffers; the nviews bias is read
     from device memory for the same reason."""
 
-    def __init__(self, engine: "DiffusionEngine", opt, batch: dict):
+    def __init__(self, engine: "DiffusionEngine", opt, batch: dict, comm: str = "graph"):
+        """comm (data-parallel runs only): "graph" — the per-pose-block bucket all-reduces (NCCL) are
+        CAPTURED inside the step's graph on the communication stream, each forked off the backward walk
+        the moment that block's gradients are written, so the exchange overlaps the rest of the backward
+        and a replay ends with reduced gradients; "after" — no collective inside the graph, all buckets
+        are reduced after the replay (round-1 behaviour); "none" — no exchange at all (measurement of
+        the exposed communication time only)."""
         from ..modules.attention import invalidate_all_packed
         from ..modules.utils_cameraray import pack_pose
         self.engine, self.opt = engine, opt
@@ -287,14 +298,22 @@ class GraphedTrainStep:
                                "leaves the fg / bg terms out of the total (diffusion.py:225)")
         self._draw()
         self.opt.zero_grad()
-        # no collectives inside the captured step: the bucket all-reduces run after each replay (opt.step)
-        self.opt.suspend_overlap = True
+        assert comm in ("graph", "after", "none")
+        world = self.opt._world()
+        self.comm = comm if world > 1 else "none"
+        self.comm_in_graph = self.comm == "graph"
+        # "after" / "none": no collectives inside the captured step (the per-block callbacks of the
+        # backward walk do nothing); "graph": they fire during capture and are recorded
+        self.opt.suspend_overlap = not self.comm_in_graph
         engine.shared_step(self._batch(), sync=False)              # warm-up: builds every frozen pack
+        self.opt.wait_reduce()
         invalidate_all_packed(unet, only_trainable=True)           # ... the trainable ones are refreshed IN PLACE inside the graph
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.terms = engine.shared_step(self._batch(), sync=False)
+            self.opt.wait_reduce()                                 # join the communication stream into the capture
+        self.opt.suspend_overlap = True                            # nothing eager may start a second exchange
 
     def _batch(self):
         bt = dict(self.static)
@@ -344,5 +363,5 @@ class GraphedTrainStep:
         self._draw()
         self.graph.replay()
         if step_optimizer:
-            self.opt.step()
+            self.opt.step(reduce=self.comm == "after")
         return self.loss

@@ -125,10 +125,14 @@ class PoseAdamW:
             self.reduce_bucket(i, force=True)
 
     def wait_reduce(self):
+        """Make the current stream wait for every exchange started since the last call.  (Also valid
+        during CUDA-graph capture: the waits join the communication stream back into the capture;
+        with nothing pending no cross-stream dependency is created.)"""
+        had = bool(self._pending)
         for w in self._pending:
             w.wait()
         self._pending = []
-        if self._comm_stream is not None:
+        if had and self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
 
     # ---- optimiser -------------------------------------------------------------------------------

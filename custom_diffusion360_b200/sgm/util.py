@@ -68,6 +68,26 @@ def load_checkpoints(engine, base_sd: dict, delta_sd: dict = None, verbose: bool
     if refs:
         dev = next(unet.parameters()).device
         unet.register_references({k: v.to(dev) for k, v in refs.items()})
+    cond = getattr(engine, "conditioner", None)
+    if cond is not None and hasattr(cond, "embedders"):
+        # conditioner.embedders.{0,1}.*: the base checkpoint's token embeddings have one row less than a
+        # tower built with `modifier_token` — the reference concatenates the delta checkpoint's `embed`
+        # rows behind them (sgm/util.py:216-228)
+        csd = {k[len("conditioner."):]: v for k, v in base_sd.items() if k.startswith("conditioner.")}
+        own = cond.state_dict()
+        for k in list(csd):
+            if k in own and k.endswith("token_embedding.weight") and csd[k].shape[0] < own[k].shape[0]:
+                full = own[k].clone()
+                full[: csd[k].shape[0]] = csd[k]
+                csd[k] = full
+        cm, cu = cond.load_state_dict(csd, strict=False)
+        for m_ in cond.modules():
+            if hasattr(m_, "invalidate_packed"):
+                m_.invalidate_packed()
+        if delta_sd is not None and "embed" in delta_sd and hasattr(cond, "load_modifier_token_rows"):
+            cond.load_modifier_token_rows(delta_sd["embed"])
+        missing = missing + ["conditioner." + k for k in cm if not k.endswith("logit_scale")]
+        unexpected = unexpected + ["conditioner." + k for k in cu if "position_ids" not in k and "attn_mask" not in k]
     if verbose:
         print(f"missing: {missing}\nunexpected: {unexpected}")
     return missing, unexpected

@@ -33,7 +33,9 @@ enum {
   CD360_ERR_NULL = -5         /* required pointer is NULL */
 };
 
-enum { CD360_ACT_NONE = 0, CD360_ACT_SILU = 1 };
+/* epilogue activations: SiLU (UNet), exact GELU (OpenCLIP text tower MLP), quick GELU x*sigmoid(1.702x)
+ * (CLIP-L text tower MLP; sgm/modules/encoders/modules.py:377-517,622-772) */
+enum { CD360_ACT_NONE = 0, CD360_ACT_SILU = 1, CD360_ACT_GELU = 2, CD360_ACT_QUICK_GELU = 3 };
 
 /* Library / build info: returns the ABI version (bumped on any signature change). */
 int cd360_abi_version(void);
@@ -250,6 +252,29 @@ int cd360_nerf_volrender(const void* feats, const float* raw, const float* dists
  * x / out bf16 [bn*res*res, c] (may alias), mask fp32 [bn, mh, mw]. */
 int cd360_nerf_mask_ref(const void* x, const float* mask, void* out, int64_t bn, int32_t res,
                         int32_t mh, int32_t mw, int32_t c, cd360_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Text conditioner: FrozenCLIPEmbedder (HF CLIPTextModel, CLIP-L) and
+ * FrozenOpenCLIPEmbedder (open_clip ViT-bigG-14 text tower), sgm/modules/encoders/modules.py:377-517,
+ * 622-772.  Projections / MLPs use cd360_gemm_bf16 (CD360_ACT_QUICK_GELU / CD360_ACT_GELU epilogues),
+ * LayerNorm cd360_layernorm_bf16, pooled projection cd360_small_linear.
+ * --------------------------------------------------------------------------------------------- */
+/* Token + positional embedding (modules.py:498-501 `text_model.embeddings(input_ids=tokens)`;
+ * :716-728 `token_embedding(text) + positional_embedding`): out[b*ctx + t, :] = bf16(tok_emb[ids[b*ctx+t], :]
+ * + pos_emb[t, :]).  ids int32 [rows], tok_emb fp32 [vocab, w] (the trainable `<new1>` row stays an fp32
+ * master), pos_emb fp32 [ctx, w], out bf16 [rows, w]; rows % ctx == 0, w % 4 == 0. */
+int cd360_embed_tokens(const int32_t* ids, const float* tok_emb, const float* pos_emb, void* out,
+                       int32_t rows, int32_t ctx, int32_t w, int32_t vocab, cd360_stream_t stream);
+/* Causal self-attention of the text towers (additive -inf mask above the diagonal, modules.py:447-453;
+ * open_clip `attn_mask`), head dim 64, scale 1/8, n <= 128 tokens per sequence.  q/k/v/out are bf16
+ * row-major views [batch*n, >= heads*64] with row strides ld* (slices of a fused QKV buffer work). */
+int cd360_attention_causal_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                int64_t ldv, void* out, int64_t ldo, int32_t batch, int32_t heads,
+                                int32_t n, cd360_stream_t stream);
+/* Row gather for the end-of-text pooling (modules.py:737-743 `x[arange(B), text.argmax(-1)]`):
+ * out[r, :] = fp32(x[idx[r], :]); x bf16 [src_rows, c] row stride ldx, idx int32 [nrows]. */
+int cd360_gather_rows_bf16_f32(const void* x, int64_t ldx, const int32_t* idx, float* out, int32_t nrows,
+                               int32_t c, int64_t src_rows, cd360_stream_t stream);
 
 /* Utility: fp32 -> bf16 and bf16 -> fp32 contiguous conversion (weight prepack, I/O). */
 int cd360_cast_f32_to_bf16(const float* x, void* out, int64_t n, cd360_stream_t stream);

@@ -294,3 +294,57 @@ def test_engine_rejects_unbuilt_training_options():
                 {"scheduler_config": {"target": "x"}}, {"use_ema": True}):
         with pytest.raises(NotImplementedError):
             DiffusionEngine(**{**base, **bad})
+
+
+def test_product_general_conditioner_glue_vs_reference_golden():
+    """GeneralConditioner of the PRODUCT (sgm/modules/encoders/modules.py) — the input_keys pairing,
+    chunk(2) into main / reference halves, feature concatenation, batch-axis append and both force_*
+    switches — against outputs of the reference's own GeneralConditioner on the same toy embedders
+    (tests/golden/conditioner_golden.pt, made by tests/golden/make_conditioner_golden.py).  The toy text
+    embedders are plain torch; ConcatTimestepEmbedderND's kernel is stood in for by the oracle formula."""
+    import os
+    import sys
+    import types
+    from oracle import conditioner_oracle as C
+    from tests import test_oracle_conditioner as T
+    from custom_diffusion360_b200.sgm.modules.encoders import modules as M
+
+    toy = types.ModuleType("cd360_toy_product_embedders")
+
+    class ToyText(M.AbstractEmbModel):
+        def __init__(self, dim, mul, pooled_dim=0):
+            super().__init__()
+            self.dim, self.mul, self.pooled_dim = dim, mul, pooled_dim
+
+        def forward(self, x):
+            z = T.toy_text(x, self.dim, self.mul)
+            return (z, T.toy_text(x, self.pooled_dim, 0.25)[:, 0]) if self.pooled_dim else z
+
+    class ToySize(M.ConcatTimestepEmbedderND):
+        def forward(self, x):
+            return C.concat_timestep_embedder_nd(x, self.outdim)
+
+    toy.ToyText, toy.ToySize = ToyText, ToySize
+    sys.modules["cd360_toy_product_embedders"] = toy
+    size = {"target": "cd360_toy_product_embedders.ToySize", "params": {"outdim": 8}}
+    cond = M.GeneralConditioner([
+        {"is_trainable": False, "input_keys": "txt,txt_ref", "target": "cd360_toy_product_embedders.ToyText",
+         "params": {"dim": 6, "mul": 1.0}},
+        {"is_trainable": False, "input_keys": "txt,txt_ref", "target": "cd360_toy_product_embedders.ToyText",
+         "params": {"dim": 10, "mul": 0.5, "pooled_dim": 7}},
+        dict(size, is_trainable=False, input_keys="original_size_as_tuple,original_size_as_tuple_ref"),
+        dict(size, is_trainable=False, input_keys="crop_coords_top_left,crop_coords_top_left_ref")])
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "conditioner_golden.pt"), map_location="cpu")
+    batch = T.toy_batch()
+    out = cond(dict(batch), force_ref_zero_embeddings=False)
+    assert torch.equal(out["crossattn"], gold["toy_crossattn"]) and torch.equal(out["vector"], gold["toy_vector"])
+    emb = T.oracle_embedders()
+    keys = [e["input_keys"] for e in emb]
+    for force_ref in (False, True):
+        c, uc = cond.get_unconditional_conditioning(dict(batch), force_uc_zero_embeddings=keys,
+                                                    force_ref_zero_embeddings=force_ref)
+        oc, ouc = C.get_unconditional_conditioning(emb, batch, None, keys, force_ref)
+        for k in ("crossattn", "vector"):
+            assert torch.equal(c[k], oc[k]) and torch.equal(uc[k], ouc[k]), (k, force_ref)
+    part = cond(dict(batch), [["txt", "txt_ref"]], True)
+    assert float(part["crossattn"].abs().max()) == 0.0 and float(part["vector"][:, 7:].abs().max()) > 0.0
