@@ -14,8 +14,8 @@ def _args(**kw):
 
 
 def test_reference_arm_line(monkeypatch, capsys):
-    fake = {"value": 0.05, "unit": bench.UNIT, "cores": 16, "kind": "port", "sample": "oracle forward of 1 of the 3 CFG rows"}
-    monkeypatch.setattr(bench, "cpu_reference", lambda steps, warmup, budget_s, latent: (dict(fake), 20.0, 1))
+    fake = {"value": 0.05, "unit": bench.UNIT, "cores": 16, "kind": "port", "sample": "oracle batch-3 guided step"}
+    monkeypatch.setattr(bench, "cpu_reference", lambda steps, warmup, latent=128: (dict(fake), 20.0, 1))
     bench.run_reference(_args(), rank=0)
     line = json.loads(capsys.readouterr().out.strip())
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
