@@ -84,6 +84,7 @@ SIGNATURES = {
                                                 _I, _I, _F, _I, _P]),
     "cd360_geglu_bwd_bf16": (C.c_int, [_P, _P, _P, _L, _I, _I, _P]),
     "cd360_add_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
+    "cd360_silu_bwd_f32": (C.c_int, [_P, _P, _P, _L, _P]),
     "cd360_transpose_to_bf16": (C.c_int, [_P, _I, _L, _P, _L, _I, _I, _P]),
     "cd360_colsum_bf16": (C.c_int, [_P, _L, _P, _L, _I, _P]),
     "cd360_col2im3x3_s2_bf16": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),

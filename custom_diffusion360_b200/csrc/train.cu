@@ -303,6 +303,20 @@ add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __rest
   }
 }
 
+// out = dy * silu'(pre), fp32 (backward of the SiLU inside time_embed / label_emb / emb_layers,
+// openaimodel.py:679-713, 270-276): silu'(x) = s (1 + x (1 - s)), s = sigmoid(x)
+__global__ void __launch_bounds__(256)
+silu_bwd_f32_kernel(const float* __restrict__ pre, const float* __restrict__ dy, float* __restrict__ out,
+                    long long n) {
+  pdl_wait();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = pre[i];
+    const float s = 1.0f / (1.0f + __expf(-x));
+    out[i] = dy[i] * s * (1.0f + x * (1.0f - s));
+  }
+}
+
 // in [rows, cols] (bf16 or fp32, row stride ld_in) -> out bf16 [cols, ld_out], out[c][r] = in[r][c];
 // columns r in [rows, ld_out) are zero filled (the transposed operand is the K-major input of a
 // weight-gradient GEMM whose K = rows must be a multiple of 8).
@@ -984,6 +998,16 @@ extern "C" int cd360_add_bf16(const void* a, const void* b, void* out, int64_t n
   if (CD360_MISALIGNED(a) || CD360_MISALIGNED(b) || CD360_MISALIGNED(out)) return CD360_ERR_ALIGN;
   launch_ex(add_bf16_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_),
             1, CD360_BF(a), CD360_BF(b), CD360_BFW(out), static_cast<long long>(n / 8));
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_silu_bwd_f32(const float* pre, const float* dy, float* out, int64_t n,
+                                  cd360_stream_t stream_) {
+  if (!pre || !dy || !out) return CD360_ERR_NULL;
+  if (n <= 0) return CD360_ERR_SHAPE;
+  launch_ex(silu_bwd_f32_kernel, dim3(grid_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream_), 1,
+            pre, dy, out, static_cast<long long>(n));
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }

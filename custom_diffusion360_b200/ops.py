@@ -599,6 +599,18 @@ def add_bf16(a, b, *, out=None):
     return out
 
 
+@_op("other")
+def silu_bwd(pre, dy, *, out=None):
+    """out = dy * silu'(pre), fp32 (same shape)."""
+    lib = _lib.load()
+    _req(pre, f32, "pre")
+    _req(dy, f32, "dy")
+    if out is None:
+        out = torch.empty_like(pre)
+    check(lib.cd360_silu_bwd_f32(_ptr(pre), _ptr(dy), _ptr(out), pre.numel(), _stream()), "cd360_silu_bwd_f32")
+    return out
+
+
 @_op("transpose")
 def transpose_to_bf16(x, *, ld_out=None):
     """x [rows, cols] bf16 / fp32 (row stride from the view) -> bf16 [cols, ld_out >= rows]."""

@@ -89,6 +89,7 @@ class DiffusionEngine(nn.Module):
         if conditioner_config is not None and str(conditioner_config.get("target", "")).startswith("custom_diffusion360_b200."):
             self.conditioner = instantiate_from_config(conditioner_config)
         self.first_stage_model = None
+        self.last_cond_grads = None
         # trainable set by parameter name (reference :119-147)
         for name, p in self.model.diffusion_model.named_parameters():
             p.requires_grad = "pose" in name
@@ -199,10 +200,31 @@ class DiffusionEngine(nn.Module):
             terms["loss_rgb"] = lr_
             w_rgb = gate * self.loss_rgb_lambda * drop / (k * dsum)
         if backward:
-            self.loss_fn.backward(1.0 / b, w_fg, w_bg, w_rgb)
+            self._route_cond_grads(self.loss_fn.backward(1.0 / b, w_fg, w_bg, w_rgb), self.loss_fn.last_cond)
         if sync:
             terms = {k_: float(v) for k_, v in terms.items()}
         return loss_mean, terms
+
+    def _route_cond_grads(self, grads, cond):
+        """Conditioning gradients of the step: `self.last_cond_grads` = {"crossattn": [b + b*n, 77, ctx],
+        "vector": [b + b*n, adm]} fp32, shaped like the conditioner's outputs (rows of the reference
+        views are zero: that stream is no_grad in the reference).  When those outputs came from a
+        torch-autograd conditioner — the reference's GeneralConditioner with its trainable `<new1>` token
+        rows (reference :343-356, main.py:627-643) — the gradients are pushed into that graph, which is
+        what the reference's `loss.backward()` does for the text encoders."""
+        self.last_cond_grads = None
+        if grads is None:
+            return
+        full = {}
+        for k, g in grads.items():
+            ref = cond[k]
+            out = torch.zeros(ref.shape, device=g.device, dtype=torch.float32)
+            out[: g.shape[0]] = g.reshape(g.shape[0], *ref.shape[1:])
+            full[k] = out
+        self.last_cond_grads = full
+        live = [(cond[k], full[k]) for k in full if cond[k].requires_grad]
+        if live and not torch.cuda.is_current_stream_capturing():
+            torch.autograd.backward([t for t, _ in live], [g.to(t.dtype) for t, g in live])
 
     def shared_step(self, batch, backward: bool = True, sync: bool = True):
         x, xr, pose, mask, mask_ref, opacity, drop_im = self.get_input(batch)
@@ -313,6 +335,9 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.terms = engine.shared_step(self._batch(), sync=False)
             self.opt.wait_reduce()                                 # join the communication stream into the capture
+        # conditioning gradients of the replayed step (static buffers of the graph's pool, rewritten by
+        # every replay): {"crossattn", "vector"} shaped like batch["cond"], or None when switched off
+        self.cond_grads = engine.last_cond_grads
         self.opt.suspend_overlap = True                            # nothing eager may start a second exchange
 
     def _batch(self):

@@ -64,6 +64,7 @@ class StandardDiffusionLossImgRef(nn.Module):
             if input_ref is not None:
                 nr = rnd["noise_ref"].to(dev) if "noise_ref" in rnd else torch.randn_like(input_ref)
                 input_ref = input_ref + nr * append_dims(sigmas_ref, input_ref.ndim)   # loss.py:163-170
+        self.last_cond = cond
         eps_tok, aux, tape, sigma_q = denoiser.train_forward(
             network, noised_input, sigmas, cond, sigmas_ref=sigmas_ref, input_ref=input_ref, pose=pose,
             noise_ref2=rnd.get("noise_ref2"), jitter=rnd.get("jitter"), mask_ref=mask_ref)
@@ -133,5 +134,6 @@ class StandardDiffusionLossImgRef(nn.Module):
                                                       tg.reshape(b, 3, -1) if use_rgb else None, st.mask_sum,
                                                       wf, wb, wr)
                 daux_of[id(blk)] = (dfg, dal, drgb)
-        st.network.diffusion_model.backward(st.tape, deps, daux_of)
+        cond_grads = st.network.diffusion_model.backward(st.tape, deps, daux_of)
         self.last = None  # free the tape
+        return cond_grads

@@ -463,7 +463,8 @@ class UNetModel(nn.Module, _Packed):
                 t = caps[name]   # stays referenced (tape / caps) until after the join below
                 m.__dict__["_live_ctxref"] = (t.reshape(-1, t.shape[-1]), n, m.__dict__.pop("_capture_ev", None))
                 m._ctxref_cache = None
-            out = train_path.unet_forward(self, x, timesteps, context[:b], y[:b], pose, in_scale, jitter)
+            out = train_path.unet_forward(self, x, timesteps, context[:b], y[:b], pose, in_scale, jitter,
+                                          cond_grad=bool(self.__dict__.get("cond_grad", True)))
             self.__dict__["_packs_warm"] = True
             return out
         finally:
@@ -478,9 +479,12 @@ class UNetModel(nn.Module, _Packed):
 
     def backward(self, tape, deps, daux_of=None):
         """Gradients of the pose weights (into `.grad`, fp32) from deps = dL/d(eps tokens) bf16
-        [b*L*L, 64] (columns >= 4 zero) and daux_of = {id(pose block): (dfg, dalphas, drgb)}."""
+        [b*L*L, 64] (columns >= 4 zero) and daux_of = {id(pose block): (dfg, dalphas, drgb)}.
+        Returns the conditioning gradients {"crossattn": fp32 [b, 77, ctx], "vector": fp32 [b, adm]} of
+        the b TARGET rows (the reference-view rows get none: that stream is no_grad in the reference,
+        openaimodel.py:95-108) unless `self.cond_grad` was set False before forward_train."""
         from .. import train_path
-        train_path.unet_backward(self, tape, deps, daux_of or {})
+        return train_path.unet_backward(self, tape, deps, daux_of or {})
 
     def forward_tokens(self, x, timesteps, context, y, pose=None, in_scale=None, batch=None):
         """Same as forward but returns eps in token layout: fp32 [B*L*L, out_channels].

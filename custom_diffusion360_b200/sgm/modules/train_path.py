@@ -14,9 +14,20 @@ reverse and launches, per layer, the gradient kernels:
   * attention, LayerNorm, GroupNorm+SiLU, GEGLU, resampling, FeatureNeRF gather / view-softmax /
     volume rendering: the dedicated backward kernels of csrc/train.cu and csrc/attention_bwd.cu;
   * dW of the (few, small) trainable Linears = GEMMs over transposed operands, fp32 out.
-The walk stops at the first pose block in forward order: nothing upstream of it is trainable.
 The reference-image stream is `no_grad` in the reference (attention.py:851-868) and stays a plain
 forward here (`UNetModel.capture_references`).
+
+Conditioning gradients (`cond_grad=True`, the default of the engine): the shipped config also trains
+the `<new1>` rows of both text encoders' token tables (sgm/models/diffusion.py:343-356,
+main.py:627-643), i.e. the reference's autograd carries dL/d(crossattn) and dL/d(vector) back into
+the conditioner.  The walk then (a) also asks the attention backward of every attn2 — the 70
+transformer blocks and the 12 `reference_attn` calls that reuse them — for dK / dV, collected in
+one [b*77, sum(2*inner)] buffer that mirrors the fused K|V projection and turned into dL/d(context)
+by ONE GEMM against the transposed K|V weights; (b) sums, per ResBlock, the gradient of
+`emb_layers` over the pixels and walks it back through emb_layers / label_emb (SiLU backward
+kernel + the small-linear kernel over transposed packs) to dL/d(vector); (c) does not stop at the
+first pose block (every ResBlock upstream still feeds (b)).  Without it the walk stops at the first
+pose block in forward order: nothing upstream of it is trainable.
 """
 from __future__ import annotations
 
@@ -76,6 +87,10 @@ def bwd_pack(m) -> dict:
         p["w"] = pack_conv3x3_bwd(m.conv.weight.detach())
     elif isinstance(m, U.UNetModel):
         p["cout"] = pack_conv3x3_bwd(m.out[2].weight.detach(), cout_pad=64)
+        if m.__dict__.get("_cond_grad"):   # conditioning gradients: dX packs of the K|V and embedding projections
+            fp = m.packed()
+            p.update(kvw_t=transposed(fp["kvw"]), embw_t=transposed(fp["embw"]), le2w_t=transposed(fp["le2w"]),
+                     le0w_t=transposed(fp["le0w"]))
     else:
         raise TypeError(type(m))
     m.__dict__["_bwdpk"] = p
@@ -201,7 +216,14 @@ def nerf_backward(block: BasicTransformerBlock, sv, d_rendered, daux):
     # feats2 = final + to_out(attn(to_q(LN2 final), K, V))   (the block's own norm2 / attn2, frozen)
     da = ops.gemm(dfeats2, bp["wo2_t"])
     dq = torch.empty_like(sv.q)
-    ops.attention_bwd(sv.q, sv.k, sv.v, sv.att, da, b, a2.heads, hw * d, sv.nkv, dq=dq)
+    dkv = _BWD.get("dkv_nerf")          # conditioning gradients: this attn2 call also reads the text K / V
+    if dkv is None:
+        ops.attention_bwd(sv.q, sv.k, sv.v, sv.att, da, b, a2.heads, hw * d, sv.nkv, dq=dq)
+    else:
+        off, _ = block.__dict__["_kv_slice"]
+        inner = a2.heads * a2.dim_head
+        ops.attention_bwd(sv.q, sv.k, sv.v, sv.att, da, b, a2.heads, hw * d, sv.nkv, dq=dq,
+                          dk=dkv[:, off:off + inner], dv=dkv[:, off + inner:off + 2 * inner])
     dfn = ops.gemm(dq, bp["wq2_t"])
     dfinal = ops.layernorm_bwd(sv.final, bp["g2"], dfn, add=dfeats2, eps=block.norm2.eps)
     # raw = final Wd^T
@@ -303,11 +325,18 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
         if stop_here:
             return None
         g = ops.gemm(g, pp["wp_x_t"])
-    # ---- text cross-attention (K / V: projections of the constant context, no gradient)
+    # ---- text cross-attention (K / V: projections of the context; their gradient only when the
+    #      conditioning gradients are asked for)
     a1, a2 = block.attn1, block.attn2
     da = ops.gemm(g, bp["wo2_t"])
     dq = torch.empty_like(sv.q2)
-    ops.attention_bwd(sv.q2, sv.k2, sv.v2, sv.att2, da, sv.batch, a2.heads, sv.n, sv.nctx, dq=dq)
+    dkv = _BWD.get("dkv")
+    if dkv is None:
+        ops.attention_bwd(sv.q2, sv.k2, sv.v2, sv.att2, da, sv.batch, a2.heads, sv.n, sv.nctx, dq=dq)
+    else:
+        off, _ = block.__dict__["_kv_slice"]
+        ops.attention_bwd(sv.q2, sv.k2, sv.v2, sv.att2, da, sv.batch, a2.heads, sv.n, sv.nctx, dq=dq,
+                          dk=dkv[:, off:off + sv.inner], dv=dkv[:, off + sv.inner:off + 2 * sv.inner])
     g = ops.layernorm_bwd(sv.x1, bp["g2"], ops.gemm(dq, bp["wq2_t"]), add=g, eps=block.norm2.eps)
     # ---- self-attention
     inner = sv.inner
@@ -352,7 +381,7 @@ def st_backward(st: SpatialTransformer, sv, g, daux_of, first_pose_block):
     return dx
 
 
-def res_forward(rb, x, batch, h, w, emb_out, skip=None):
+def res_forward(rb, x, batch, h, w, emb_out, skip=None, emb_slice=None):
     p = rb.packed()
     hw = h * w
     hn = ops.groupnorm(x, p["g1"], p["b1"], batch, hw, x1=skip, eps=rb.in_layers[0].eps, silu=True)
@@ -360,7 +389,7 @@ def res_forward(rb, x, batch, h, w, emb_out, skip=None):
     hn2 = ops.groupnorm(h1, p["g2"], p["b2"], batch, hw, eps=rb.out_layers[0].eps, silu=True)
     xs = ops.gemm(x, p["ws"], bias=p["bs"], a1=skip) if "ws" in p else x
     out = ops.conv3x3(hn2, p["w2"], batch, h, w, bias=p["cb2"], residual=xs)
-    return out, NS(x=x, skip=skip, h1=h1, batch=batch, h=h, w=w)
+    return out, NS(x=x, skip=skip, h1=h1, batch=batch, h=h, w=w, emb_slice=emb_slice)
 
 
 def res_backward(rb, sv, g):
@@ -371,6 +400,11 @@ def res_backward(rb, sv, g):
     hw = h * w
     dhn2 = ops.conv3x3(g, bp["w2"], b, h, w)
     dh1, _ = ops.groupnorm_bwd(sv.h1, p["g2"], p["b2"], dhn2, b, hw, eps=rb.out_layers[0].eps, silu=True)
+    demb = _BWD.get("demb")
+    if demb is not None:     # h1 = conv(...) + emb_out[:, :, None, None]: per-image sum over the pixels
+        off, n = sv.emb_slice
+        for i in range(b):
+            ops.colsum(dh1[i * hw:(i + 1) * hw], out=demb[i, off:off + n])
     dhn = ops.conv3x3(dh1, bp["w1"], b, h, w)
     c0 = sv.x.shape[1]
     if "ws_t" in bp:
@@ -399,7 +433,7 @@ def up_backward(layer, g, batch, h, w):
 # ------------------------------------------------------------------------------------------------
 # UNet
 # ------------------------------------------------------------------------------------------------
-def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=None):
+def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=None, cond_grad=False):
     """Taped main-stream forward (pose blocks read the live reference-stream tokens installed by the
     caller).  Returns (eps fp32 tokens [B*L*L, 4], aux list [(block, (fg, alphas, rgb))], tape).
     Tape entries, in forward order: ("layer", kind, module, saved), ("push", i) = h became skip
@@ -415,8 +449,10 @@ def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=Non
     t_emb = ops.timestep_embedding(timesteps.to(device=dev, dtype=f32).contiguous(), unet.model_channels)
     e1 = ops.small_linear(t_emb, p["te0w"], p["te0b"], act_out=ACT_SILU)
     emb = ops.small_linear(e1, p["te2w"], p["te2b"])
-    l1 = ops.small_linear(y.float().contiguous(), p["le0w"], p["le0b"], act_out=ACT_SILU)
-    emb = ops.small_linear(l1, p["le2w"], p["le2b"], add=emb)
+    # (label_emb's SiLU is applied on the NEXT layer's input so that its pre-activation is kept for the
+    # backward to dL/d(vector); same arithmetic as act_out=SILU here)
+    l1p = ops.small_linear(y.float().contiguous(), p["le0w"], p["le0b"])
+    emb = ops.small_linear(l1p, p["le2w"], p["le2b"], add=emb, act_in=ACT_SILU)
     emb_all = ops.small_linear(emb, p["embw"], p["embb"], act_in=ACT_SILU)
     ctx_tok, nctx = to_tokens(context), context.shape[1]
     cams = pack_pose(pose, dev) if pose is not None else None
@@ -429,7 +465,7 @@ def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=Non
         for layer in layers:
             if isinstance(layer, U.ResBlock):
                 off, n = p["emb_off"][id(layer)]
-                h, sv = res_forward(layer, h, b, hh, ww, emb_all[:, off:off + n], skip=skip)
+                h, sv = res_forward(layer, h, b, hh, ww, emb_all[:, off:off + n], skip=skip, emb_slice=(off, n))
                 skip = None
                 tape.append(("layer", "res", layer, sv))
             elif isinstance(layer, SpatialTransformer):
@@ -491,7 +527,9 @@ def unet_forward(unet, x, timesteps, context, y, pose, in_scale=None, jitter=Non
         if nerf_stream is not None:
             torch.cuda.current_stream(dev).wait_stream(nerf_stream)
         _FWD.clear()
-    return eps, aux, NS(tape=tape, h_last=h, batch=b, hh=hh, ww=ww)
+    cond = NS(l1p=l1p, emb=emb, nctx=nctx, kv_width=kv_all.shape[1], emb_width=emb_all.shape[1],
+              ctx_dim=ctx_tok.shape[1]) if cond_grad else None
+    return eps, aux, NS(tape=tape, h_last=h, batch=b, hh=hh, ww=ww, cond=cond)
 
 
 def pose_blocks_in_order(unet) -> List[BasicTransformerBlock]:
@@ -510,9 +548,22 @@ def first_pose_block(unet) -> Optional[BasicTransformerBlock]:
 def unet_backward(unet, fw, deps, daux_of: Dict[int, tuple]):
     """deps: bf16 [B*L*L, 64] gradient of the loss w.r.t. the UNet output tokens (columns >= 4
     zero); daux_of: {id(pose block): (dfg, dalphas, drgb)}.  Writes the gradients of every pose
-    parameter into its `.grad` (fp32)."""
+    parameter into its `.grad` (fp32).  When the forward was taped with cond_grad=True, returns
+    {"crossattn": fp32 [b, nctx, ctx_dim], "vector": fp32 [b, adm]} (else None)."""
     from .diffusionmodules.openaimodel import OVERLAP_REF_STREAM
     side = None
+    cg = fw.cond
+    dev = deps.device
+    if cg is not None:
+        unet.__dict__["_cond_grad"] = True
+        b = fw.batch
+        # every transformer block writes its own K|V column slice (all 70 are visited); the FeatureNeRF
+        # branch runs on the side stream and accumulates into a buffer of its own, added after the join
+        _BWD["dkv"] = torch.empty(b * cg.nctx, cg.kv_width, device=dev, dtype=bf16)
+        _BWD["dkv_nerf"] = torch.zeros(b * cg.nctx, cg.kv_width, device=dev, dtype=bf16)
+        _BWD["demb"] = torch.zeros(b, cg.emb_width, device=dev, dtype=f32)
+    else:
+        _BWD["dkv"] = _BWD["dkv_nerf"] = _BWD["demb"] = None
     if deps.is_cuda and OVERLAP_REF_STREAM and unet.__dict__.get("_packs_warm") and unet.__dict__.get("_bwd_warm"):
         side = unet.__dict__.get("_side_stream")
         if side is None or side.device != deps.device:
@@ -526,13 +577,36 @@ def unet_backward(unet, fw, deps, daux_of: Dict[int, tuple]):
         if side is not None:
             torch.cuda.current_stream(deps.device).wait_stream(side)
         _BWD["side"], _BWD["keep"] = None, []
+        dkv, dkv_nerf, demb = _BWD.get("dkv"), _BWD.get("dkv_nerf"), _BWD.get("demb")
+        _BWD["dkv"] = _BWD["dkv_nerf"] = _BWD["demb"] = None
+    if cg is None:
+        return None
+    return _cond_backward(unet, cg, fw.batch, dkv, dkv_nerf, demb)
+
+
+def _cond_backward(unet, cg, b, dkv, dkv_nerf, demb):
+    """dL/d(context) and dL/d(vector) from the collected dK|dV and emb_layers gradients."""
+    bp = bwd_pack(unet)
+    if "kvw_t" not in bp:      # the pack was built before the first conditioning-gradient request
+        unet.__dict__.pop("_bwdpk", None)
+        bp = bwd_pack(unet)
+    ops.add_bf16(dkv, dkv_nerf, out=dkv)
+    dctx = ops.gemm(dkv, bp["kvw_t"], out_fp32=True)                     # K|V = ctx [Wk ; Wv]^T  (to_k / to_v, no bias)
+    # emb_out = Linear(SiLU(emb));  emb = time_embed(t) + Linear(SiLU(Linear(y)))   (openaimodel.py:679-713, 1026-1031)
+    # (K = sum of the 17 ResBlocks' widths exceeds the small-linear kernel's smem-resident row: tensor-core GEMM, split-K)
+    d_act = ops.gemm(ops.cast_bf16(demb), bp["embw_t"], out_fp32=True)
+    d_emb = ops.silu_bwd(cg.emb, d_act)
+    d_l1 = ops.small_linear(d_emb, bp["le2w_t"])
+    d_l1p = ops.silu_bwd(cg.l1p, d_l1)
+    dy = ops.small_linear(d_l1p, bp["le0w_t"])
+    return {"crossattn": dctx.view(b, cg.nctx, cg.ctx_dim), "vector": dy}
 
 
 def _unet_backward(unet, fw, deps, daux_of):
     p = unet.packed()
     bp = bwd_pack(unet)
     b = fw.batch
-    stop = first_pose_block(unet)
+    stop = first_pose_block(unet) if fw.cond is None else None    # conditioning gradients need the whole walk
     g = ops.conv3x3(deps, bp["cout"], b, fw.hh, fw.ww)
     g, _ = ops.groupnorm_bwd(fw.h_last, p["og"], p["ob"], g, b, fw.hh * fw.ww, eps=unet.out[0].eps, silu=True)
     skip_grads: Dict[int, torch.Tensor] = {}

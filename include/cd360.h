@@ -354,6 +354,11 @@ int cd360_geglu_bwd_bf16(const void* raw, const void* dh, void* draw, int64_t ro
  * openaimodel.py:1074). */
 int cd360_add_bf16(const void* a, const void* b, void* out, int64_t n, cd360_stream_t stream);
 
+/* out = dy * silu'(pre), fp32, n elements: backward of the SiLU inside time_embed / label_emb /
+ * ResBlock.emb_layers (openaimodel.py:679-713, 270-276) on the way to dL/d(vector) — the gradient the
+ * reference's conditioner needs for its trainable token rows (sgm/models/diffusion.py:343-356). */
+int cd360_silu_bwd_f32(const float* pre, const float* dy, float* out, int64_t n, cd360_stream_t stream);
+
 /* in [rows, cols] (bf16, or fp32 if in_is_fp32; row stride ld_in) -> out bf16 [cols, ld_out] with
  * out[c][r] = in[r][c], zero for r in [rows, ld_out): the K-major operand of a weight-gradient GEMM. */
 int cd360_transpose_to_bf16(const void* in, int32_t in_is_fp32, int64_t ld_in, void* out,

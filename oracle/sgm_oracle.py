@@ -587,13 +587,16 @@ def unet_forward_with_reference_stream(sd, cfg: dict, x: Tensor, timesteps: Tens
     over the n views (:1041-1049) and whose text / vector conditioning are the second halves of
     context / y; every pose block of the main stream then reads the reference stream's tokens of
     that block as its context_ref (attention.py:852-854) instead of a stored `references` buffer.
+    The reference stream carries no gradient: the reference runs it under torch.no_grad and hands
+    `xr.detach()` to the pose blocks (openaimodel.py:95-108, attention.py:846-868).
     Returns ((eps, aux), captured reference tokens)."""
     b, n = input_ref.shape[:2]
     cap: dict = {}
     t_ref = sigmas_ref.reshape(b, 1).expand(b, n).reshape(b * n)
-    unet_forward(sd, cfg, input_ref.reshape(b * n, *input_ref.shape[2:]), t_ref, context_ref,
-                 y_ref.reshape(b * n, -1), capture=cap)
-    live = {p: v.reshape(b, n, *v.shape[1:]) for p, v in cap.items()}
+    with torch.no_grad():
+        unet_forward(sd, cfg, input_ref.reshape(b * n, *input_ref.shape[2:]), t_ref, context_ref,
+                     y_ref.reshape(b * n, -1), capture=cap)
+    live = {p: v.detach().reshape(b, n, *v.shape[1:]) for p, v in cap.items()}
     return unet_forward(sd, cfg, x, timesteps, context, y, cams=cams, ctx_ref=live), cap
 
 

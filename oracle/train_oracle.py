@@ -128,13 +128,26 @@ def training_loss(sd: Dict[str, Tensor], cfg: dict, batch: dict, *, global_step:
     return total, terms
 
 
-def training_gradients(sd, cfg, batch, **kw):
-    """(total loss, terms, {pose parameter name: gradient}) by autograd over the functional oracle."""
+def training_gradients(sd, cfg, batch, cond_grads: bool = False, **kw):
+    """(total loss, terms, {pose parameter name: gradient}) by autograd over the functional oracle.
+    cond_grads=True additionally returns, under the keys "cond.crossattn" / "cond.vector", the
+    gradients w.r.t. the conditioner's outputs — what the reference's autograd hands back to the
+    text encoders so that the `<new1>` token-embedding rows train (sgm/models/diffusion.py:343-356,
+    main.py:627-643).  The rows of the reference views (b:) come out exactly zero: the reference
+    stream runs under torch.no_grad (openaimodel.py:79-111, attention.py:846-868)."""
     names = pose_param_names(sd)
     sd = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    leaves = [sd[k] for k in names]
+    if cond_grads:
+        batch = dict(batch)
+        batch["crossattn"] = batch["crossattn"].clone().requires_grad_(True)
+        batch["vector"] = batch["vector"].clone().requires_grad_(True)
+        leaves += [batch["crossattn"], batch["vector"]]
+        names = names + ["cond.crossattn", "cond.vector"]
     total, terms = training_loss(sd, cfg, batch, **kw)
-    grads = torch.autograd.grad(total, [sd[k] for k in names], allow_unused=True)
-    return total.detach(), terms, {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads)}
+    grads = torch.autograd.grad(total, leaves, allow_unused=True)
+    return total.detach(), terms, {k: (g if g is not None else torch.zeros_like(l))
+                                   for k, g, l in zip(names, grads, leaves)}
 
 
 def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,

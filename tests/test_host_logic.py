@@ -122,7 +122,10 @@ def test_real_ops_refuse_cpu_tensors():
 def test_training_step_control_flow_with_fake_kernels():
     """Host logic of the training step (loss -> taped forward -> explicit backward walk -> flat
     AdamW) with shape-checking stand-ins for the kernels: every pose block gets a FeatureNeRF
-    backward, skip-connection gradients are joined, the walk stops at the first pose block."""
+    backward, skip-connection gradients are joined; with the conditioning gradients on (default) every
+    attn2 backward — 1 per transformer block + 1 per FeatureNeRF block — also yields dK / dV, every
+    ResBlock contributes to dL/d(vector), and the result has the conditioner outputs' shapes; with
+    them off the walk stops at the first pose block."""
     from collections import Counter
 
     from tests import test_train_step_gpu as G
@@ -143,6 +146,21 @@ def test_training_step_control_flow_with_fake_kernels():
         assert set(eng.last_loss_dict) == {"loss", "loss_fg", "loss_bg", "loss_rgb"}
         opt.step()
         calls = Counter(k for k, _ in fake.calls)
+        kv_grads = sum(1 for k, kw in fake.calls if k == "attention_bwd" and kw["kv_grad"] and kw["nkv"] == 77)
+        unet = eng.model.diffusion_model
+        n_blocks = sum(len(m.transformer_blocks) for m in unet.modules() if type(m).__name__ == "SpatialTransformer")
+        assert kv_grads == n_blocks + n_pose and calls["silu_bwd"] == 2
+        cg = eng.last_cond_grads
+        bt = G._to_engine_batch(batch, torch.device("cpu"))
+        assert cg["crossattn"].shape == bt["cond"]["crossattn"].shape and cg["vector"].shape == bt["cond"]["vector"].shape
+        # conditioning gradients off: no dK / dV of the text context, shorter walk
+        n_gn = calls["groupnorm_bwd"]
+        fake.calls.clear()
+        unet.cond_grad = False
+        eng.training_step(bt)
+        assert eng.last_cond_grads is None
+        assert not any(k == "attention_bwd" and kw["kv_grad"] and kw["nkv"] == 77 for k, kw in fake.calls)
+        assert Counter(k for k, _ in fake.calls)["groupnorm_bwd"] < n_gn
     assert calls["volrender"] == calls["volrender_bwd"] == n_pose
     assert calls["nerf_aux_loss"] == 2 * n_pose and calls["diffusion_loss"] == 2 and calls["adamw"] == 1
     assert eng.global_step == 2

@@ -185,7 +185,11 @@ def _reference_training_step(ns, cfg, sd, batch, seed, train_mode):
     net = ns.wrappers.OpenAIWrapper(unet)
     b, n = batch["x_ref"].shape[:2]
     pose = [H.cameras_from_packed(batch["cams"][i]) for i in range(b)]
-    conditioner = lambda bt: {"crossattn": batch["crossattn"], "vector": batch["vector"]}
+    # the conditioner's outputs are autograd leaves here: their gradients are what the reference's
+    # text encoders receive for the `<new1>` token rows (diffusion.py:343-356)
+    ca = batch["crossattn"].clone().requires_grad_(True)
+    vec = batch["vector"].clone().requires_grad_(True)
+    conditioner = lambda bt: {"crossattn": ca, "vector": vec}
     torch.manual_seed(seed)
     loss, loss_fg, loss_bg, loss_rgb = loss_fn(net, denoiser, conditioner, batch["x"], batch["rgb"], batch["x_ref"],
                                                pose, batch["mask"], batch.get("mask_ref"), batch["opacity"], {})
@@ -198,6 +202,7 @@ def _reference_training_step(ns, cfg, sd, batch, seed, train_mode):
     total = total + 10.0 * lf + 10.0 * lb + 5.0 * lr
     total.backward()
     grads = {k: p.grad.clone() for k, p in unet.named_parameters() if p.requires_grad}
+    grads["cond.crossattn"], grads["cond.vector"] = ca.grad.clone(), vec.grad.clone()
     # replay the draws: CubicSampling torch.rand, randn_like(input), DiscreteSampling torch.randint,
     # randn_like(input_ref) (loss.py:147-170), randn_like(input_ref) (denoiser.py:31), then per pose
     # block in execution order: rand_like x2 (utils_cameraray.py:111-140), torch.rand (nerfsd:317-325)
@@ -233,8 +238,13 @@ def test_training_step_vs_reference(ns, train_mode, mask_ref):
     batch = T.synthetic_train_batch(cfg, L, n_views=n, b=1, seed=5, image=48, mask_ref=mask_ref)
     total_ref, terms_ref, grads_ref, rand = _reference_training_step(ns, cfg, sd, batch, seed=11, train_mode=train_mode)
     batch = dict(batch, rand=rand)
-    total, terms, grads = T.training_gradients(sd, cfg, batch)
+    total, terms, grads = T.training_gradients(sd, cfg, batch, cond_grads=True)
     assert abs(float(total) - float(total_ref)) <= 1e-4 * max(1.0, abs(float(total_ref)))
+    # conditioning gradients: target rows carry signal, reference-view rows are exactly zero
+    b_ = batch["x"].shape[0]
+    for k in ("cond.crossattn", "cond.vector"):
+        assert float(grads_ref[k][:b_].abs().max()) > 0 and float(grads_ref[k][b_:].abs().max()) == 0.0, k
+        assert float(grads[k][b_:].abs().max()) == 0.0, k
     for k in ("loss", "loss_fg", "loss_bg", "loss_rgb"):
         assert abs(float(terms[k]) - float(terms_ref[k])) <= 1e-4 * max(1.0, abs(float(terms_ref[k]))), k
     assert set(grads) == set(grads_ref) and len(grads) > 0

@@ -90,7 +90,8 @@ def test_training_step_gradients_vs_oracle(jitter, b, mask_ref):
     batch = T.synthetic_train_batch(cfg, L, n_views=n, b=b, seed=5, image=48, jitter=jitter, mask_ref=mask_ref)
     if b > 1:
         batch["drop_im"] = torch.tensor([1.0, 0.0])[:b]     # second sample: reference images dropped
-    total_ref, terms_ref, grads_ref = T.training_gradients(sd, cfg, _oracle_batch(batch))
+    total_ref, terms_ref, grads_ref = T.training_gradients(sd, cfg, _oracle_batch(batch), cond_grads=True)
+    cond_ref = {k[len("cond."):]: grads_ref.pop(k) for k in ("cond.crossattn", "cond.vector")}
     engine = _engine(cfg, sd, dev)
     engine.global_step = 1
     opt = engine.configure_optimizers()
@@ -127,6 +128,17 @@ def test_training_step_gradients_vs_oracle(jitter, b, mask_ref):
     _record(f"jitter={jitter}/b={b}/mask_ref={mask_ref}/summary", loss=float(loss), loss_oracle=float(total_ref), worst_rel_rms=worst[0],
             worst_tensor=worst[1], tensors=len(grads_ref), global_cosine=gcos)
     assert gcos >= 0.998, gcos
+    # conditioning gradients (what the reference's autograd hands to the text encoders for the `<new1>`
+    # token rows, diffusion.py:343-356): same bf16-activation-gradient tolerance as the weights; the rows
+    # of the reference views are exactly zero (no_grad stream)
+    for k, g_ref in cond_ref.items():
+        g = engine.last_cond_grads[k].float().cpu()
+        assert g.shape == g_ref.shape, (k, g.shape, g_ref.shape)
+        assert float(g[b:].abs().max()) == 0.0 and float(g_ref[b:].abs().max()) == 0.0, k
+        rel = float((g - g_ref).norm() / g_ref.norm())
+        cos = float((g * g_ref).sum() / (g.norm() * g_ref.norm()).clamp_min(1e-30))
+        _record(f"jitter={jitter}/b={b}/mask_ref={mask_ref}/cond.{k}", rel_rms=rel, cosine=cos, ref_norm=float(g_ref.norm()))
+        assert rel <= 0.12 and cos >= 0.99, f"cond.{k}: rel_rms {rel:.4g}, cosine {cos:.5f}"
     # optimiser: one fused AdamW step over the flat buffer == torch.optim.AdamW semantics on the same gradients
     before = {k: named[k].detach().clone() for k in grads_ref}
     grads = {k: named[k].grad.detach().clone() for k in grads_ref}
@@ -141,6 +153,36 @@ def test_training_step_gradients_vs_oracle(jitter, b, mask_ref):
 
 def _oracle_batch(batch):
     return dict(batch)
+
+
+@gpu
+def test_conditioning_gradients_reach_an_autograd_conditioner():
+    """The drop-in case of INTEGRATION.md: `cond` comes from a torch-autograd conditioner (the
+    reference's GeneralConditioner with trainable token rows).  training_step must leave, in the
+    conditioner's parameter .grad, the contraction of the step's conditioning gradients with the
+    conditioner's own Jacobian — i.e. what `loss.backward()` does in the reference."""
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    sd = O.synthetic_state_dict(cfg, seed=2)
+    batch = _to_engine_batch(T.synthetic_train_batch(cfg, 16, n_views=3, b=1, seed=5, image=48), dev)
+    ca0, vec0 = batch["cond"]["crossattn"], batch["cond"]["vector"]
+    row = torch.nn.Parameter(torch.randn(ca0.shape[-1], device=dev) * 0.1)      # a "token embedding row"
+    gain = torch.nn.Parameter(torch.ones(vec0.shape[-1], device=dev))
+    onehot = torch.zeros(ca0.shape[0], ca0.shape[1], 1, device=dev)
+    onehot[:, 5] = 1.0                                                           # the token sits at position 5
+    batch["cond"] = {"crossattn": ca0 + onehot * row, "vector": vec0 * gain}
+    engine = _engine(cfg, sd, dev)
+    engine.global_step = 1
+    opt = engine.configure_optimizers()
+    opt.zero_grad()
+    engine.training_step(batch)
+    torch.cuda.synchronize()
+    cg = engine.last_cond_grads
+    assert row.grad is not None and gain.grad is not None
+    exp_row = (cg["crossattn"] * onehot).sum((0, 1))
+    exp_gain = (cg["vector"] * vec0).sum(0)
+    assert float(row.grad.abs().max()) > 0
+    assert torch.allclose(row.grad, exp_row, rtol=1e-5, atol=1e-8) and torch.allclose(gain.grad, exp_gain, rtol=1e-5, atol=1e-8)
 
 
 @gpu
