@@ -78,6 +78,8 @@ SIGNATURES = {
     # training step (backward / loss / optimiser)
     "cd360_attention_bwd_bf16": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L,
                                            _P, _P, _I, _I, _I, _I, _P]),
+    "cd360_attention_bwd_kv_split_bf16": (C.c_int, [_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _P, _P, _L, _P, _L,
+                                                    _I, _I, _I, _I, _I, _P]),
     "cd360_layernorm_bwd_bf16": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "cd360_groupnorm_bwd_workspace_floats": (C.c_int64, [_I]),
     "cd360_groupnorm_silu_bwd_bf16": (C.c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P,

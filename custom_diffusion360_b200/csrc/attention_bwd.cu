@@ -520,14 +520,39 @@ attention_bwd_dq_mma_kernel(const AttnBwdParams p) {
   }
 }
 
+// accumulator tiles -> fp32 atomics into acc [B * n, heads * 64] (query-split partial sums)
+__device__ __forceinline__ void atomic_acc_rows(const float (&acc)[8][4], float* dst, int heads, int batch, int n,
+                                                int head, int row_lo) {
+  const int lane = threadIdx.x & 31, t = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int row = row_lo + 8 * h;
+    if (row < n) {
+      float* p = dst + (static_cast<long long>(batch) * n + row) * (heads * AB_T) + head * AB_T + 2 * t;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        atomicAdd(p + nt * 8, acc[nt][2 * h]);
+        atomicAdd(p + nt * 8 + 1, acc[nt][2 * h + 1]);
+      }
+    }
+  }
+}
+
+// NSPLIT == 0: one CTA per (key tile, head, batch) walks every query tile and stores bf16 dK / dV.
+// NSPLIT == 1 (query-split, few keys x very many queries: reference_attn's 24 samples per ray against
+// the 77 text tokens): blockIdx.x = key_tile * nsplit + split, the CTA walks its share of the query
+// tiles and adds its partial sums into the zeroed fp32 accumulators kv_acc = [dK | dV].
+template <int NSPLIT>
 __global__ void __launch_bounds__(AB_THREADS)
-attention_bwd_dkdv_mma_kernel(const AttnBwdParams p) {
+attention_bwd_dkdv_mma_kernel(const AttnBwdParams p, float* kv_acc, int nsplit) {
   __shared__ __align__(128) __nv_bfloat16 sQ[AB_T * AB_LD];
   __shared__ __align__(128) __nv_bfloat16 sDO[AB_T * AB_LD];
   __shared__ float sLse[AB_T], sD[AB_T];
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int key0 = blockIdx.x * AB_T, head = blockIdx.y, batch = blockIdx.z;
+  const int key_tile = NSPLIT ? static_cast<int>(blockIdx.x) / nsplit : static_cast<int>(blockIdx.x);
+  const int split = NSPLIT ? static_cast<int>(blockIdx.x) - key_tile * nsplit : 0;
+  const int key0 = key_tile * AB_T, head = blockIdx.y, batch = blockIdx.z;
   const int w16 = warp * 16;
   const int key_lo = key0 + w16 + g;
   load_tile(sQ, p.k, p.ldk, batch, p.nkv, head, key0);
@@ -546,7 +571,9 @@ attention_bwd_dkdv_mma_kernel(const AttnBwdParams p) {
     }
   const bool key_ok[2] = {key_lo < p.nkv, key_lo + 8 < p.nkv};
   const int nt_q = (p.nq + AB_T - 1) / AB_T;
-  for (int i = 0; i < nt_q; ++i) {
+  const int per = NSPLIT ? (nt_q + nsplit - 1) / nsplit : nt_q;
+  const int i_begin = split * per, i_end = min(nt_q, i_begin + per);
+  for (int i = i_begin; i < i_end; ++i) {
     __syncthreads();
     load_tile(sQ, p.q, p.ldq, batch, p.nq, head, i * AB_T);
     load_tile(sDO, p.dout, p.lddo, batch, p.nq, head, i * AB_T);
@@ -572,8 +599,31 @@ attention_bwd_dkdv_mma_kernel(const AttnBwdParams p) {
     mma_x_b(dv, st, sDO);      // dV += P^T dO
     mma_x_b(dk, dpt, sQ);      // dK += dS^T Q
   }
-  store_acc_rows(dk, p.dk, p.lddk, batch, p.nkv, head, key_lo);
-  store_acc_rows(dv, p.dv, p.lddv, batch, p.nkv, head, key_lo);
+  if (NSPLIT) {
+    atomic_acc_rows(dk, kv_acc, p.heads, batch, p.nkv, head, key_lo);
+    atomic_acc_rows(dv, kv_acc + static_cast<long long>(gridDim.z) * p.nkv * p.heads * AB_T, p.heads, batch, p.nkv,
+                    head, key_lo);
+  } else {
+    store_acc_rows(dk, p.dk, p.lddk, batch, p.nkv, head, key_lo);
+    store_acc_rows(dv, p.dv, p.lddv, batch, p.nkv, head, key_lo);
+  }
+}
+
+// fp32 accumulators [dK | dV] (each [rows, inner]) -> bf16 dk / dv (row strides lddk / lddv)
+__global__ void __launch_bounds__(256)
+attention_bwd_kv_finish_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dk, long long lddk,
+                               __nv_bfloat16* __restrict__ dv, long long lddv, long long rows, int inner) {
+  pdl_wait();
+  const long long half = rows * inner;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2; i < 2 * half;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 2) {
+    const bool is_v = i >= half;
+    const long long j = is_v ? i - half : i;
+    const long long r = j / inner;
+    const int c = static_cast<int>(j - r * inner);
+    __nv_bfloat16* dst = (is_v ? dv + r * lddv : dk + r * lddk) + c;
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[i], acc[i + 1]);
+  }
 }
 
 constexpr int AB_SMEM_STATS = 2 * AB_TILE_B + AB_TILE_F;
@@ -637,7 +687,8 @@ extern "C" int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* 
       return CD360_ERR_LAUNCH;
     if (dk != nullptr) {
       const dim3 gk((nkv + AB_T - 1) / AB_T, heads, batch);
-      if (launch_ex(attention_bwd_dkdv_mma_kernel, gk, dim3(AB_THREADS), 0, stream, 1, p) != cudaSuccess)
+      if (launch_ex(attention_bwd_dkdv_mma_kernel<0>, gk, dim3(AB_THREADS), 0, stream, 1, p,
+                    static_cast<float*>(nullptr), 1) != cudaSuccess)
         return CD360_ERR_LAUNCH;
     }
     CD360_CHECK_LAUNCH();
@@ -652,6 +703,52 @@ extern "C" int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* 
     if (launch_ex(attention_bwd_dkdv_kernel, gk, dim3(AB_THREADS), AB_SMEM_DKDV, stream, 1, p) != cudaSuccess)
       return CD360_ERR_LAUNCH;
   }
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_attention_bwd_kv_split_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                                 const void* v, int64_t ldv, const void* dout, int64_t lddo,
+                                                 const float* lse, const float* dsum, float* kv_acc,
+                                                 void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                                 int32_t batch, int32_t heads, int32_t nq, int32_t nkv,
+                                                 int32_t nsplit, cd360_stream_t stream_) {
+  if (!q || !k || !v || !dout || !lse || !dsum || !kv_acc || !dk || !dv) return CD360_ERR_NULL;
+  if (batch <= 0 || heads <= 0 || nq <= 0 || nkv <= 0 || nsplit <= 0 || batch > 65535 || heads > 65535)
+    return CD360_ERR_SHAPE;
+  const int64_t lds[6] = {ldq, ldk, ldv, lddo, lddk, lddv};
+  for (int i = 0; i < 6; ++i)
+    if ((lds[i] & 7) || lds[i] < heads * AB_T) return CD360_ERR_ALIGN;
+  const void* ptrs[7] = {q, k, v, dout, dk, dv, kv_acc};
+  for (int i = 0; i < 7; ++i)
+    if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return CD360_ERR_ALIGN;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  AttnBwdParams p{};
+  p.q = reinterpret_cast<const __nv_bfloat16*>(q);
+  p.k = reinterpret_cast<const __nv_bfloat16*>(k);
+  p.v = reinterpret_cast<const __nv_bfloat16*>(v);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.lddo = lddo;
+  p.lse = const_cast<float*>(lse);
+  p.dsum = const_cast<float*>(dsum);
+  p.nq = nq; p.nkv = nkv; p.heads = heads;
+  p.scale = 0.125f;
+  const int key_tiles = (nkv + AB_T - 1) / AB_T;
+  const int q_tiles = (nq + AB_T - 1) / AB_T;
+  if (nsplit > q_tiles) nsplit = q_tiles;
+  const dim3 gk(static_cast<unsigned>(key_tiles * nsplit), heads, batch);
+  if (launch_ex(attention_bwd_dkdv_mma_kernel<1>, gk, dim3(AB_THREADS), 0, stream, 1, p, kv_acc, nsplit) !=
+      cudaSuccess)
+    return CD360_ERR_LAUNCH;
+  const long long rows = static_cast<long long>(batch) * nkv;
+  const long long pairs = rows * heads * AB_T;   // 2 * rows * inner / 2
+  unsigned blocks = static_cast<unsigned>((pairs + 255) / 256);
+  if (blocks > 1184u) blocks = 1184u;
+  if (launch_ex(attention_bwd_kv_finish_kernel, dim3(blocks), dim3(256), 0, stream, 1,
+                static_cast<const float*>(kv_acc), reinterpret_cast<__nv_bfloat16*>(dk),
+                static_cast<long long>(lddk), reinterpret_cast<__nv_bfloat16*>(dv), static_cast<long long>(lddv),
+                rows, heads * AB_T) != cudaSuccess)
+    return CD360_ERR_LAUNCH;
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }

@@ -527,17 +527,30 @@ def gather_rows(x, idx):
 @_op("attention_bwd")
 def attention_bwd(q, k, v, o, dout, batch, heads, nq, nkv, *, dq, dk=None, dv=None):
     """Gradients of `attention`.  q/k/v/o/dout and dq/dk/dv are 2-D views (row strides taken from
-    the views, so slices of a fused QKV buffer work).  dk/dv None: query gradient only."""
+    the views, so slices of a fused QKV buffer work).  dk/dv None: query gradient only.
+    Few keys x very many queries (reference_attn over the ray samples): dK / dV come from the
+    query-split kernel (partial sums over `nsplit` CTAs per key tile meet in an fp32 scratch)."""
     lib = _lib.load()
     dev = q.device
     lse = torch.empty((batch, heads, nq), device=dev, dtype=f32)
     dsum = torch.empty((batch, heads, nq), device=dev, dtype=f32)
-    LaunchStats.launches += 1 if dk is None else 2  # stats + dq (+ dkdv)
+    key_tiles, q_tiles = (nkv + 63) // 64, (nq + 63) // 64
+    base_ctas = key_tiles * heads * batch
+    split = dk is not None and base_ctas < 148 and q_tiles >= 32
+    LaunchStats.launches += 1 if dk is None else (3 if split else 2)  # stats + dq (+ dkdv (+ finish))
     check(lib.cd360_attention_bwd_bf16(
         _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
-        _ptr(dout), dout.stride(0), _ptr(dq), dq.stride(0), _ptr(dk), 0 if dk is None else dk.stride(0),
-        _ptr(dv), 0 if dv is None else dv.stride(0), _ptr(lse), _ptr(dsum), batch, heads, nq, nkv,
+        _ptr(dout), dout.stride(0), _ptr(dq), dq.stride(0), _ptr(None if split else dk),
+        0 if dk is None or split else dk.stride(0), _ptr(None if split else dv),
+        0 if dv is None or split else dv.stride(0), _ptr(lse), _ptr(dsum), batch, heads, nq, nkv,
         _stream()), "cd360_attention_bwd_bf16")
+    if split:
+        nsplit = max(1, min(q_tiles // 4, (2 * 148) // base_ctas))
+        acc = torch.zeros((2, batch * nkv, heads * 64), device=dev, dtype=f32)
+        check(lib.cd360_attention_bwd_kv_split_bf16(
+            _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(dout), dout.stride(0),
+            _ptr(lse), _ptr(dsum), _ptr(acc), _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0),
+            batch, heads, nq, nkv, nsplit, _stream()), "cd360_attention_bwd_kv_split_bf16")
     return dq, dk, dv
 
 

@@ -326,6 +326,19 @@ int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t 
                              float* lse, float* dsum, int32_t batch, int32_t heads, int32_t nq,
                              int32_t nkv, cd360_stream_t stream);
 
+/* dK / dV of an attention with FEW keys and VERY MANY queries — reference_attn's attn2 over the
+ * hw*24 ray samples against the 77 text tokens (attention.py:571-598), whose gradient the conditioner
+ * needs (sgm/models/diffusion.py:343-356).  The query tiles are divided among `nsplit` CTAs per
+ * (key tile, head, batch); partial sums meet in kv_acc (fp32 [2][batch*nkv][heads*64], ZEROED by the
+ * caller) and are converted to bf16 dk / dv.  lse / dsum: the per-query statistics written by a
+ * preceding cd360_attention_bwd_bf16 call on the same operands (its dk / dv NULL). */
+int cd360_attention_bwd_kv_split_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk,
+                                      const void* v, int64_t ldv, const void* dout, int64_t lddo,
+                                      const float* lse, const float* dsum, float* kv_acc,
+                                      void* dk, int64_t lddk, void* dv, int64_t lddv,
+                                      int32_t batch, int32_t heads, int32_t nq, int32_t nkv,
+                                      int32_t nsplit, cd360_stream_t stream);
+
 /* LayerNorm backward w.r.t. the input (nn.LayerNorm, attention.py:531-533; gamma/beta are frozen):
  * dx = dLN(x)^T dy [+ add].  x, dy, add, dx bf16 [rows, c]; c <= 1280. */
 int cd360_layernorm_bwd_bf16(const void* x, const float* gamma, const void* dy, const void* add,

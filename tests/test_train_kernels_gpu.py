@@ -114,6 +114,7 @@ def test_geglu_bwd(rows, f, block):
     (1, 10, 1024, 1024, True),   # level-1 self-attention of the 64x64 training latents
     (2, 4, 300, 77, False),      # text cross-attention: dq only
     (1, 5, 1536, 77, False),     # FeatureNeRF samples x text
+    (1, 5, 4096, 77, False),     # ... long enough for the query-split dK / dV kernel
 ])
 def test_attention_bwd(batch, heads, nq, nkv, self_attn):
     from custom_diffusion360_b200 import ops
@@ -149,6 +150,14 @@ def test_attention_bwd(batch, heads, nq, nkv, self_attn):
         dq = torch.empty_like(q)
         ops.attention_bwd(q, k, v, o, do, batch, heads, nq, nkv, dq=dq)
         _check(dq, merge(qr.grad, nq), rel_rms=2e-2, max_frac=6e-2, what="dq (cross)")
+        # conditioning gradients: dK / dV of the text context (strided column slices of one K|V buffer);
+        # nq = 1536 takes the plain kernel, 4096 queries x 77 keys the query-split one
+        dkv = torch.zeros_like(kv)
+        dq2 = torch.empty_like(q)
+        ops.attention_bwd(q, k, v, o, do, batch, heads, nq, nkv, dq=dq2, dk=dkv[:, :inner], dv=dkv[:, inner:])
+        assert torch.equal(dq2, dq)
+        _check(dkv[:, :inner], merge(kr.grad, nkv), rel_rms=2e-2, max_frac=6e-2, what="dk (cross)")
+        _check(dkv[:, inner:], merge(vr.grad, nkv), rel_rms=2e-2, max_frac=6e-2, what="dv (cross)")
 
 
 @gpu
