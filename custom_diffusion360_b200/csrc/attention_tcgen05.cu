@@ -25,6 +25,22 @@
 
 #include "cd360_common.cuh"
 
+// Per-tile clock stamps of ONE CTA of the ping-pong kernel for tools/attn_trace.py (never compiled into
+// libcd360.so): slot * 64 + key tile.
+#ifdef CD360_ATT_TRACE
+__device__ long long* g_cd360_att_trace = nullptr;
+#define ATT_TR(slot, j)                                                                            \
+  do {                                                                                             \
+    if (g_cd360_att_trace != nullptr && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && (j) < 64) \
+      g_cd360_att_trace[(slot) * 64 + (j)] = clock64();                                            \
+  } while (0)
+extern "C" int cd360_att_set_trace(long long* buf) {
+  return cudaMemcpyToSymbol(g_cd360_att_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define ATT_TR(slot, j) do {} while (0)
+#endif
+
 namespace cd360 {
 
 constexpr int ATT_BQ = 128;
@@ -126,7 +142,10 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint64_t* o_full = p_full + 2;                // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index from lane 0 (provably warp-uniform): the single-thread roles below run as whole warps
+  // with one elected lane issuing, which keeps TMA / MMA operands in uniform registers (see the
+  // ping-pong kernel)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int head = blockIdx.y;
@@ -173,25 +192,31 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // Q/K/V come from the preceding projection GEMM
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ================================ TMA producer ================================
-    mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
-    tma_load_4d(smem + ATT_SQ, &tmQ, q_full, 0, head, q_tile * ATT_BQ, batch);
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
+      tma_load_4d(smem + ATT_SQ, &tmQ, q_full, 0, head, q_tile * ATT_BQ, batch);
+    }
+    __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&kv_empty[stage], phase ^ 1);
       uint8_t* sk = smem + ATT_SKV + stage * 2 * ATT_KV_BYTES;
       uint8_t* sv = sk + ATT_KV_BYTES;
-      mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
-      tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * ATT_BKV, batch);
-      tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * ATT_BKV, batch);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * ATT_KV_BYTES);
+        tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * ATT_BKV, batch);
+        tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * ATT_BKV, batch);
+      }
+      __syncwarp();
       if (++stage == ATT_STAGES) {
         stage = 0;
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ================================ MMA issuer ================================
     constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BQ, ATT_BKV, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BQ, ATT_D, true);  // V is MN-major
@@ -204,11 +229,14 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       tc_fence_after();
       const uint32_t k_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_KV_BYTES);
       const uint32_t d = tmem_base + ATT_TMEM_S + (j & 1) * ATT_BKV;
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k)
-        umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
-                  idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&s_full[j & 1]);
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                    idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_s(0);
@@ -220,16 +248,19 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       tc_fence_after();
       const uint32_t p_addr = smem_u32(smem + ATT_SP + b * ATT_P_BYTES);
       const uint32_t v_addr = smem_u32(smem + ATT_SKV + stage * 2 * ATT_KV_BYTES) + ATT_KV_BYTES;
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < ATT_BKV / 16; ++k) {
-        const uint64_t a = make_smem_desc_sw128(p_addr + k * 32);
-        umma_bf16(tmem_base + ATT_TMEM_O, a, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
-                  (j | k) != 0 ? 1u : 0u);
-        // row sums of the bf16 P the product actually uses: 16 identical columns of l
-        umma_bf16(tmem_base + ATT_TMEM_L, a, ones_desc, idesc_l, (j | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < ATT_BKV / 16; ++k) {
+          const uint64_t a = make_smem_desc_sw128(p_addr + k * 32);
+          umma_bf16(tmem_base + ATT_TMEM_O, a, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
+                    (j | k) != 0 ? 1u : 0u);
+          // row sums of the bf16 P the product actually uses: 16 identical columns of l
+          umma_bf16(tmem_base + ATT_TMEM_L, a, ones_desc, idesc_l, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[b]);
+        umma_commit(&kv_empty[stage]);
       }
-      umma_commit(&o_full[b]);
-      umma_commit(&kv_empty[stage]);
+      __syncwarp();
       if (j + 2 < nt) issue_s(j + 2);
     }
   } else if (warp >= 4) {
@@ -410,7 +441,12 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint64_t* o_full = p_full + 2;                   // [2] O_t += P_t(j) V_j retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index broadcast from lane 0: provably warp-uniform, so the role branches below are uniform
+  // branches and the single-thread roles (TMA producer, MMA issuer) keep their addresses /
+  // descriptors in uniform registers — under `lane == 0` every cp.async.bulk.tensor / tcgen05.mma was
+  // wrapped in an ELECT + R2UR.BROADCAST x5 + BRA.U.ANY loop, ~100 clk per MMA, and the issuer thread
+  // (24 MMAs per key tile) set the pace of the whole kernel (tools/attn_trace.py)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int q_pair = blockIdx.x;   // 256 queries
   const int head = blockIdx.y;
@@ -452,38 +488,53 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
-    mbar_arrive_expect_tx(q_full, AT2_Q_BYTES);
-    tma_load_4d(smem + AT2_SQ, &tmQ, q_full, 0, head, q_pair * 256, batch);
+  if (warp == 0) {
+    // ================================ TMA producer (whole warp, one elected lane issues) =========
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, AT2_Q_BYTES);
+      tma_load_4d(smem + AT2_SQ, &tmQ, q_full, 0, head, q_pair * 256, batch);
+    }
+    __syncwarp();
     int stage = 0;
     uint32_t phase = 0;
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&kv_empty[stage], phase ^ 1);
       uint8_t* sk = smem + AT2_SKV + stage * 2 * AT2_KV_BYTES;
       uint8_t* sv = sk + AT2_KV_BYTES;
-      mbar_arrive_expect_tx(&kv_full[stage], 2 * AT2_KV_BYTES);
-      tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * AT2_BKV, batch);
-      tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * AT2_BKV, batch);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * AT2_KV_BYTES);
+        ATT_TR(14, j);
+        tma_load_4d(sk, &tmK, &kv_full[stage], 0, head, j * AT2_BKV, batch);
+        tma_load_4d(sv, &tmV, &kv_full[stage], 0, head, j * AT2_BKV, batch);
+      }
+      __syncwarp();
       if (++stage == AT2_STAGES) {
         stage = 0;
         phase ^= 1;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1) {
+    // ================================ MMA issuer (whole warp, one elected lane issues) ==========
+    // All 32 lanes run the event loop with identical state; barrier polls are combined with a warp
+    // vote so every decision is uniform, and only the tcgen05 instructions sit under elect.sync.
     constexpr uint32_t idesc_s = make_idesc_bf16(128, AT2_BKV, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_D, true);   // V is MN-major
+    auto poll = [&](uint64_t* bar, uint32_t parity) -> bool {
+      return __all_sync(0xffffffffu, mbar_try_wait(bar, parity)) != 0;
+    };
     auto issue_s = [&](int t, int j) {  // S_t(j) = Q_t K_j^T (kv_full of tile j already waited)
       const int stage = j % AT2_STAGES;
       const uint32_t q_addr = smem_u32(smem + AT2_SQ + t * 128 * 128);
       const uint32_t k_addr = smem_u32(smem + AT2_SKV + stage * 2 * AT2_KV_BYTES);
       const uint32_t d = tmem_base + t * AT2_TILE_COLS;
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k)
-        umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
-                  idesc_s, k != 0 ? 1u : 0u);
-      umma_commit(&s_full[t]);
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(d, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                    idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
     };
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
@@ -502,25 +553,30 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int js = next_s[t];
-        if (js < nt && mbar_try_wait(&s_free[t], (js - 1) & 1) &&
-            mbar_try_wait(&kv_full[js % AT2_STAGES], (js / AT2_STAGES) & 1)) {
+        if (js < nt && poll(&s_free[t], (js - 1) & 1) &&
+            poll(&kv_full[js % AT2_STAGES], (js / AT2_STAGES) & 1)) {
           tc_fence_after();
+          ATT_TR(t, js);
           issue_s(t, js);
           next_s[t] = js + 1;
           progress = true;
         }
         const int jp = next_pv[t];
-        if (jp < nt && mbar_try_wait(&p_full[t], jp & 1)) {  // P_t(jp) in TMEM, O_t rescaled if needed
+        if (jp < nt && poll(&p_full[t], jp & 1)) {  // P_t(jp) in TMEM, O_t rescaled if needed
           tc_fence_after();
           const uint32_t v_addr =
               smem_u32(smem + AT2_SKV + (jp % AT2_STAGES) * 2 * AT2_KV_BYTES) + AT2_KV_BYTES;
           const uint32_t a_p = tmem_base + t * AT2_TILE_COLS + AT2_COL_P;
           const uint32_t d_o = tmem_base + t * AT2_TILE_COLS + AT2_COL_O;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < AT2_BKV / 16; ++k)  // 16 keys = 8 TMEM columns of packed bf16 pairs
-            umma_bf16_ts(d_o, a_p + k * 8, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
-                         (jp | k) != 0 ? 1u : 0u);
-          umma_commit(&o_full[t]);
+            for (int k = 0; k < AT2_BKV / 16; ++k)  // 16 keys = 8 TMEM columns of packed bf16 pairs
+              umma_bf16_ts(d_o, a_p + k * 8, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
+                           (jp | k) != 0 ? 1u : 0u);
+            umma_commit(&o_full[t]);
+          }
+          __syncwarp();
+          ATT_TR(2 + t, jp);
           next_pv[t] = jp + 1;
           progress = true;
         }
@@ -528,7 +584,8 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       // stage j is free once both P V products of tile j have been issued (the commit tracks
       // every MMA issued so far, including both S products that read K_j)
       while (released < min(next_pv[0], next_pv[1])) {
-        umma_commit(&kv_empty[released % AT2_STAGES]);
+        if (elect_one_sync()) umma_commit(&kv_empty[released % AT2_STAGES]);
+        __syncwarp();
         ++released;
       }
       if (progress) {
@@ -551,8 +608,10 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
 
     for (int j = 0; j < nt; ++j) {
       const int valid = min(AT2_BKV, p.nkv - j * AT2_BKV);
+      if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 4, j);   // loop top (after the previous p_full arrive)
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 0, j);
       uint32_t r[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -561,6 +620,7 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[t]);  // S_t may be overwritten by S_t(j+1)
+      if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 1, j);
       float mx = -INFINITY;
       if (valid == AT2_BKV) {
         float mx1 = -INFINITY;
@@ -610,10 +670,12 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
         }
       }
       // P_t V of tile j-1 must have retired: frees the P buffer and fixes O_t
+      if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 2, j);
       if (j > 0) {
         mbar_wait(&o_full[t], (j - 1) & 1);
         tc_fence_after();
       }
+      if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 3, j);
       if (any_grow && j > 0) {
         const float alpha = grow ? ex2_approx((m_ref - m_new) * p.scale_log2) : 1.0f;
         l0 *= alpha;

@@ -225,7 +225,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2 * kEpiWarps);
 
-  const int warp = threadIdx.x >> 5;
+  // Warp index broadcast from lane 0: provably warp-uniform, so the role branches are uniform branches
+  // and the single-lane roles run as WHOLE warps with one elected lane issuing the asynchronous
+  // instruction.  Under `lane == 0` (a divergent region) every cp.async.bulk.tensor / tcgen05.mma /
+  // tcgen05.commit had its operands in vector registers and was wrapped by ptxas in an
+  // ELECT + R2UR.BROADCAST x5 + BRA.U.ANY loop (~100 clk per instruction); with uniform control flow
+  // the addresses and descriptors live in uniform registers and the UTCHMMAs issue back to back.
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // cluster = MC CTA pairs (or single CTAs); pair `pr` works on M block m_blk*MC + pr of the SAME
   // N block, so with MC == 2 the two pairs share every W tile (TMA multicast below)
@@ -282,8 +288,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
   pdl_wait();  // nothing above touches global memory written by earlier kernels
   if (threadIdx.x == 0) CD360_TRACE(2);
 
-  if (warp == 0 && lane == 0) {
-    // ================================ TMA producer ================================
+  if (warp == 0) {
+    // ================================ TMA producer (whole warp; one elected lane issues) ========
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units) {
@@ -308,6 +314,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + A_TILE_BYTES;
         uint64_t* fb = &full_bar[stage];
+        if (elect_one_sync()) {
         if (CG == 1) {
           mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
         } else if (leader) {
@@ -341,14 +348,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
         if (tile == unit && kb == kb_begin) CD360_TRACE(3);
         if (tile + num_units >= num_tiles && kb == kb_end - 1) CD360_TRACE(4);
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && leader) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 && leader) {
+    // ================================ MMA issuer (whole warp; one elected lane issues) ==========
     constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
@@ -368,22 +377,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (t == 0 && kb == kb_begin + 1) CD360_TRACE(6);
         const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
-          const uint32_t accumulate = (kb != kb_begin || k != 0) ? 1u : 0u;
-          if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
-          else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
+            const uint32_t accumulate = (kb != kb_begin || k != 0) ? 1u : 0u;
+            if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+          }
+          // free the smem slot (in both CTAs) once these MMAs retire
+          if (CG == 2) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>((1u << (CG * MC)) - 1u));
+          else umma_commit(&empty_bar[stage]);
+          if (kb == kb_end - 1) {
+            if (CG == 2) umma_commit_2sm(&tmem_full[buf], static_cast<uint16_t>(0x3u << (pr * 2)));
+            else umma_commit(&tmem_full[buf]);
+            if (tile + num_units >= num_tiles) CD360_TRACE(7);
+          }
         }
-        // free the smem slot (in both CTAs) once these MMAs retire
-        if (CG == 2) umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>((1u << (CG * MC)) - 1u));
-        else umma_commit(&empty_bar[stage]);
-        if (kb == kb_end - 1) {
-          if (CG == 2) umma_commit_2sm(&tmem_full[buf], static_cast<uint16_t>(0x3u << (pr * 2)));
-          else umma_commit(&tmem_full[buf]);
-          if (tile + num_units >= num_tiles) CD360_TRACE(7);
-        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -411,11 +423,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       return n_blk * out_tile_cols + (half * n_slabs + s) * 64;
     };
     uint32_t slab_cnt = 0;  // slabs this warp has processed: buffer = cnt & 1, parity = (cnt >> 1) & 1
-    if (use_res && lane == 0 && unit < num_tiles) {
+    if (use_res && unit < num_tiles) {
       const int m_blk = unit % p.num_m_blocks, n_blk = unit / p.num_m_blocks;
-      mbar_arrive_expect_tx(&wres[0], WSLAB_BYTES);
-      tma_load_2d(wbuf, &tmRes, &wres[0], slab_col(n_blk, 0),
-                  ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&wres[0], WSLAB_BYTES);
+        tma_load_2d(wbuf, &tmRes, &wres[0], slab_col(n_blk, 0),
+                    ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32);
+      }
+      __syncwarp();
     }
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
@@ -587,7 +602,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
           } else {
             // the store issued from this buffer two slabs ago must have finished reading it
-            if (lane == 0) tma_store_wait_read_1();
+            // (bulk groups are per thread: elect.sync picks the same lane for the same full mask)
+            if (elect_one_sync()) tma_store_wait_read_1();
             __syncwarp();
           }
           CD360_TRACE_CLK(trace_me && s < 2, 18 + 5 * s);
@@ -616,20 +632,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
           fence_proxy_async_smem();
           __syncwarp();  // the warp's 32 rows are complete in smem
           CD360_TRACE_CLK(trace_me && s < 2, 20 + 5 * s);
-          if (lane == 0) {
-            tma_store_2d(&tmOut, sbuf, slab_col(n_blk, s), row0 + q * 32);
+          // coordinates of the next residual slab (this or the next tile), computed in uniform code
+          int nxt_t = tile, nxt_s = s + 1;
+          if (nxt_s == n_slabs) { nxt_t = tile + num_units; nxt_s = 0; }
+          const bool nxt_ok = use_res && nxt_t < num_tiles;
+          const int nxt_m = nxt_t % p.num_m_blocks, nxt_n = nxt_t / p.num_m_blocks;
+          const int nxt_col = slab_col(nxt_n, nxt_s);
+          const int nxt_row = ((nxt_m * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32;
+          const int out_col = slab_col(n_blk, s), out_row = row0 + q * 32;
+          uint64_t* nb = &wres[(slab_cnt + 1u) & 1u];
+          uint8_t* nbuf = wbuf + ((slab_cnt + 1u) & 1u) * WSLAB_BYTES;
+          if (elect_one_sync()) {
+            tma_store_2d(&tmOut, sbuf, out_col, out_row);
             tma_store_commit();
-            if (use_res) {  // prefetch the next residual slab (this or the next tile) into the other buffer
-              int nt = tile, ns = s + 1;
-              if (ns == n_slabs) { nt = tile + num_units; ns = 0; }
-              if (nt < num_tiles) {
-                const int nm = nt % p.num_m_blocks, nn = nt / p.num_m_blocks;
-                tma_store_wait_read_1();  // the previous slab's store has released that buffer
-                uint64_t* nb = &wres[(slab_cnt + 1u) & 1u];
-                mbar_arrive_expect_tx(nb, WSLAB_BYTES);
-                tma_load_2d(wbuf + ((slab_cnt + 1u) & 1u) * WSLAB_BYTES, &tmRes, nb, slab_col(nn, ns),
-                            ((nm * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM + q * 32);
-              }
+            if (nxt_ok) {  // prefetch the next residual slab into the other buffer
+              tma_store_wait_read_1();  // the previous slab's store has released that buffer
+              mbar_arrive_expect_tx(nb, WSLAB_BYTES);
+              tma_load_2d(nbuf, &tmRes, nb, nxt_col, nxt_row);
             }
           }
           __syncwarp();
@@ -700,7 +719,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     if (warp == 4 && lane == 0) CD360_TRACE(10);
     // smem must outlive the bulk stores' READS; the writes are complete at grid completion
-    if (p.epi_tma && lane == 0) tma_store_wait_read();
+    __syncwarp();
+    if (p.epi_tma && elect_one_sync()) tma_store_wait_read();
     if (warp == 4 && lane == 0) CD360_TRACE(11);
     CD360_TRACE_CLK(warp == 4 && lane == 0, 27);
   }
