@@ -623,13 +623,15 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       if (q == 0 && lane == 0) ATT_TR(4 + 5 * t + 1, j);
       float mx = -INFINITY;
       if (valid == AT2_BKV) {
-        float mx1 = -INFINITY;
+        float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; i += 4) {
+        for (int i = 0; i < 128; i += 8) {
           mx = fmax3(mx, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
           mx1 = fmax3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
         }
-        mx = fmaxf(mx, mx1);
+        mx = fmaxf(fmaxf(mx, mx1), fmaxf(mx2, mx3));
       } else {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -643,6 +645,11 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       float s0 = 0.f, s1 = 0.f;
       if (valid == AT2_BKV) {
         const float2 nmb2 = make_float2(-mb, -mb);
+        const float2 one2 = make_float2(1.f, 1.f);
+        // row sums: packed fp32 adds (one FFMA2 per element pair instead of two FADDs) on four
+        // independent accumulator pairs, so no add waits for the previous one
+        float2 acc2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f),
+                          make_float2(0.f, 0.f)};
 #pragma unroll
         for (int i = 0; i < 128; i += 2) {
           const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
@@ -655,9 +662,10 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
             e.y = ex2_approx(a.y);
           }
           pk[i >> 1] = pack_bf16x2(e.x, e.y);
-          s0 += e.x;
-          s1 += e.y;
+          acc2[(i >> 1) & 3] = ffma2(e, one2, acc2[(i >> 1) & 3]);
         }
+        s0 = (acc2[0].x + acc2[1].x) + (acc2[2].x + acc2[3].x);
+        s1 = (acc2[0].y + acc2[1].y) + (acc2[2].y + acc2[3].y);
       } else {
 #pragma unroll
         for (int i = 0; i < 128; i += 2) {
@@ -736,8 +744,271 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   }
 }
 
+// =================================================================================================
+// Third kernel: few keys (nkv <= 128: the 77 text tokens of every attn2, sgm/modules/attention.py:
+// 352-425 with context = text embedding, and of reference_attn's attn2 over the ray samples, :571-598).
+// One (128-query tile, head, batch) item is ~0.6 MFLOP: the two kernels above spend a whole CTA
+// life (barrier init, TMEM allocation, descriptor fetch, three TMA round trips, teardown: ~8 us) on
+// each.  This one is PERSISTENT: one CTA per SM (320 threads) walks a static list of items,
+//   warp 0  TMA producer: ring of up to 6 x (Q 128x64, K NK x 64, V NK x 64), NK = nkv rounded up
+//           (rows >= nkv are zero-filled by TMA and masked in the softmax)
+//   warp 1  tcgen05.mma issuer: S(n) = Q K^T (N = NK) into TMEM buffer n & 1; O(n) = P(n) V with P
+//           read from TMEM (TS mode) as soon as the softmax group has written it
+//   warps 2-5 / 6-9  softmax group 0 / 1 (items n even / odd): one thread per query row: S ->
+//           registers, exp2, bf16 P -> TMEM, row sum in registers, then O / l -> bf16 -> global.
+// The two groups alternate items, so one group's exponentials overlap the other's MMA round trips.
+// =================================================================================================
+constexpr int SK_THREADS = 320;
+constexpr uint32_t SK_TMEM_COLS = 512;     // two buffers x (S 128 | P 64 | O 64)
+constexpr uint32_t SK_BUF_COLS = 256;
+constexpr uint32_t SK_COL_P = 128;
+constexpr uint32_t SK_COL_O = 192;
+
+template <int NK>
+struct SkSmem {
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int KV_BYTES = NK * 128;                           // one of K / V (TMA box)
+  static constexpr int KV_STRIDE = (KV_BYTES + 1023) / 1024 * 1024;   // tiles stay 1024 B aligned
+  static constexpr int STAGE_BYTES = Q_BYTES + 2 * KV_STRIDE;
+  // a stage is held from the TMA issue until the item's P V retires (HBM latency + the wait for the
+  // softmax group + two MMA round trips, ~4-5 us): the ring depth bounds the item rate (3 stages:
+  // one item per 1.7 us per SM on the 98304-query FeatureNeRF shape), so use what shared memory allows
+  static constexpr int STAGES = (220 * 1024 / STAGE_BYTES) < 6 ? (220 * 1024 / STAGE_BYTES) : 6;
+  static constexpr int BAR = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR + 256;
+  static_assert(TOTAL <= 227 * 1024, "smem budget");
+};
+
+template <int NK>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                 const __grid_constant__ CUtensorMap tmK,
+                                 const __grid_constant__ CUtensorMap tmV, const AttnParams p,
+                                 const int q_tiles, const int num_items) {
+  static_assert(NK % 16 == 0 && NK >= 16 && NK <= 128, "key tile");
+  using L = SkSmem<NK>;
+  constexpr int SK_STAGES = L::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
+  uint64_t* st_full = bars + 0;                 // [SK_STAGES] Q/K/V of an item landed
+  uint64_t* st_empty = st_full + SK_STAGES;     // [SK_STAGES] both MMAs of the item retired
+  uint64_t* s_full = st_empty + SK_STAGES;      // [2] S(n) complete in TMEM buffer n & 1
+  uint64_t* s_free = s_full + 2;                // [2] the group holds S(n) in registers
+  uint64_t* p_full = s_free + 2;                // [2] P(n) written to TMEM (and O(n-2) read out)
+  uint64_t* o_full = p_full + 2;                // [2] O(n) = P(n) V retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  // items of this CTA: blockIdx.x, + gridDim.x, ...; item = (batch * heads + head) * q_tiles + q_tile
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_items = first < num_items ? (num_items - first + stride - 1) / stride : 0;
+
+  CD360_TL(1);
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("cd360 attention: dynamic smem base not 1024-aligned\n");
+      __trap();
+    }
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SK_STAGES; ++s) {
+      mbar_init(&st_full[s], 1);
+      mbar_init(&st_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_free[b], 4);
+      mbar_init(&p_full[b], 4);
+      mbar_init(&o_full[b], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, SK_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    for (int n = 0; n < my_items; ++n) {
+      const int item = first + n * stride;
+      const int stage = n % SK_STAGES;
+      mbar_wait(&st_empty[stage], ((n / SK_STAGES) & 1) ^ 1);
+      const int q_tile = item % q_tiles;
+      const int bh = item / q_tiles;
+      const int head = bh % p.heads, batch = bh / p.heads;
+      uint8_t* sq = smem + stage * L::STAGE_BYTES;
+      uint8_t* sk = sq + L::Q_BYTES;
+      uint8_t* sv = sk + L::KV_STRIDE;
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&st_full[stage], L::Q_BYTES + 2 * L::KV_BYTES);
+        tma_load_4d(sq, &tmQ, &st_full[stage], 0, head, q_tile * 128, batch);
+        tma_load_4d(sk, &tmK, &st_full[stage], 0, head, 0, batch);
+        tma_load_4d(sv, &tmV, &st_full[stage], 0, head, 0, batch);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, NK, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_D, true);   // V is MN-major
+    auto poll = [&](uint64_t* bar, uint32_t parity) -> bool {
+      return __all_sync(0xffffffffu, mbar_try_wait(bar, parity)) != 0;
+    };
+    int next_s = 0, next_pv = 0;
+    long long t_idle = clock64();
+    while (next_pv < my_items) {
+      bool progress = false;
+      if (next_s < my_items) {   // S(n): stage landed, S(n-2) of this TMEM buffer read by its group
+        const int n = next_s, b = n & 1, stage = n % SK_STAGES;
+        if ((n < 2 || poll(&s_free[b], ((n - 2) >> 1) & 1)) && poll(&st_full[stage], (n / SK_STAGES) & 1)) {
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t k_addr = q_addr + L::Q_BYTES;
+          const uint32_t d_s = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < ATT_D / 16; ++k)
+              umma_bf16(d_s, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                        idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[b]);
+          }
+          __syncwarp();
+          next_s = n + 1;
+          progress = true;
+        }
+      }
+      if (next_pv < next_s) {    // O(n) = P(n) V(n)
+        const int n = next_pv, b = n & 1, stage = n % SK_STAGES;
+        if (poll(&p_full[b], (n >> 1) & 1)) {
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem + stage * L::STAGE_BYTES) + L::Q_BYTES + L::KV_STRIDE;
+          const uint32_t t_p = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS + SK_COL_P;
+          const uint32_t t_o = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS + SK_COL_O;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < NK / 16; ++k)   // 16 keys = 8 TMEM columns of packed bf16 pairs
+              umma_bf16_ts(t_o, t_p + k * 8, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
+                           k != 0 ? 1u : 0u);
+            umma_commit(&o_full[b]);
+            umma_commit(&st_empty[stage]);
+          }
+          __syncwarp();
+          next_pv = n + 1;
+          progress = true;
+        }
+      }
+      if (progress) {
+        t_idle = clock64();
+      } else if (clock64() - t_idle > 8000000000LL) {
+        printf("cd360 attention (small kv): MMA issuer starved (block %d)\n", blockIdx.x);
+        __trap();
+      }
+    }
+  } else {
+    // ================================ softmax / output ================================
+    const int g = (warp - 2) >> 2;   // group == TMEM buffer == item parity
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;   // row inside the query tile == TMEM lane
+    const uint32_t t_buf = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g) * SK_BUF_COLS;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    for (int n = g; n < my_items; n += 2) {
+      const int item = first + n * stride;
+      const uint32_t ph = (n >> 1) & 1;
+      mbar_wait(&s_full[g], ph);
+      tc_fence_after();
+      uint32_t r[NK];
+#pragma unroll
+      for (int c = 0; c < NK / 16; ++c)
+        tmem_ld_32x32b_x16(t_buf + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&r[c * 16]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+      float mx = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NK; i += 2) {
+        if (i < p.nkv) mx = fmaxf(mx, __uint_as_float(r[i]));
+        if (i + 1 < p.nkv) mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+      }
+      mx = fmaxf(mx, mx1);
+      const float mb = mx * p.scale_log2;
+      const float2 nmb2 = make_float2(-mb, -mb);
+      uint32_t pk[NK / 2];
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NK; i += 2) {
+        const float2 a = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nmb2);
+        float e0 = ex2_approx(a.x), e1 = ex2_approx(a.y);
+        if (i >= p.nkv) e0 = 0.f;
+        if (i + 1 >= p.nkv) e1 = 0.f;
+        pk[i >> 1] = pack_bf16x2(e0, e1);
+        s0 += e0;
+        s1 += e1;
+      }
+      // bf16 P row -> TMEM (column c holds keys 2c, 2c+1): A operand of the P V MMA.  (P(n-2) V retired
+      // before this group's epilogue of item n-2, so the columns are free.)
+#pragma unroll
+      for (int c = 0; c < NK / 32; ++c)
+        tmem_st_32x32b_x16(t_buf + SK_COL_P + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
+      if (NK % 32)
+        tmem_st_32x32b_x8(t_buf + SK_COL_P + (NK / 32) * 16, *reinterpret_cast<uint32_t(*)[8]>(&pk[(NK / 32) * 16]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      const float inv = 1.f / (s0 + s1);
+      // ---- O / l -> bf16 -> global
+      const int q_tile = item % q_tiles;
+      const int bh = item / q_tiles;
+      const int head = bh % p.heads, batch = bh / p.heads;
+      const int qrow = q_tile * 128 + row;
+      __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
+      mbar_wait(&o_full[g], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(t_buf + SK_COL_O + c * 32, t);
+        tmem_ld_wait();
+        if (qrow < p.nq) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(t[8 * gg + 0]) * inv, __uint_as_float(t[8 * gg + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(t[8 * gg + 2]) * inv, __uint_as_float(t[8 * gg + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(t[8 * gg + 4]) * inv, __uint_as_float(t[8 * gg + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(t[8 * gg + 6]) * inv, __uint_as_float(t[8 * gg + 7]) * inv);
+            d4[gg] = u;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, SK_TMEM_COLS);
+  }
+}
+
 int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, bool l2_256);
+int num_sms();
 
 static int make_qkv_map(CUtensorMap* tm, const void* base, long long ld, int heads, int n,
                         int batch, int box_rows) {
@@ -777,12 +1048,49 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
   p.heads = heads;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   // Kernel choice: the ping-pong kernel (one CTA per SM, two query tiles, 128-key tiles, P through
-  // TMEM) for long key sequences — 221 vs 252 us on level-1 self-attention, 41 vs 46 us on level 2 —
-  // and the two-CTAs-per-SM kernel for short ones (77 text keys fill 60 % of a 128-key tile: 19.5
-  // vs 18.4 us).  CD360_ATT_KERNEL=1|2 forces one (read per call so tests can switch).
+  // TMEM) for long key sequences, the persistent few-keys kernel for nkv <= 128 (text cross-attention).
+  // The first kernel (two CTAs per SM, 64-key tiles) remains selectable: CD360_ATT_KERNEL=1|2|3 forces
+  // one (read per call so tests can switch).
   const char* which_env = getenv("CD360_ATT_KERNEL");
-  int which = nkv > 128 ? 2 : 1;
-  if (which_env != nullptr && (which_env[0] == '1' || which_env[0] == '2')) which = which_env[0] - '0';
+  int which = nkv > 128 ? 2 : 3;
+  if (which_env != nullptr && which_env[0] >= '1' && which_env[0] <= '3') which = which_env[0] - '0';
+  if (which == 3 && nkv > 128) which = 2;
+  if (which == 3) {
+    // persistent few-keys kernel: NK = key-tile rows (TMA box; rows >= nkv zero-filled and masked)
+    const int NK = nkv <= 32 ? 32 : nkv <= 64 ? 64 : nkv <= 80 ? 80 : 128;
+    int rc3 = make_qkv_map(&tq, q, ldq, heads, nq, batch, 128);
+    if (rc3 != CD360_OK) return rc3;
+    rc3 = make_qkv_map(&tk, k, ldk, heads, nkv, batch, NK);
+    if (rc3 != CD360_OK) return rc3;
+    rc3 = make_qkv_map(&tv, v, ldv, heads, nkv, batch, NK);
+    if (rc3 != CD360_OK) return rc3;
+    const int q_tiles = (nq + 127) / 128;
+    const long long items = static_cast<long long>(q_tiles) * heads * batch;
+    if (items > 0x7fffffffLL) return CD360_ERR_SHAPE;
+    int ctas = num_sms();
+    if (items < ctas) ctas = static_cast<int>(items);
+    typedef void (*AttnKern3)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams, int, int);
+    AttnKern3 k3;
+    int smem3;
+    switch (NK) {
+      case 32: k3 = attention_smallkv_tcgen05_kernel<32>; smem3 = SkSmem<32>::TOTAL; break;
+      case 64: k3 = attention_smallkv_tcgen05_kernel<64>; smem3 = SkSmem<64>::TOTAL; break;
+      case 80: k3 = attention_smallkv_tcgen05_kernel<80>; smem3 = SkSmem<80>::TOTAL; break;
+      default: k3 = attention_smallkv_tcgen05_kernel<128>; smem3 = SkSmem<128>::TOTAL; break;
+    }
+    static bool attr3[4] = {false, false, false, false};
+    const int slot = NK == 32 ? 0 : NK == 64 ? 1 : NK == 80 ? 2 : 3;
+    if (!attr3[slot]) {
+      if (cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3) != cudaSuccess)
+        return CD360_ERR_LAUNCH;
+      attr3[slot] = true;
+    }
+    if (launch_ex(k3, dim3(ctas), dim3(SK_THREADS), smem3, stream, 1, tq, tk, tv, p, q_tiles,
+                  static_cast<int>(items)) != cudaSuccess)
+      return CD360_ERR_LAUNCH;
+    CD360_CHECK_LAUNCH();
+    return CD360_OK;
+  }
   if (which == 2) {
     int rc2 = make_qkv_map(&tq, q, ldq, heads, nq, batch, 256);
     if (rc2 != CD360_OK) return rc2;

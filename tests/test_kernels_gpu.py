@@ -259,11 +259,15 @@ def test_conv3x3(B, H, W, Cin, Cout):
     (3, 4, 256, 77),          # text cross-attention: masked KV tail
     (1, 2, 64, 200),          # ragged queries and keys
     (2, 20, 384, 77),
+    (2, 3, 200, 20),          # few keys, ragged queries
+    (1, 2, 1000, 50),
+    (1, 5, 3000, 77),         # more items than SMs: a persistent CTA walks several
 ])
-@pytest.mark.parametrize("kernel", ["1", "2"])
+@pytest.mark.parametrize("kernel", ["1", "2", "3"])
 def test_attention(batch, heads, nq, nkv, kernel, monkeypatch):
-    """kernel 1: default (two CTAs per SM, 64-key tiles); kernel 2: opt-in ping-pong kernel (one CTA
-    per SM, two query tiles, 128-key tiles), selected per call through CD360_ATT_KERNEL."""
+    """kernel 1: two CTAs per SM, 64-key tiles; kernel 2: ping-pong kernel (one CTA per SM, two query
+    tiles, 128-key tiles; the default for nkv > 128); kernel 3: persistent few-keys kernel (default for
+    nkv <= 128, falls back to 2 above that), selected per call through CD360_ATT_KERNEL."""
     from custom_diffusion360_b200 import ops
     monkeypatch.setenv("CD360_ATT_KERNEL", kernel)
     torch.manual_seed(5)
