@@ -395,8 +395,14 @@ attention_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
 // =================================================================================================
 // Second kernel: one CTA per SM, TWO query tiles (256 queries) ping-ponging over 128-key tiles.
 //   warp 0 (1 thread)  TMA producer: Q (2 x 128 rows) once, then a 3-stage ring of (K_j, V_j), 128 keys
-//   warp 1 (1 thread)  tcgen05.mma issuer: S_t(j+1) = Q_t K_{j+1}^T as soon as group t has READ S_t(j)
-//                      out of TMEM, O_t += P_t(j) V_j when P_t(j) is in TMEM
+//   warp 1             tcgen05.mma issuer (event loop over both query tiles): S_t(j+1) = Q_t K_{j+1}^T as
+//                      soon as group t has READ S_t(j) out of TMEM, O_t += P_t(j) V_j when P_t(j) is in TMEM.
+//                      Measured alternatives (tools/attn_trace.py, level-1 self-attention): one issuer warp
+//                      per query tile with blocking waits 215 us (the two groups fall into lockstep and
+//                      their exponentials collide on the MUFU), non-blocking mbarrier.test_wait probes
+//                      221 us (the polling warp takes issue slots from the softmax warps on its
+//                      scheduler); this loop with mbarrier.try_wait 190 us (the groups stay ~half a tile
+//                      apart, i.e. they actually ping-pong)
 //   warp 2             TMEM allocator (per query tile: 128 columns S, 64 columns bf16 P, 64 O)
 //   warps 4-7 / 8-11   softmax of query tile 0 / 1: one thread per row, whole 128-key row in registers
 // P never touches shared memory: the softmax threads tcgen05.st the bf16 probabilities into TMEM
@@ -749,16 +755,21 @@ attention_pingpong_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
 // 352-425 with context = text embedding, and of reference_attn's attn2 over the ray samples, :571-598).
 // One (128-query tile, head, batch) item is ~0.6 MFLOP: the two kernels above spend a whole CTA
 // life (barrier init, TMEM allocation, descriptor fetch, three TMA round trips, teardown: ~8 us) on
-// each.  This one is PERSISTENT: one CTA per SM (320 threads) walks a static list of items,
+// each.  This one is PERSISTENT: one CTA per SM (384 threads) walks a static list of items,
 //   warp 0  TMA producer: ring of up to 6 x (Q 128x64, K NK x 64, V NK x 64), NK = nkv rounded up
 //           (rows >= nkv are zero-filled by TMA and masked in the softmax)
-//   warp 1  tcgen05.mma issuer: S(n) = Q K^T (N = NK) into TMEM buffer n & 1; O(n) = P(n) V with P
-//           read from TMEM (TS mode) as soon as the softmax group has written it
-//   warps 2-5 / 6-9  softmax group 0 / 1 (items n even / odd): one thread per query row: S ->
-//           registers, exp2, bf16 P -> TMEM, row sum in registers, then O / l -> bf16 -> global.
+//   warps 1 / 2  tcgen05.mma issuer of the even / odd items: S(n) = Q K^T (N = NK) into TMEM buffer
+//           n & 1; O(n) = P(n) V with P read from TMEM (TS mode) as soon as its group has written it
+//           (blocking waits in the group's fixed event order, like the ping-pong kernel)
+//   warps 4-7 / 8-11  softmax group 0 / 1 (items n even / odd): one thread per query row: S ->
+//           registers, exp2, bf16 P -> TMEM, row sum in registers, then O / l -> bf16 -> the item's
+//           (dead) Q tile in shared memory -> one TMA store per warp (32 rows x 128 B).  Row-per-
+//           thread global stores (32 half-filled sectors per instruction, 8 instructions per item)
+//           bounded the item rate before.  A stage returns to the producer when the four warps'
+//           stores have finished reading it.
 // The two groups alternate items, so one group's exponentials overlap the other's MMA round trips.
 // =================================================================================================
-constexpr int SK_THREADS = 320;
+constexpr int SK_THREADS = 384;
 constexpr uint32_t SK_TMEM_COLS = 512;     // two buffers x (S 128 | P 64 | O 64)
 constexpr uint32_t SK_BUF_COLS = 256;
 constexpr uint32_t SK_COL_P = 128;
@@ -783,7 +794,8 @@ template <int NK>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
                                  const __grid_constant__ CUtensorMap tmK,
-                                 const __grid_constant__ CUtensorMap tmV, const AttnParams p,
+                                 const __grid_constant__ CUtensorMap tmV,
+                                 const __grid_constant__ CUtensorMap tmO, const AttnParams p,
                                  const int q_tiles, const int num_items) {
   static_assert(NK % 16 == 0 && NK >= 16 && NK <= 128, "key tile");
   using L = SkSmem<NK>;
@@ -791,7 +803,7 @@ attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR);
   uint64_t* st_full = bars + 0;                 // [SK_STAGES] Q/K/V of an item landed
-  uint64_t* st_empty = st_full + SK_STAGES;     // [SK_STAGES] both MMAs of the item retired
+  uint64_t* st_empty = st_full + SK_STAGES;     // [SK_STAGES] item done: O stores of its 4 warps have read the stage
   uint64_t* s_full = st_empty + SK_STAGES;      // [2] S(n) complete in TMEM buffer n & 1
   uint64_t* s_free = s_full + 2;                // [2] the group holds S(n) in registers
   uint64_t* p_full = s_free + 2;                // [2] P(n) written to TMEM (and O(n-2) read out)
@@ -814,11 +826,12 @@ attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < SK_STAGES; ++s) {
       mbar_init(&st_full[s], 1);
-      mbar_init(&st_empty[s], 1);
+      mbar_init(&st_empty[s], 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1);
@@ -828,7 +841,7 @@ attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 3) {
     tmem_alloc(tmem_ptr, SK_TMEM_COLS);
     tmem_relinquish();
   }
@@ -858,70 +871,55 @@ attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || warp == 2) {
+    // ================================ MMA issuers (even / odd items) ================================
+    const int g = warp - 1;
     constexpr uint32_t idesc_s = make_idesc_bf16(128, NK, false);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_D, true);   // V is MN-major
-    auto poll = [&](uint64_t* bar, uint32_t parity) -> bool {
-      return __all_sync(0xffffffffu, mbar_try_wait(bar, parity)) != 0;
+    const uint32_t d_s = tmem_base + static_cast<uint32_t>(g) * SK_BUF_COLS;
+    const uint32_t t_p = d_s + SK_COL_P;
+    const uint32_t t_o = d_s + SK_COL_O;
+    auto issue_s = [&](int n) {   // S(n) = Q K^T of item n
+      const int stage = n % SK_STAGES;
+      mbar_wait(&st_full[stage], (n / SK_STAGES) & 1);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+      const uint32_t k_addr = q_addr + L::Q_BYTES;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(d_s, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                    idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
     };
-    int next_s = 0, next_pv = 0;
-    long long t_idle = clock64();
-    while (next_pv < my_items) {
-      bool progress = false;
-      if (next_s < my_items) {   // S(n): stage landed, S(n-2) of this TMEM buffer read by its group
-        const int n = next_s, b = n & 1, stage = n % SK_STAGES;
-        if ((n < 2 || poll(&s_free[b], ((n - 2) >> 1) & 1)) && poll(&st_full[stage], (n / SK_STAGES) & 1)) {
-          tc_fence_after();
-          const uint32_t q_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t k_addr = q_addr + L::Q_BYTES;
-          const uint32_t d_s = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS;
-          if (elect_one_sync()) {
+    if (g < my_items) issue_s(g);
+    for (int n = g; n < my_items; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
+      if (n + 2 < my_items) {
+        mbar_wait(&s_free[g], ph);   // the group holds S(n) in registers
+        issue_s(n + 2);
+      }
+      mbar_wait(&p_full[g], ph);     // P(n) in TMEM (and O(n-2) read out)
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(smem + (n % SK_STAGES) * L::STAGE_BYTES) + L::Q_BYTES + L::KV_STRIDE;
+      if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < ATT_D / 16; ++k)
-              umma_bf16(d_s, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
-                        idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[b]);
-          }
-          __syncwarp();
-          next_s = n + 1;
-          progress = true;
-        }
+        for (int k = 0; k < NK / 16; ++k)   // 16 keys = 8 TMEM columns of packed bf16 pairs
+          umma_bf16_ts(t_o, t_p + k * 8, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o, k != 0 ? 1u : 0u);
+        umma_commit(&o_full[g]);
       }
-      if (next_pv < next_s) {    // O(n) = P(n) V(n)
-        const int n = next_pv, b = n & 1, stage = n % SK_STAGES;
-        if (poll(&p_full[b], (n >> 1) & 1)) {
-          tc_fence_after();
-          const uint32_t v_addr = smem_u32(smem + stage * L::STAGE_BYTES) + L::Q_BYTES + L::KV_STRIDE;
-          const uint32_t t_p = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS + SK_COL_P;
-          const uint32_t t_o = tmem_base + static_cast<uint32_t>(b) * SK_BUF_COLS + SK_COL_O;
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int k = 0; k < NK / 16; ++k)   // 16 keys = 8 TMEM columns of packed bf16 pairs
-              umma_bf16_ts(t_o, t_p + k * 8, make_smem_desc_sw128(v_addr + k * 16 * 128), idesc_o,
-                           k != 0 ? 1u : 0u);
-            umma_commit(&o_full[b]);
-            umma_commit(&st_empty[stage]);
-          }
-          __syncwarp();
-          next_pv = n + 1;
-          progress = true;
-        }
-      }
-      if (progress) {
-        t_idle = clock64();
-      } else if (clock64() - t_idle > 8000000000LL) {
-        printf("cd360 attention (small kv): MMA issuer starved (block %d)\n", blockIdx.x);
-        __trap();
-      }
+      __syncwarp();
     }
-  } else {
+  } else if (warp >= 4) {
     // ================================ softmax / output ================================
-    const int g = (warp - 2) >> 2;   // group == TMEM buffer == item parity
+    const int g = (warp - 4) >> 2;   // group == TMEM buffer == item parity
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;   // row inside the query tile == TMEM lane
     const uint32_t t_buf = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(g) * SK_BUF_COLS;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    int pending_stage = -1;   // stage whose O store (issued by this warp) may still be reading shared memory
     for (int n = g; n < my_items; n += 2) {
       const int item = first + n * stride;
       const uint32_t ph = (n >> 1) & 1;
@@ -968,39 +966,63 @@ attention_smallkv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ,
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
       const float inv = 1.f / (s0 + s1);
-      // ---- O / l -> bf16 -> global
+      // ---- O / l -> bf16 -> this warp's 32 rows of the item's Q tile (dead since S(n) retired) -> TMA store
       const int q_tile = item % q_tiles;
       const int bh = item / q_tiles;
       const int head = bh % p.heads, batch = bh / p.heads;
-      const int qrow = q_tile * 128 + row;
-      __nv_bfloat16* dst = p.o + (static_cast<long long>(batch) * p.nq + qrow) * p.ldo + head * ATT_D;
+      const int stage = n % SK_STAGES;
+      uint8_t* orow = smem + stage * L::STAGE_BYTES + row * 128;
+      const int sw = row & 7;
       mbar_wait(&o_full[g], ph);
       tc_fence_after();
+      // the previous store of this warp (item n-2) must have finished reading its stage: hand that stage
+      // back to the producer (deferred by one item so that nobody waits for the TMA engine)
+      if (pending_stage >= 0) {
+        if (elect_one_sync()) {
+          tma_store_wait_read();
+          mbar_arrive(&st_empty[pending_stage]);
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t t[32];
         tmem_ld_32x32b_x32(t_buf + SK_COL_O + c * 32, t);
         tmem_ld_wait();
-        if (qrow < p.nq) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(t[8 * gg + 0]) * inv, __uint_as_float(t[8 * gg + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(t[8 * gg + 2]) * inv, __uint_as_float(t[8 * gg + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(t[8 * gg + 4]) * inv, __uint_as_float(t[8 * gg + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(t[8 * gg + 6]) * inv, __uint_as_float(t[8 * gg + 7]) * inv);
-            d4[gg] = u;
-          }
+        for (int gg = 0; gg < 4; ++gg) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(t[8 * gg + 0]) * inv, __uint_as_float(t[8 * gg + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(t[8 * gg + 2]) * inv, __uint_as_float(t[8 * gg + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(t[8 * gg + 4]) * inv, __uint_as_float(t[8 * gg + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(t[8 * gg + 6]) * inv, __uint_as_float(t[8 * gg + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + (((c * 4 + gg) ^ sw) << 4)) = u;
         }
       }
       tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      const uint8_t* wsrc = smem + stage * L::STAGE_BYTES + q * 32 * 128;
+      const int out_row = q_tile * 128 + q * 32;
+      if (elect_one_sync()) {
+        if (out_row < p.nq) tma_store_4d(&tmO, wsrc, 0, head, out_row, batch);   // rows >= nq are clipped
+        tma_store_commit();
+      }
+      __syncwarp();
+      pending_stage = stage;
+    }
+    if (pending_stage >= 0) {
+      if (elect_one_sync()) {
+        tma_store_wait_read();
+        mbar_arrive(&st_empty[pending_stage]);
+      }
+      __syncwarp();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tmem_base, SK_TMEM_COLS);
   }
@@ -1069,7 +1091,10 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
     if (items > 0x7fffffffLL) return CD360_ERR_SHAPE;
     int ctas = num_sms();
     if (items < ctas) ctas = static_cast<int>(items);
-    typedef void (*AttnKern3)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams, int, int);
+    CUtensorMap to;   // O [b, nq, heads, 64] like Q, box = one warp's 32 rows
+    rc3 = make_qkv_map(&to, o, ldo, heads, nq, batch, 32);
+    if (rc3 != CD360_OK) return rc3;
+    typedef void (*AttnKern3)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, AttnParams, int, int);
     AttnKern3 k3;
     int smem3;
     switch (NK) {
@@ -1085,7 +1110,7 @@ extern "C" int cd360_attention_bf16(const void* q, int64_t ldq, const void* k, i
         return CD360_ERR_LAUNCH;
       attr3[slot] = true;
     }
-    if (launch_ex(k3, dim3(ctas), dim3(SK_THREADS), smem3, stream, 1, tq, tk, tv, p, q_tiles,
+    if (launch_ex(k3, dim3(ctas), dim3(SK_THREADS), smem3, stream, 1, tq, tk, tv, to, p, q_tiles,
                   static_cast<int>(items)) != cudaSuccess)
       return CD360_ERR_LAUNCH;
     CD360_CHECK_LAUNCH();
