@@ -85,6 +85,7 @@ SIGNATURES = {
     "cd360_groupnorm_silu_bwd_bf16": (C.c_int, [_P, _I, _P, _I, _P, _P, _P, _P, _L, _P, _L, _P, _P, _P,
                                                 _I, _I, _F, _I, _P]),
     "cd360_geglu_bwd_bf16": (C.c_int, [_P, _P, _P, _L, _I, _I, _P]),
+    "cd360_geglu_fwd_bf16": (C.c_int, [_P, _P, _L, _I, _I, _P]),
     "cd360_add_bf16": (C.c_int, [_P, _P, _P, _L, _P]),
     "cd360_silu_bwd_f32": (C.c_int, [_P, _P, _P, _L, _P]),
     "cd360_transpose_to_bf16": (C.c_int, [_P, _I, _L, _P, _L, _I, _I, _P]),

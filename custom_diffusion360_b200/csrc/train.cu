@@ -284,6 +284,31 @@ geglu_bwd_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __r
   }
 }
 
+// GEGLU forward on a KEPT pre-activation (training: raw is saved for geglu_bwd instead of being
+// recomputed): h = a * gelu(gate), same [a | gate] block layout as above, exact erf like the reference's
+// F.gelu (attention.py:96).
+__global__ void __launch_bounds__(256)
+geglu_fwd_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ h, long long rows, int F,
+                 int blk) {
+  pdl_wait();
+  const int nvec = F >> 3;
+  const long long total = rows * nvec;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / nvec;
+    const int j = static_cast<int>(i - row * nvec) * 8;
+    const int t = j / blk, w = j - t * blk;
+    const long long ca = row * 2 * F + static_cast<long long>(t) * 2 * blk + w;
+    float a[8], gt[8], o[8];
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(raw + ca)), a);
+    unpack8f(__ldg(reinterpret_cast<const uint4*>(raw + ca + blk)), gt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      o[k] = a[k] * 0.5f * gt[k] * (1.0f + erff(gt[k] * 0.70710678118654752440f));
+    *reinterpret_cast<uint4*>(h + row * F + j) = pack8f(o);
+  }
+}
+
 // =================================================================================================
 // small layout / reduction helpers
 // =================================================================================================
@@ -987,6 +1012,18 @@ extern "C" int cd360_geglu_bwd_bf16(const void* raw, const void* dh, void* draw,
   launch_ex(geglu_bwd_kernel, dim3(grid_for(rows * (f / 8), 256)), dim3(256), 0,
             reinterpret_cast<cudaStream_t>(stream_), 1, CD360_BF(raw), CD360_BF(dh), CD360_BFW(draw),
             static_cast<long long>(rows), f, block);
+  CD360_CHECK_LAUNCH();
+  return CD360_OK;
+}
+
+extern "C" int cd360_geglu_fwd_bf16(const void* raw, void* h, int64_t rows, int32_t f, int32_t block,
+                                    cd360_stream_t stream_) {
+  if (!raw || !h) return CD360_ERR_NULL;
+  if (rows <= 0 || f <= 0 || (f & 7) || block <= 0 || (block & 7) || (f % block) != 0) return CD360_ERR_SHAPE;
+  if (CD360_MISALIGNED(raw) || CD360_MISALIGNED(h)) return CD360_ERR_ALIGN;
+  launch_ex(geglu_fwd_kernel, dim3(grid_for(rows * (f / 8), 256)), dim3(256), 0,
+            reinterpret_cast<cudaStream_t>(stream_), 1, CD360_BF(raw), CD360_BFW(h), static_cast<long long>(rows), f,
+            block);
   CD360_CHECK_LAUNCH();
   return CD360_OK;
 }

@@ -601,6 +601,19 @@ def geglu_bwd(raw, dh, block=None):
     return out
 
 
+@_op("geglu_fwd")
+def geglu_fwd(raw, block=None):
+    """raw bf16 [rows, 2f] ([a | gate] in blocks of `block` columns) -> bf16 [rows, f] = a * gelu(gate)."""
+    lib = _lib.load()
+    _req(raw, bf16, "raw")
+    rows, f2 = raw.shape
+    f = f2 // 2
+    out = torch.empty((rows, f), device=raw.device, dtype=bf16)
+    check(lib.cd360_geglu_fwd_bf16(_ptr(raw), _ptr(out), rows, f, f if block is None else block, _stream()),
+          "cd360_geglu_fwd_bf16")
+    return out
+
+
 @_op("add")
 def add_bf16(a, b, *, out=None):
     lib = _lib.load()

@@ -252,24 +252,41 @@ def nerf_backward(block: BasicTransformerBlock, sv, d_rendered, daux):
 # ------------------------------------------------------------------------------------------------
 # BasicTransformerBlock
 # ------------------------------------------------------------------------------------------------
-def block_forward(block: BasicTransformerBlock, x, batch, n, kv, nctx, cams=None, jitter=None):
+def block_forward(block: BasicTransformerBlock, x, batch, n, kv, nctx, cams=None, jitter=None, stats=None):
     """Taped `BasicTransformerBlock._forward` (attention.py:600-637) in token layout.  Residual
-    updates are out of place: every saved tensor stays valid until the backward."""
+    updates are out of place: every saved tensor stays valid until the backward.
+    stats: fp32 [M, c/64, 2] row moments of x written by the GEMM that produced x -> the three
+    LayerNorms are folded into the consuming GEMMs' epilogues (attention.BasicTransformerBlock.ln_packed,
+    same algebra as the sampling path); None -> stand-alone LayerNorm kernels.  Returns
+    (x4, aux, saved, stats of x4 | None)."""
     a1, a2 = block.attn1, block.attn2
     p1, p2 = a1.packed(), a2.packed()
     inner = a1.heads * a1.dim_head
-    qkv = ops.gemm(block.norm1.tokens(x), p1["wqkv"])
+    M, c = x.shape
+    fused = stats is not None
+    eps = block.norm1.eps
+    new_stats = (lambda: torch.empty((M, c // 64, 2), device=x.device, dtype=f32)) if fused else (lambda: None)
+    lp = block.ln_packed() if fused else None
+    if fused:
+        qkv = ops.gemm(x, lp["wqkv"], bias=lp["bqkv"], ln_stats=stats, ln_colsum=lp["cqkv"], ln_eps=eps)
+    else:
+        qkv = ops.gemm(block.norm1.tokens(x), p1["wqkv"])
     att1 = ops.attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], batch, a1.heads, n, n,
                          ldq=3 * inner, ldk=3 * inner, ldv=3 * inner)
-    x1 = ops.gemm(att1, p1["wo"], bias=p1["bo"], residual=x)
-    q2 = ops.gemm(block.norm2.tokens(x1), p2["wq"])
+    st1 = new_stats()
+    x1 = ops.gemm(att1, p1["wo"], bias=p1["bo"], residual=x, stats_out=st1)
+    if fused:
+        q2 = ops.gemm(x1, lp["wq2"], bias=lp["bq2"], ln_stats=st1, ln_colsum=lp["cq2"], ln_eps=eps)
+    else:
+        q2 = ops.gemm(block.norm2.tokens(x1), p2["wq"])
     k2, v2 = kv[:, :inner], kv[:, inner:2 * inner]
     att2 = ops.attention(q2, k2, v2, batch, a2.heads, n, nctx, ldq=inner, ldk=kv.stride(0), ldv=kv.stride(0))
-    x2 = ops.gemm(att2, p2["wo"], bias=p2["bo"], residual=x1)
+    st2 = new_stats()
+    x2 = ops.gemm(att2, p2["wo"], bias=p2["bo"], residual=x1, stats_out=st2)
     sv = NS(x0=x, qkv=qkv, att1=att1, x1=x1, q2=q2, k2=k2, v2=v2, att2=att2, x2=x2, batch=batch, n=n,
             nctx=nctx, inner=inner, nerf=None, rendered=None)
     aux = None
-    x3 = x2
+    x3, st3 = x2, st2
     if block.image_cross and cams is not None:
         pre = _FWD.get(id(block))
         if pre is not None:      # FeatureNeRF already enqueued on its own stream (unet_forward)
@@ -281,10 +298,21 @@ def block_forward(block: BasicTransformerBlock, x, batch, n, kv, nctx, cams=None
             rendered, aux, sv.nerf = nerf_forward(block, cams, xref_tok, n_views, kv, nctx, batch, n,
                                                   next(jitter) if jitter is not None else None)
         sv.rendered = rendered
-        x3 = block.pose_emb_layers.tokens(x2, a1=rendered)
+        st3 = new_stats()
+        x3 = block.pose_emb_layers.tokens(x2, a1=rendered, stats_out=st3)
     sv.x3 = x3
-    x4 = block.ff.tokens(block.norm3.tokens(x3), residual=x3)
-    return x4, aux, sv
+    # feed-forward.  The GEGLU pre-activation is KEPT (bf16 [M, 8c], packed column order) instead of being
+    # recomputed in the backward: one elementwise launch here replaces a LayerNorm + an [M, 8c, c] GEMM there.
+    ffp = block.ff.net[0].packed()
+    if fused:
+        raw = ops.gemm(x3, lp["wff"], bias=lp["bff"], ln_stats=st3, ln_colsum=lp["cff"], ln_eps=eps)
+    else:
+        raw = ops.gemm(block.norm3.tokens(x3), ffp["w"], bias=ffp["b"])
+    sv.ff_raw = raw
+    h = ops.geglu_fwd(raw, ops.geglu_pack_block(raw.shape[1]))
+    st4 = new_stats()
+    x4 = block.ff.net[2].tokens(h, residual=x3, stats_out=st4)
+    return x4, aux, sv, st4
 
 
 def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
@@ -295,10 +323,8 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
     blk = ops.geglu_pack_block(ff.net[0].proj.out_features)
     # ---- feed-forward: x4 = x3 + W2 geglu(Wff LN3(x3) + bff) + b2
     dh = ops.gemm(g, bp["w2_t"])
-    pk = ff.net[0].packed()
-    raw = ops.gemm(block.norm3.tokens(sv.x3), pk["w"], bias=pk["b"])        # recomputed, packed column order
-    draw = ops.geglu_bwd(raw, dh, blk)
-    del raw, dh
+    draw = ops.geglu_bwd(sv.ff_raw, dh, blk)          # pre-activation kept by the forward (packed column order)
+    del dh
     g = ops.layernorm_bwd(sv.x3, bp["g3"], ops.gemm(draw, bp["wff_t"]), add=g, eps=block.norm3.eps)
     del draw
     # ---- pose_emb_layers: x3 = [x2 | rendered] Wp^T
@@ -354,13 +380,19 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
 def st_forward(st: SpatialTransformer, x, batch, hw, nctx, kv_all, cams, aux_out, jitter=None):
     p = st.packed()
     xn = ops.groupnorm(x, p["g"], p["b"], batch, hw, eps=st.norm.eps, silu=False)
-    h = st.proj_in.tokens(xn)
+    from .attention import LN_FUSED
+    stats = None
+    if LN_FUSED and st.in_channels % 64 == 0:   # proj_in's epilogue emits the row moments of the first LayerNorm
+        stats = torch.empty((xn.shape[0], st.in_channels // 64, 2), device=xn.device, dtype=f32)
+        h = st.proj_in.tokens(xn, stats_out=stats)
+    else:
+        h = st.proj_in.tokens(xn)
     saved = []
     for i, block in enumerate(st.transformer_blocks):
         use_pose = st.image_cross and (i % st.poscontrol_interval == 0)
         off, width = block.__dict__["_kv_slice"]
-        h, aux, sv = block_forward(block, h, batch, hw, kv_all[:, off:off + width], nctx,
-                                   cams if use_pose else None, jitter)
+        h, aux, sv, stats = block_forward(block, h, batch, hw, kv_all[:, off:off + width], nctx,
+                                          cams if use_pose else None, jitter, stats=stats)
         if aux is not None:
             aux_out.append((block, aux))
         saved.append(sv)

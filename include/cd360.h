@@ -363,6 +363,12 @@ int cd360_groupnorm_silu_bwd_bf16(const void* x0, int32_t c0, const void* x1, in
 int cd360_geglu_bwd_bf16(const void* raw, const void* dh, void* draw, int64_t rows, int32_t f,
                          int32_t block, cd360_stream_t stream);
 
+/* GEGLU forward from a KEPT pre-activation (training: raw is saved for cd360_geglu_bwd_bf16 instead of
+ * being recomputed): raw bf16 [rows, 2f] in the same block layout -> h bf16 [rows, f] = a * gelu(gate)
+ * (attention.py:94-96, exact erf). */
+int cd360_geglu_fwd_bf16(const void* raw, void* h, int64_t rows, int32_t f, int32_t block,
+                         cd360_stream_t stream);
+
 /* out = a + b, bf16, n % 8 == 0 (sum of the gradients arriving at a skip connection,
  * openaimodel.py:1074). */
 int cd360_add_bf16(const void* a, const void* b, void* out, int64_t n, cd360_stream_t stream);
