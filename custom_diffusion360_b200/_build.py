@@ -23,6 +23,7 @@ SOURCES = [
     "elementwise.cu",
     "nerf.cu",
     "attention_bwd.cu",
+    "attention_bwd_tcgen05.cu",
     "train.cu",
     "vae.cu",
     "conditioner.cu",

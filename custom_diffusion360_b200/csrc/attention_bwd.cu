@@ -23,6 +23,22 @@
 namespace cd360 {
 namespace wm = nvcuda::wmma;
 
+// attention_bwd_tcgen05.cu: the tcgen05 / TMEM kernels (default path).  which: bit 0 = dQ + statistics,
+// bit 1 = dK / dV (nsplit > 1: partial sums into kv_acc).
+int attention_bwd_tcgen05(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                          const void* o, long long ldo, const void* dout, long long lddo, void* dq, long long lddq,
+                          void* dk, long long lddk, void* dv, long long lddv, float* lse, float* dsum, float* kv_acc,
+                          int batch, int heads, int nq, int nkv, int nsplit, int which, cudaStream_t stream);
+// 0: tcgen05 (default), 1: mma.sync kernels of this file (CD360_ATTBWD=mma), 2: first-generation wmma
+// kernels (CD360_ATTBWD=wmma); read per call so tests can switch
+static int attn_bwd_impl() {
+  const char* e = getenv("CD360_ATTBWD");
+  if (e == nullptr) return 0;
+  if (e[0] == 'm') return 1;
+  if (e[0] == 'w') return 2;
+  return 0;
+}
+
 constexpr int AB_T = 64;     // tile edge: queries / keys / head dim
 constexpr int AB_LD = 72;    // bf16 smem row stride (elements): 144 B rows, fragment loads stay 32 B aligned
 constexpr int AB_LDF = 68;   // fp32 smem row stride
@@ -676,12 +692,12 @@ extern "C" int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* 
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.nq = nq; p.nkv = nkv; p.heads = heads;
   p.scale = 0.125f;
+  const int impl = attn_bwd_impl();
+  if (impl == 0)
+    return attention_bwd_tcgen05(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, dq, lddq, dk, lddk, dv, lddv, lse, dsum,
+                                 nullptr, batch, heads, nq, nkv, 1, dk != nullptr ? 3 : 1, stream);
   const dim3 gq((nq + AB_T - 1) / AB_T, heads, batch);
-  static int use_wmma = -1;   // CD360_ATTBWD=wmma selects the first-generation kernels (A/B, debugging)
-  if (use_wmma < 0) {
-    const char* e = getenv("CD360_ATTBWD");
-    use_wmma = (e != nullptr && e[0] == 'w') ? 1 : 0;
-  }
+  const int use_wmma = impl == 2;
   if (!use_wmma) {
     if (launch_ex(attention_bwd_dq_mma_kernel, gq, dim3(AB_THREADS), 0, stream, 1, p) != cudaSuccess)
       return CD360_ERR_LAUNCH;
@@ -733,13 +749,20 @@ extern "C" int cd360_attention_bwd_kv_split_bf16(const void* q, int64_t ldq, con
   p.dsum = const_cast<float*>(dsum);
   p.nq = nq; p.nkv = nkv; p.heads = heads;
   p.scale = 0.125f;
-  const int key_tiles = (nkv + AB_T - 1) / AB_T;
-  const int q_tiles = (nq + AB_T - 1) / AB_T;
-  if (nsplit > q_tiles) nsplit = q_tiles;
-  const dim3 gk(static_cast<unsigned>(key_tiles * nsplit), heads, batch);
-  if (launch_ex(attention_bwd_dkdv_mma_kernel<1>, gk, dim3(AB_THREADS), 0, stream, 1, p, kv_acc, nsplit) !=
-      cudaSuccess)
-    return CD360_ERR_LAUNCH;
+  if (attn_bwd_impl() == 0) {
+    const int rc = attention_bwd_tcgen05(q, ldq, k, ldk, v, ldv, nullptr, 0, dout, lddo, nullptr, 0, nullptr, 0, nullptr,
+                                         0, const_cast<float*>(lse), const_cast<float*>(dsum), kv_acc, batch, heads, nq,
+                                         nkv, nsplit, 2, stream);
+    if (rc != CD360_OK) return rc;
+  } else {
+    const int key_tiles = (nkv + AB_T - 1) / AB_T;
+    const int q_tiles = (nq + AB_T - 1) / AB_T;
+    if (nsplit > q_tiles) nsplit = q_tiles;
+    const dim3 gk(static_cast<unsigned>(key_tiles * nsplit), heads, batch);
+    if (launch_ex(attention_bwd_dkdv_mma_kernel<1>, gk, dim3(AB_THREADS), 0, stream, 1, p, kv_acc, nsplit) !=
+        cudaSuccess)
+      return CD360_ERR_LAUNCH;
+  }
   const long long rows = static_cast<long long>(batch) * nkv;
   const long long pairs = rows * heads * AB_T;   // 2 * rows * inner / 2
   unsigned blocks = static_cast<unsigned>((pairs + 255) / 256);

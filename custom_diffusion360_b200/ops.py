@@ -534,9 +534,9 @@ def attention_bwd(q, k, v, o, dout, batch, heads, nq, nkv, *, dq, dk=None, dv=No
     dev = q.device
     lse = torch.empty((batch, heads, nq), device=dev, dtype=f32)
     dsum = torch.empty((batch, heads, nq), device=dev, dtype=f32)
-    key_tiles, q_tiles = (nkv + 63) // 64, (nq + 63) // 64
+    key_tiles, q_tiles = (nkv + 127) // 128, (nq + 127) // 128      # 128 x 128 tiles (tcgen05 kernels)
     base_ctas = key_tiles * heads * batch
-    split = dk is not None and base_ctas < 148 and q_tiles >= 32
+    split = dk is not None and base_ctas < 148 and q_tiles >= 16
     LaunchStats.launches += 1 if dk is None else (3 if split else 2)  # stats + dq (+ dkdv (+ finish))
     check(lib.cd360_attention_bwd_bf16(
         _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0),
@@ -545,7 +545,7 @@ def attention_bwd(q, k, v, o, dout, batch, heads, nq, nkv, *, dq, dk=None, dv=No
         0 if dv is None or split else dv.stride(0), _ptr(lse), _ptr(dsum), batch, heads, nq, nkv,
         _stream()), "cd360_attention_bwd_bf16")
     if split:
-        nsplit = max(1, min(q_tiles // 4, (2 * 148) // base_ctas))
+        nsplit = max(1, min(q_tiles // 2, (2 * 148) // base_ctas))
         acc = torch.zeros((2, batch * nkv, heads * 64), device=dev, dtype=f32)
         check(lib.cd360_attention_bwd_kv_split_bf16(
             _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(dout), dout.stride(0),
