@@ -322,7 +322,7 @@ int cd360_softmax_rows_f32_bf16(const float* s, int64_t lds, void* out, int64_t 
  * are projections of the constant context).  lse / dsum: fp32 scratch [batch, heads, nq] (opaque per-query
  * statistics; only cd360_attention_bwd_kv_split_bf16 may consume them).  Runs on tcgen05 / TMEM
  * (csrc/attention_bwd_tcgen05.cu: 128 x 128 tiles, S / dP by SS MMAs, P / dS handed to the second MMA
- * through TMEM); CD360_ATTBWD=mma selects the earlier mma.sync kernels (A/B runs, debugging). */
+ * through TMEM). */
 int cd360_attention_bwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                              int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo,
                              void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
