@@ -42,9 +42,10 @@ def _hide_launch_latency(seconds: float):
 
 def ncu_traffic(kernel: str):
     """Average DRAM bytes (read + write) per launch of `kernel` in one steady-state step, from the
-    committed ncu launch list of this command (profiles/launches_r01_summary.json; dram__bytes_read.sum
-    + dram__bytes_write.sum per launch, tools/ncu_step_list.py).  None if the summary is absent."""
-    path = os.path.join(ROOT, "profiles", "launches_r01_summary.json")
+    COMMITTED ncu launch list of this command (profiles/launches_r02_summary.json; dram__bytes_read.sum
+    + dram__bytes_write.sum per launch, tools/ncu_step_list.py) — a capture of the same build taken under
+    ncu, not a measurement of this run.  None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", "launches_r02_summary.json")
     try:
         with open(path) as f:
             k = json.load(f)["kernels"]
@@ -758,7 +759,7 @@ def main():
                      "bound": "tensor", "achieved": gk.get("tflops"), "peak": peaks["burst"], "unit": "TFLOP/s",
                      "frac": (gk["tflops"] / peaks["burst"]) if gk.get("tflops") else None,
                      "traffic": ncu_traffic("gemm_bf16_tcgen05_kernel") if (args.latent == 128 and args.n_img == 1) else None,
-                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches)",
+                     "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches; committed capture profiles/launches_r02_summary.json, not measured in this run)",
                      "launches_per_step": gk.get("launches"), "algorithmic_tflop_per_step": gk.get("algorithmic_tflop"),
                      "kernel_ms_per_step": gk.get("ms"), "peak_source": peaks["source"] + " burst (kernel timed alone)"},
         "roofline_step": {"bound": "tensor", "algorithmic_tflop_per_step": tflop_step,

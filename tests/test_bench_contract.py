@@ -29,5 +29,5 @@ def test_reference_arm_line(monkeypatch, capsys):
 
 def test_ncu_traffic_reads_the_committed_summary():
     t = bench.ncu_traffic("gemm_bf16_tcgen05_kernel")
-    assert t is not None and 1e6 < t < 1e9               # DRAM bytes per launch, profiles/launches_r01_summary.json
+    assert t is not None and 1e6 < t < 1e9               # DRAM bytes per launch, profiles/launches_r02_summary.json
     assert bench.ncu_traffic("no_such_kernel") is None

@@ -2,7 +2,7 @@
 launch index inside the step, kernel, grid, block, duration (ns) and DRAM bytes.
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \\
-        -k regex:cd360 -c 4500 --csv --log-file gpurun_out/ncu_launches_raw.csv \\
+        -k regex:"gemm_bf16|attention_|groupnorm|small_linear|im2col|upsample2x|cfg_euler|timestep_emb|cast_|nerf_|layernorm|splitk" -c 4500 --csv --log-file gpurun_out/ncu_launches_raw.csv \\
         python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline
     python tools/ncu_step_list.py gpurun_out/ncu_launches_raw.csv profiles/launches_r01_step.csv
 
