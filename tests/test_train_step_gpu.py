@@ -12,8 +12,15 @@ right after the output convolution and 5.4 % off at the middle block (profiles/R
 Weight gradients inherit the error of the activation gradient they contract (no cancellation
 amplification, checked on the oracle), so per trainable tensor we require
     err = ||g - g_oracle|| <= 0.12 ||g_oracle||  and cosine >= 0.99,
-    or, for tensors that carry < 10 % of their block's gradient, err <= 0.012 ||g_oracle(block)||
-and over ALL trainable values cosine(g, g_oracle) >= 0.998 (measured 0.9992).  Loss terms agree to
+    or, for tensors that carry < 10 % of their block's gradient, err <= 0.005 ||g_oracle(block)||
+and over ALL trainable values cosine(g, g_oracle) >= 0.998 (measured 0.9993).  The second clause is used
+by exactly one tensor in one case (`output_blocks.1.1...nviews.weight`, no jitter, b = 1: rel_rms 0.29 at
+0.34 % of its block's gradient norm; <= 0.06 in the jittered cases): the view-softmax logit gradients sum to
+zero over the views, dlogit_v = a_v (da_v - sum_u a_u da_u) with da_v = <dS, silu(h_v)>, so when the views
+nearly agree the result is a small difference of nearly equal terms and inherits the bf16 rounding of the
+STORED forward activations h_v (the reference keeps them in fp32).  Keeping the logit gradients in fp32 all
+the way into the weight gradient (tried: fp32-weighted column sum instead of the bf16 GEMM operand) does not
+change it — the rounding happens in the forward.  Loss terms agree to
 2e-2 relative.  Measured values are written to gpurun_out/train_parity_metrics.json.
 """
 import json
@@ -121,7 +128,7 @@ def test_training_step_gradients_vs_oracle(jitter, b, mask_ref):
         bn = block_norm[block_of(k)] ** 0.5
         _record(f"jitter={jitter}/b={b}/mask_ref={mask_ref}/{k}", rel_rms=rel, cosine=cos, ref_norm=float(g_ref.norm()), err_over_block=err / bn)
         minor = float(g_ref.norm()) < 0.1 * bn
-        assert (rel <= 0.12 and cos >= 0.99) or (minor and err <= 0.012 * bn), \
+        assert (rel <= 0.12 and cos >= 0.99) or (minor and err <= 0.005 * bn), \
             f"{k}: rel_rms {rel:.4g}, cosine {cos:.5f}, err / block norm {err / bn:.4g}"
         worst = max(worst, (rel, k))
     gcos = dot / (n1 * n2) ** 0.5
