@@ -52,21 +52,36 @@ class BaseDiffusionSampler:
 class EDMSampler(BaseDiffusionSampler):
     def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        if s_churn != 0.0:
-            raise NotImplementedError("stochastic churn is unused by the shipped sampler config")
         self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
 
+    def _gamma(self, sigma_i, num_sigmas: int) -> float:
+        """Stochastic churn of one step (reference sampling.py:121-125); 0 with the shipped config."""
+        if self.s_churn == 0.0 or not (self.s_tmin <= float(sigma_i) <= self.s_tmax):
+            return 0.0
+        return min(self.s_churn / (num_sigmas - 1), 2 ** 0.5 - 1)
+
+    def _churn(self, x, sigma, gamma: float):
+        """x + eps * sqrt(sigma_hat^2 - sigma^2), sigma_hat = sigma (1 + gamma) (reference :96-100).  The noise
+        draw and this axpy are torch ops: an option the shipped sampler config never takes (s_churn: 0)."""
+        sigma_hat = sigma * (gamma + 1.0)
+        if gamma > 0:
+            eps = torch.randn_like(x) * self.s_noise
+            x = x + eps * append_dims(sigma_hat ** 2 - sigma ** 2, x.ndim) ** 0.5
+        return x, sigma_hat
+
     def sampler_step(self, sigma, next_sigma, denoiser, x, cond, uc=None, gamma=0.0):
-        denoised, rgb_list = self.denoise(x, denoiser, sigma, cond, uc)
-        d = to_d(x, sigma, denoised)
-        dt = append_dims(next_sigma - sigma, x.ndim)
+        x, sigma_hat = self._churn(x, sigma, gamma)
+        denoised, rgb_list = self.denoise(x, denoiser, sigma_hat, cond, uc)
+        d = to_d(x, sigma_hat, denoised)
+        dt = append_dims(next_sigma - sigma_hat, x.ndim)
         return self.possible_correction_step(x + dt * d, x, d, dt, next_sigma, denoiser, cond, uc), rgb_list
 
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None, mask=None, init_im=None):
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
         rgb_list = None
         for i in range(num_sigmas - 1):
-            x, rgb_list = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], denoiser, x, cond, uc)
+            x, rgb_list = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], denoiser, x, cond, uc,
+                                            self._gamma(sigmas[i], num_sigmas))
         return x, rgb_list
 
     forward = __call__
@@ -77,7 +92,13 @@ class EDMSampler(BaseDiffusionSampler):
         sigmas = self.discretization(self.num_steps if num_steps is None else num_steps, device="cpu")
         x *= float(torch.sqrt(1.0 + sigmas[0] ** 2.0))
         for i in range(len(sigmas) - 1):
-            step(x, float(sigmas[i]), float(sigmas[i + 1]))
+            sigma = float(sigmas[i])
+            gamma = self._gamma(sigma, len(sigmas))
+            if gamma > 0:       # churn: noise the latent up to sigma_hat, then the fused step from there
+                xn, sigma_hat = self._churn(x, torch.full((x.shape[0],), sigma, device=x.device), gamma)
+                x.copy_(xn)
+                sigma = float(sigma_hat[0])
+            step(x, sigma, float(sigmas[i + 1]))
         return x
 
 

@@ -279,3 +279,43 @@ def test_vae_decoder_oracle_vs_reference():
         ref = dec(F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
     out = V.autoencoder_decode(sd, cfg, z)
     assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+def test_product_edm_sampler_with_churn_vs_reference(ns):
+    """The PRODUCT EulerEDMSampler (generic path: sampler_step / __call__, host logic only) against the
+    reference's own class with stochastic churn switched on (s_churn > 0: sigma_hat, the extra noise draw,
+    the step from sigma_hat; reference sampling.py:96-136) — same torch generator state, a linear toy
+    denoiser, bit-identical trajectory."""
+    import importlib
+
+    H.install()
+    ref_sampling = importlib.import_module("sgm.modules.diffusionmodules.sampling")
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules import sampling as ours
+    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+    kw = dict(s_churn=20.0, s_tmin=0.05, s_tmax=10.0, s_noise=1.003, num_steps=12, device="cpu")
+    ref = ref_sampling.EulerEDMSampler(
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"},
+        guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFGImgRef", "params": {"scale": 3.0}}, **kw)
+    mine = ours.EulerEDMSampler(
+        discretization_config={"target": P + "discretizer.LegacyDDPMDiscretization"},
+        guider_config={"target": P + "guiders.VanillaCFGImgRef", "params": {"scale": 3.0}}, **kw)
+
+    def denoiser(x, sigma, c):   # the reference's 4-tuple contract (denoiser.py:22-44)
+        d = x * (1.0 / (1.0 + sigma.reshape(-1, 1, 1, 1) ** 2)) + 0.01 * c["vector"].reshape(-1, 1, 1, 1)
+        return d, None, None, None
+
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(2, 4, 8, 8, generator=g)
+    c = {"crossattn": torch.randn(2, 77, 16, generator=g), "vector": torch.randn(2, 1, generator=g)}
+    uc = {"crossattn": torch.zeros(2, 77, 16), "vector": torch.randn(2, 1, generator=g)}
+    torch.manual_seed(11)
+    a, _ = ref(denoiser, x0.clone(), c, uc=uc)
+    torch.manual_seed(11)
+    b, _ = mine(denoiser, x0.clone(), c, uc=uc)
+    assert torch.equal(a, b)
+    torch.manual_seed(11)
+    c0, _ = ours.EulerEDMSampler(
+        discretization_config={"target": P + "discretizer.LegacyDDPMDiscretization"},
+        guider_config={"target": P + "guiders.VanillaCFGImgRef", "params": {"scale": 3.0}},
+        **dict(kw, s_churn=0.0))(denoiser, x0.clone(), c, uc=uc)
+    assert not torch.equal(b, c0)      # the churn must matter, or this case pins nothing
