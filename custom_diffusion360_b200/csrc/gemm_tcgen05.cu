@@ -100,6 +100,7 @@ struct GemmKParams {
   // stores: deterministic), summed in fixed order by cd360_splitk_finish
   int ksplit, kb_per;
   long long split_stride;  // elements between the partial slices
+  int dyn_n;               // 1: the last n-block's MMAs are issued with its real width (CD360_GEMM_DYNN=0: full BN)
 };
 
 template <int BN, int STAGES, int CG>
@@ -300,7 +301,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int kb_begin = ks * p.kb_per;
       const int kb_end = min(nkb, kb_begin + p.kb_per);
       const int m0 = ((m_blk * MC + static_cast<int>(pr)) * CG + static_cast<int>(rank)) * BM;
-      const int n0 = n_blk * BN + static_cast<int>(rank) * L::BNC;
+      // N extent this tile really has (multiple of 16): the last n-block of N = 320 / 640 / 1920 is 64 / 128
+      // columns wide, and the MMA is issued with THAT N (no tensor-core work on zero padding: 6.6 % of the
+      // step's MMA work, and the step runs at the power cap).  In pair mode each CTA supplies N/2 rows of W
+      // from the start of its smem tile, so CTA `rank` loads from row n_blk*BN + rank * ntile/2.
+      const int ntile = (MC == 1 && p.dyn_n) ? min(BN, (p.N - n_blk * BN + 15) & ~15) : BN;
+      const int n0 = n_blk * BN + static_cast<int>(rank) * (ntile / CG);
       int cb = 0, cy = 0, cx = 0;
       if (p.conv) {
         const int hw = p.H * p.W;
@@ -358,11 +364,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   } else if (warp == 1 && leader) {
     // ================================ MMA issuer (whole warp; one elected lane issues) ==========
-    constexpr uint32_t idesc = make_idesc_bf16(BM * CG, BN);
     int stage = 0;
     uint32_t phase = 0;
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
+      const int n_blk_t = (tile % mn_tiles) / p.num_m_blocks;
+      const int ntile = (MC == 1 && p.dyn_n) ? min(BN, (p.N - n_blk_t * BN + 15) & ~15) : BN;   // see the producer
+      const uint32_t idesc = make_idesc_bf16(BM * CG, ntile);
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
@@ -913,6 +921,14 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
   p.act = a->act;
   p.geglu = a->geglu;
   if (a->row_bias != nullptr && a->geglu) return CD360_ERR_UNSUPPORTED;
+  {
+    static int dyn = -1;
+    if (dyn < 0) {
+      const char* e = getenv("CD360_GEMM_DYNN");
+      dyn = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    p.dyn_n = dyn;
+  }
   p.ksplit = 1;
   if (a->k_splits > 1) {
     // partial tiles go to fp32 slices of `out`; everything an epilogue would apply (bias, residual,
