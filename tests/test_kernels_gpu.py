@@ -65,6 +65,8 @@ def test_gemm_linear(M, N, K, bn):
     (12288, 640, 640),
     (640, 5120, 1280),
     (129, 264, 64),           # peer CTA owns a single valid row; N tail inside the peer's W half
+    (512, 320, 192),          # last n-block 64 wide: its MMAs are issued with N = 64 (level-0 convolutions)
+    (768, 1920, 128),         # ... 128 wide (level-1 QKV)
 ])
 @pytest.mark.parametrize("bn", [512, 1024])
 def test_gemm_cta_pair(M, N, K, bn):
