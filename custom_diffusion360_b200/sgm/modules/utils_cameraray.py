@@ -44,12 +44,21 @@ def pack_pose(pose: Sequence, device) -> torch.Tensor:
     return torch.stack(rows).to(device).contiguous()
 
 
+_XY_CACHE: dict = {}
+
+
 def patch_ray_xy(res: int, device) -> torch.Tensor:
     """NDC centres of a res x res patch grid, row-major, [res*res, 2] — the deterministic branch of
     get_patch_raybundle (utils_cameraray.py:106-153): midpoints of linspace(1, -1, res+1),
     meshgrid(indexing='xy')."""
+    key = (res, str(device))
+    hit = _XY_CACHE.get(key)
+    if hit is not None:       # (cached: a host -> device copy is not allowed while a CUDA graph is captured)
+        return hit
     edges = torch.linspace(1, -1, res + 1, dtype=torch.float32)
     centers = (edges[:-1] + edges[1:]) / 2
     xs = centers[None, :].expand(res, res)  # x varies along the fast (column) index
     ys = centers[:, None].expand(res, res)
-    return torch.stack([xs.reshape(-1), ys.reshape(-1)], dim=-1).contiguous().to(device)
+    out = torch.stack([xs.reshape(-1), ys.reshape(-1)], dim=-1).contiguous().to(device)
+    _XY_CACHE[key] = out
+    return out

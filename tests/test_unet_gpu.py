@@ -317,6 +317,63 @@ def test_fused_guided_sampler_vs_golden(gold):
 
 
 @gpu
+def test_fused_step_long_schedule_graph_vs_eager():
+    """12 steps issued back to back with no host synchronisation, so the host runs many graph replays
+    ahead of the GPU: the replayed trajectory must equal the eagerly launched one bit for bit at every
+    step (the per-step sigma scalars travel through a pinned staging ring; a single staging buffer
+    would be overwritten before the queued upload reads it), and so must a second and third image
+    through the same object (step 0 replayed from its own captured graph)."""
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    L, nv, steps = 16, 4, 12
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=nv + 1)
+    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+    engine = DiffusionEngine(
+        network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+        denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+            "num_idx": 1000,
+            "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+            "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"},
+            "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"}}},
+        sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+            "num_steps": steps,
+            "discretization_config": {"target": P + "discretizer.LegacyDDPMDiscretization"},
+            "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef",
+                              "params": {"scale": 7.5, "scale_im": 3.5}}}})
+    net = engine.model.diffusion_model
+    net.load_state_dict({k: v for k, v in sd.items() if not k.endswith("references")}, strict=False)
+    engine = engine.to(dev).eval()
+    net.register_references({k: v.to(dev) for k, v in sd.items() if k.endswith("references")})
+    engine.set_reference_choices(list(range(nv)))
+    inp = O.synthetic_inputs(cfg, L, n_img=1, seed=0, n_views=nv)
+    c = {"crossattn": inp["crossattn"], "vector": inp["vector"]}
+    uc = {"crossattn": torch.zeros_like(inp["crossattn"]), "vector": inp["vector"].clone()}
+    sig = engine.sampler.discretization(steps, device="cpu")
+
+    def image(step):
+        x = inp["x"].clone().to(dev) * float(torch.sqrt(1 + sig[0] ** 2))
+        outs = []
+        for i in range(steps):
+            step(x, float(sig[i]), float(sig[i + 1]))
+            outs.append(x.clone())
+        net.clear_rendered_feat()
+        return outs
+
+    with torch.no_grad():
+        kw = dict(pose=[inp["cams"][0]], n_img=1, latent_shape=(4, L, L))
+        eager = image(FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, c, uc, use_graph=False, **kw))
+        graphed = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, c, uc, **kw)
+        for n_image in range(3):
+            got = image(graphed)
+            for i in range(steps):
+                assert torch.equal(got[i], eager[i]), (n_image, i, float((got[i] - eager[i]).abs().max()))
+    assert graphed.graph is not None
+    _record("fused_long_schedule_graph_vs_eager", got[-1], eager[-1])
+
+
+@gpu
 def test_sdxl_unet_config1_vs_oracle():
     """BASELINE.json configs[0]: the full SDXL UNet (2.57 B params), one forward, 64x64 latent,
     batch 1, FeatureNeRF off — CUDA path vs the fp32 CPU oracle on the same seeded weights.
