@@ -672,16 +672,19 @@ def main():
         e2e_ms = float(t2)
         # ---- step 0 of the NEXT image (packs, allocator and modules warm): FeatureNeRF in all pose
         #      blocks + one eager guided step; the very first call above also builds every weight pack ----
-        net.clear_rendered_feat()
-        torch.cuda.synchronize()
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ea.record()
-        step(x, float(sigmas[0]), float(sigmas[1]))
-        eb.record()
-        torch.cuda.synchronize()
-        step0_warm_ms = ea.elapsed_time(eb)
-        step(x, *sched(1))          # back to the steady state for the per-kernel pass
-        torch.cuda.synchronize()
+        step0_ms_each = []
+        for _ in range(3):          # image 2 captures the step-0 graph, images 3 and 4 replay it
+            net.clear_rendered_feat()
+            torch.cuda.synchronize()
+            ea.record()
+            step(x, float(sigmas[0]), float(sigmas[1]))
+            eb.record()
+            torch.cuda.synchronize()
+            step0_ms_each.append(ea.elapsed_time(eb))
+            step(x, *sched(1))      # back to the steady state
+            torch.cuda.synchronize()
+        step0_warm_ms = step0_ms_each[-1]
         # the same step-0 once more with CUDA events around every launch: where FeatureNeRF's time goes
         rec0 = {}
 
@@ -696,7 +699,9 @@ def main():
         net.clear_rendered_feat()
         ops.LaunchStats.hook = hook0
         _hide_launch_latency(0.12)
+        step.use_graph = False      # eager launches: the hook sees every kernel
         step(x, float(sigmas[0]), float(sigmas[1]))
+        step.use_graph = not args.no_graph
         ops.LaunchStats.hook = None
         torch.cuda.synchronize()
         step0_kernels = {name: {"launches": len(items), "ms": sum(a.elapsed_time(b) for _, a, b in items),
@@ -775,7 +780,9 @@ def main():
         "kernels": kern, "first_call_ms": step0_ms, "step0_featurenerf_ms": step0_warm_ms,
         "step0_kernels": step0_kernels,
         "step0_note": "first_call_ms = first step of the process (builds every bf16 weight pack, loads modules); "
-                      "step0_featurenerf_ms = first step of the NEXT image: FeatureNeRF of all 12 pose blocks + one eager guided step",
+                      "step0_featurenerf_ms = first step of a LATER image (FeatureNeRF of all 12 pose blocks + one guided step), "
+                      "replayed from its own CUDA graph; step0_ms_each = images 2 (captures that graph), 3, 4",
+        "step0_ms_each": step0_ms_each,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": lat_bytes + 4 * (2 * 3 * args.n_img + 4),
                 "d2h_bytes_per_step": lat_bytes, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches_per_step * args.steps * world, "launches_per_step": launches_per_step,

@@ -242,8 +242,10 @@ class FusedGuidedStep:
         ~26 us of host time each, i.e. host-bound (74-104 ms against ~50 ms of kernels).  The captured graph
         reads the cameras, the text conditioning and the stored references through the same buffers that
         `set_pose` / `set_cond` overwrite in place; a change of the reference choices re-captures it."""
-        key = tuple((tuple(m.choices) if m.choices is not None else None, m.references.data_ptr())
-                    for m in self._pose_blocks)
+        # (the per-row reference tokens are a cache of the block, built OUTSIDE the capture; the graph reads
+        # them by address, so a cache rebuilt in between — another batch size went through the block — re-captures)
+        key = tuple((tuple(m.choices) if m.choices is not None else None, m.references.data_ptr(),
+                     m.context_ref_tokens(self.B).data_ptr()) for m in self._pose_blocks)
         self.n_step0 += 1
         if self.n_step0 < 2 or self.x_static is None or self.graph is None:
             self._step0_key = key
