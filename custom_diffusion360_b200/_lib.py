@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("geglu", C.c_int32), ("block_n", C.c_int32), ("max_ctas", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_slabs", C.c_int32), ("ln_eps", C.c_float),
         ("ln_colsum", C.c_void_p), ("stats_out", C.c_void_p), ("k_splits", C.c_int32), ("split_stride", C.c_int64),
+        ("tn", C.c_int32), ("ldw", C.c_int64),
     ]
 
 

@@ -393,9 +393,11 @@ __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, dense.
 //   [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)
 //   [15] a_major (0=K)     [16] b_major (0=K, 1=MN) [17,23) N>>3   [24,29) M>>4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool b_mn_major = false) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) |
-         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool b_mn_major = false,
+                                                       bool a_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+         ((b_mn_major ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 // Shared-memory matrix descriptor for a 128B-swizzled tile whose rows are 128 bytes
 // (64 bf16): 8-row groups are 1024 B apart (SBO).  Valid both for K-major operands
@@ -408,6 +410,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO = 1024 B
   d |= static_cast<uint64_t>(1) << 46;             // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+  return d;
+}
+
+// MN-major operand wider than one swizzle atom: [chunks of 64 MN-elements][rows = K][128 B], the chunks
+// `lbo_bytes` apart (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // LBO: next 64 MN-elements
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                  // SBO: next 8 K-rows
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
 

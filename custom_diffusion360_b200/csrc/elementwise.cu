@@ -503,7 +503,7 @@ extern "C" int cd360_cfg_euler_step_dev(float* x, const float* eps, float* denoi
   return CD360_OK;
 }
 
-extern "C" int cd360_abi_version(void) { return 6; }
+extern "C" int cd360_abi_version(void) { return 7; }
 
 extern "C" const char* cd360_strerror(int code) {
   switch (code) {

@@ -101,6 +101,11 @@ struct GemmKParams {
   int ksplit, kb_per;
   long long split_stride;  // elements between the partial slices
   int dyn_n;               // 1: the last n-block's MMAs are issued with its real width (CD360_GEMM_DYNN=0: full BN)
+  // 1: both operands are stored contraction-major-OUTER ("TN": A^T as [K, M], W^T as [K, N], row-major) and
+  // are consumed in place as MN-major UMMA operands: a stage holds, per operand, 64-column chunks
+  // [64 K-rows][128 B] (one TMA box {64 MN, 64 K} each).  Weight gradients dW = dY^T X contract over the
+  // token rows of two activation matrices; this replaces two transposing copies per GEMM.
+  int tn;
 };
 
 template <int BN, int STAGES, int CG>
@@ -305,7 +310,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
       // columns wide, and the MMA is issued with THAT N (no tensor-core work on zero padding: 6.6 % of the
       // step's MMA work, and the step runs at the power cap).  In pair mode each CTA supplies N/2 rows of W
       // from the start of its smem tile, so CTA `rank` loads from row n_blk*BN + rank * ntile/2.
-      const int ntile = (MC == 1 && p.dyn_n) ? min(BN, (p.N - n_blk * BN + 15) & ~15) : BN;
+      const int ntile = (MC == 1 && p.dyn_n && !p.tn) ? min(BN, (p.N - n_blk * BN + 15) & ~15) : BN;
       const int n0 = n_blk * BN + static_cast<int>(rank) * (ntile / CG);
       int cb = 0, cy = 0, cx = 0;
       if (p.conv) {
@@ -328,6 +333,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         } else {
           mbar_arrive_remote(fb, leader_rank);
         }
+        if (p.tn) {
+          // MN-major operands: chunk j = columns [64 j, 64 j + 64) of this CTA's M rows / W rows, 64 K-rows each
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) {
+            if (CG == 2) tma_load_2d_2sm(sa + j * 8192, &tmA0, fb, m0 + j * 64, kb * BK);
+            else tma_load_2d(sa + j * 8192, &tmA0, fb, m0 + j * 64, kb * BK);
+          }
+#pragma unroll
+          for (int j = 0; j < L::BNC / 64; ++j) {
+            if (CG == 2) tma_load_2d_2sm(sb + j * 8192, &tmB, fb, n0 + j * 64, kb * BK);
+            else tma_load_2d(sb + j * 8192, &tmB, fb, n0 + j * 64, kb * BK);
+          }
+        } else {
         if (p.conv) {
           const int tap = kb / p.cblocks;
           const int kc = kb - tap * p.cblocks;
@@ -352,6 +370,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         } else {
           tma_load_2d(sb, &tmB, fb, kb * BK, n0);
         }
+        }
         if (tile == unit && kb == kb_begin) CD360_TRACE(3);
         if (tile + num_units >= num_tiles && kb == kb_end - 1) CD360_TRACE(4);
         }
@@ -369,8 +388,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
     int t = 0;
     for (int tile = unit; tile < num_tiles; tile += num_units, ++t) {
       const int n_blk_t = (tile % mn_tiles) / p.num_m_blocks;
-      const int ntile = (MC == 1 && p.dyn_n) ? min(BN, (p.N - n_blk_t * BN + 15) & ~15) : BN;   // see the producer
-      const uint32_t idesc = make_idesc_bf16(BM * CG, ntile);
+      const int ntile = (MC == 1 && p.dyn_n && !p.tn) ? min(BN, (p.N - n_blk_t * BN + 15) & ~15) : BN;   // see the producer
+      const uint32_t idesc = make_idesc_bf16(BM * CG, ntile, p.tn != 0, p.tn != 0);
       const int buf = t & 1;
       const uint32_t acc_phase = (t >> 1) & 1;
       mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
@@ -388,8 +407,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32);
+            // K-major: 16 K-elements = 32 B inside the 128-byte rows; MN-major: 16 K-rows = 2048 B
+            const uint64_t adesc = p.tn ? make_smem_desc_sw128_mn(a_addr + k * 2048, 8192)
+                                        : make_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t bdesc = p.tn ? make_smem_desc_sw128_mn(b_addr + k * 2048, 8192)
+                                        : make_smem_desc_sw128(b_addr + k * 32);
             const uint32_t accumulate = (kb != kb_begin || k != 0) ? 1u : 0u;
             if (CG == 2) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
             else umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
@@ -845,7 +867,7 @@ static int launch_gemm(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 // 256x256 CTA-pair (cta_group::2) kernel, 1024 the pair kernel in clusters of two pairs that share
 // W through TMA multicast; 0 = heuristic (pair whenever M spans two CTAs, multicast whenever the
 // number of 256-row blocks is even).  Returns 128, 512 or 1024.
-static int pick_config(int M, int N, int geglu, int requested) {
+static int pick_config(int M, int N, int K, int geglu, int requested) {
   static int pair_ok = -1;
   if (pair_ok < 0) {
     const char* e = getenv("CD360_GEMM_PAIR");
@@ -865,7 +887,7 @@ static int pick_config(int M, int N, int geglu, int requested) {
   if (N <= 128 || M <= 128 || !pair_ok) return (geglu && (N % 256) == 0) ? 512 : 128;
   {
     // small problems (training step at batch 1: M = 256 ... 1024 rows): when 128x128 tiles fill at most
-    // half a wave of single CTAs, twice as many CTAs pull the operands and the epilogue tail of each is half
+    // one wave of single CTAs, twice as many CTAs pull the operands and the epilogue tail of each is half
     // as long as a CTA pair's 128x256 share (CD360_GEMM_SMALL=0 keeps the pair tiles, for A/B runs)
     static int small_ok = -1;
     if (small_ok < 0) {
@@ -874,7 +896,19 @@ static int pick_config(int M, int N, int geglu, int requested) {
     }
     const long long single_tiles =
         static_cast<long long>((M + BM - 1) / BM) * static_cast<long long>((N + 127) / 128);
-    if (small_ok && !geglu && single_tiles <= num_sms() / 2) return 128;  // (leaves room for split-K)
+    // up to ONE wave of single CTAs.  Training step, A/B in one session: threshold num_sms / 2: 45.19 ms,
+    // num_sms: 44.32 ms, num_sms only for K < 2560: 44.88 ms, 2 x num_sms: slower again.
+    // (CD360_GEMM_SMALL_MAX=<tiles>, CD360_GEMM_SMALL_MAXK=<K>: A/B runs of the thresholds)
+    static int small_max = -1, small_maxk = -1;
+    if (small_max < 0) {
+      const char* e = getenv("CD360_GEMM_SMALL_MAX");
+      small_max = (e != nullptr && atoi(e) > 0) ? atoi(e) : num_sms();
+      const char* k = getenv("CD360_GEMM_SMALL_MAXK");
+      small_maxk = (k != nullptr && atoi(k) > 0) ? atoi(k) : (1 << 30);
+    }
+    if (small_ok && !geglu &&
+        (single_tiles <= num_sms() / 2 || (single_tiles <= small_max && K < small_maxk)))
+      return 128;
   }
   const int pair_blocks = (M + 2 * BM - 1) / (2 * BM);
   return (mc_ok && pair_blocks >= 2 && (pair_blocks & 1) == 0) ? 1024 : 512;
@@ -895,12 +929,18 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     return CD360_ERR_NULL;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (a->M <= 0 || a->N <= 0) return CD360_ERR_SHAPE;
-  const int cfgsel = pick_config(a->M, a->N, a->geglu, a->block_n);
+  const int cfgsel = pick_config(a->M, a->N, a->conv ? 9 * a->C : a->k0 + a->k1, a->geglu, a->block_n);
   const int CGsel = cfgsel >= 512 ? 2 : 1;
   const int MCsel = cfgsel == 1024 ? 2 : 1;
   const int BN = cfgsel >= 512 ? 256 : 128;
   if (a->geglu && (a->N % BN != 0 || (a->N & 1))) return CD360_ERR_SHAPE;
   if (a->geglu && a->act != CD360_ACT_NONE) return CD360_ERR_UNSUPPORTED;
+  if (a->tn) {  // contraction over the ROWS of a0 [K, M] and w [K, N]: plain / split-K epilogues only
+    if (a->conv || a->k1 != 0 || a->geglu || a->ln_stats || a->stats_out || a->row_bias || cfgsel == 1024)
+      return CD360_ERR_UNSUPPORTED;
+    if ((a->M & 7) || (a->N & 7) || (a->lda0 & 7) || a->lda0 < a->M || (a->ldw & 7) || a->ldw < a->N)
+      return CD360_ERR_ALIGN;
+  }
 
   GemmKParams p{};
   p.M = a->M;
@@ -929,6 +969,7 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     }
     p.dyn_n = dyn;
   }
+  p.tn = a->tn ? 1 : 0;
   p.ksplit = 1;
   if (a->k_splits > 1) {
     // partial tiles go to fp32 slices of `out`; everything an epilogue would apply (bias, residual,
@@ -1008,6 +1049,17 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
     rc = encode_tmap_bf16(&tmA0, a->a0, 4, dims, strides, box, false);
     if (rc != CD360_OK) return rc;
     tmA1 = tmA0;
+  } else if (a->tn) {
+    if (a->k0 <= 0) return CD360_ERR_SHAPE;
+    p.kb0 = (a->k0 + BK - 1) / BK;   // K tail: TMA zero-fills the rows past k0
+    p.kb1 = 0;
+    ktot = a->k0;
+    uint64_t dims[2] = {static_cast<uint64_t>(a->M), static_cast<uint64_t>(a->k0)};
+    uint64_t strides[1] = {static_cast<uint64_t>(a->lda0) * 2};
+    uint32_t box[2] = {64, BK};
+    rc = encode_tmap_bf16(&tmA0, a->a0, 2, dims, strides, box, false);
+    if (rc != CD360_OK) return rc;
+    tmA1 = tmA0;
   } else {
     if (a->k0 <= 0 || (a->k0 & 7) || (a->lda0 & 7) || a->lda0 < a->k0) return CD360_ERR_ALIGN;
     if (a->k1 < 0) return CD360_ERR_SHAPE;
@@ -1046,7 +1098,13 @@ extern "C" int cd360_gemm_bf16(const cd360_gemm_args* a, cd360_stream_t stream_)
       p.ksplit = (nkb_host + p.kb_per - 1) / p.kb_per;  // no empty split
     }
   }
-  {
+  if (a->tn) {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->k0)};
+    uint64_t strides[1] = {static_cast<uint64_t>(a->ldw) * 2};
+    uint32_t box[2] = {64, BK};
+    rc = encode_tmap_bf16(&tmB, a->w, 2, dims, strides, box, false);
+    if (rc != CD360_OK) return rc;
+  } else {
     uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
     uint32_t box[2] = {BK, static_cast<uint32_t>(BN / CGsel / MCsel)};

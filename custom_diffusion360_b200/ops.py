@@ -50,6 +50,8 @@ import os as _os
 SPLITK = _os.environ.get("CD360_SPLITK", "1") != "0"
 # below ~2.5 k of K the fixed cost of a launch dominates and the extra finish launch does not pay
 GEMM_SMALL = _os.environ.get("CD360_GEMM_SMALL", "1") != "0"   # mirrors pick_config's small-problem rule
+GEMM_SMALL_MAX = int(_os.environ.get("CD360_GEMM_SMALL_MAX", "0")) or 148   # (one wave of single CTAs ...
+GEMM_SMALL_MAXK = int(_os.environ.get("CD360_GEMM_SMALL_MAXK", "0")) or (1 << 30)  # ... when K is below this)
 SPLITK_MIN_KB = int(_os.environ.get("CD360_SPLITK_MIN_KB", "40"))
 _splitk_ws: dict = {}
 
@@ -67,7 +69,8 @@ def _splitk_plan(M, N, K, out, residual, bias, plain_epilogue):
     if bias is not None and (bias.data_ptr() & 15):
         return 1
     singles = _math.ceil(M / 128) * _math.ceil(N / 128)
-    pair = N > 128 and M > 128 and not (GEMM_SMALL and singles <= 74)     # pick_config of gemm_tcgen05.cu
+    small = GEMM_SMALL and (singles <= 74 or (singles <= GEMM_SMALL_MAX and K < GEMM_SMALL_MAXK))
+    pair = N > 128 and M > 128 and not small                               # pick_config of gemm_tcgen05.cu
     units = _math.ceil(M / 256) * _math.ceil(N / 256) if pair else singles
     max_units = 74 if pair else 148
     nkb = _math.ceil(K / 64)
@@ -145,6 +148,45 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=0, residual=None, out
         ln_eps=float(ln_eps), ln_colsum=_ptr(ln_colsum), stats_out=_ptr(stats_out), k_splits=0, split_stride=0)
     _run("gemm", 2.0 * M * N * (k0 + k1),
          lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16"))
+    return out
+
+
+def gemm_tn(a_t, w_t, *, bias=None, out=None, out_fp32=True, k_splits=None):
+    """out [M, N] = a_t^T @ w_t for a_t bf16 [K, M] and w_t bf16 [K, N] (row strides from the views): the
+    contraction runs over the ROWS of both operands, which the kernel consumes in place as MN-major
+    tcgen05 operands (cd360_gemm_args.tn).  The weight gradients dW = dY^T X of the training step."""
+    lib = _lib.load()
+    for name, t in (("a_t", a_t), ("w_t", w_t)):
+        if not t.is_cuda or t.dtype != bf16 or t.dim() != 2:
+            raise Cd360Error(f"gemm_tn: {name} must be a 2-D bf16 CUDA tensor (libcd360 has no CPU path)")
+    K, M = a_t.shape
+    N = w_t.shape[1]
+    if w_t.shape[0] != K:
+        raise Cd360Error(f"gemm_tn: contraction lengths differ ({K} vs {w_t.shape[0]})")
+    if a_t.stride(1) != 1 or w_t.stride(1) != 1:
+        raise Cd360Error("gemm_tn: operands must have unit column stride")
+    if out is None:
+        out = torch.empty((M, N), device=a_t.device, dtype=f32 if out_fp32 else bf16)
+    if k_splits is None:
+        k_splits = _splitk_plan(M, N, K, out, None, bias, True)
+    common = dict(a0=_ptr(a_t), lda0=a_t.stride(0), k0=K, a1=0, lda1=0, k1=0, w=_ptr(w_t), row_bias=0,
+                  rows_per_group=0, ld_row_bias=0, residual=0, ldr=0, M=M, N=N, conv=0, B=0, H=0, W=0, C=0,
+                  act=ACT_NONE, geglu=0, block_n=0, max_ctas=0, ln_stats=0, ln_slabs=0, ln_eps=0.0, ln_colsum=0,
+                  stats_out=0, tn=1, ldw=w_t.stride(0))
+    if k_splits > 1:
+        slices = lib.cd360_splitk_slices(K, 0, int(k_splits))
+        stride = (M * N + 3) // 4 * 4
+        ws = _splitk_workspace(slices * stride, a_t.device)
+        args = GemmArgs(bias=0, out=_ptr(ws), ldo=N, out_fp32=1, k_splits=int(k_splits), split_stride=stride, **common)
+        _run("gemm", 2.0 * M * N * K,
+             lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(tn, split-K)"))
+        _run("splitk_finish", 0.0, lambda: check(lib.cd360_splitk_finish(
+            _ptr(ws), N, stride, slices, _ptr(bias), 0, 0, _ptr(out), out.stride(0),
+            int(out.dtype == f32), M, N, _stream()), "cd360_splitk_finish"))
+        return out
+    args = GemmArgs(bias=_ptr(bias), out=_ptr(out), ldo=out.stride(0), out_fp32=int(out.dtype == f32),
+                    k_splits=0, split_stride=0, **common)
+    _run("gemm", 2.0 * M * N * K, lambda: check(lib.cd360_gemm_bf16(C.byref(args), _stream()), "cd360_gemm_bf16(tn)"))
     return out
 
 

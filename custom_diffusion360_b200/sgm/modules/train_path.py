@@ -32,6 +32,7 @@ pose block in forward order: nothing upstream of it is trainable.
 from __future__ import annotations
 
 import contextlib
+import os
 import math
 from types import SimpleNamespace as NS
 from typing import Dict, List, Optional
@@ -128,9 +129,19 @@ def _grad_buf(param: torch.nn.Parameter) -> torch.Tensor:
     return param.grad
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor):
-    """out[N, K] (fp32, may be a strided view) = dy^T x for dy bf16/fp32 [M, N], x bf16 [M, K]."""
-    return ops.gemm(ops.transpose_to_bf16(dy), ops.transpose_to_bf16(x), out=out)
+WGRAD_TN = os.environ.get("CD360_WGRAD_TN", "1") != "0"   # 0: transposed copies + the K-major GEMM (A/B runs)
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """out[N, K] (fp32, may be a strided view) = dy^T x for dy bf16/fp32 [M, N], x bf16 [M, K]: the
+    contraction over the M token rows reads both activations in place (MN-major tcgen05 operands)."""
+    ok = lambda t: t.stride(1) == 1 and (t.stride(0) & 7) == 0 and (t.shape[1] & 7) == 0 and (t.data_ptr() & 15) == 0
+    if WGRAD_TN and x.dtype == torch.bfloat16 and ok(x):
+        if dy.dtype != torch.bfloat16:
+            dy = ops.cast_bf16(dy.contiguous())
+        if ok(dy):
+            return ops.gemm_tn(dy, x, out=out)
+    return ops.gemm(ops.transpose_to_bf16(dy), ops.transpose_to_bf16(x), out=out, out_fp32=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,7 +239,7 @@ def nerf_backward(block: BasicTransformerBlock, sv, d_rendered, daux):
     dfinal = ops.layernorm_bwd(sv.final, bp["g2"], dfn, add=dfeats2, eps=block.norm2.eps)
     # raw = final Wd^T
     dfinal = ops.gemm(draw8, pp["wd_t8"], residual=dfinal, out=dfinal)
-    dwd = ops.gemm(ops.transpose_to_bf16(draw8), ops.transpose_to_bf16(sv.final), out_fp32=True)   # [8, c]
+    dwd = _wgrad(draw8, sv.final)                                                  # [8, c]
     _grad_buf(model.decoder.weight).copy_(dwd[: model.decoder.weight.shape[0]])
     # final = S W2^T + b2
     _wgrad(dfinal, sv.s, _grad_buf(model.plane_coefs[2].weight))
@@ -238,10 +249,10 @@ def nerf_backward(block: BasicTransformerBlock, sv, d_rendered, daux):
     dhpre, dlogit, dg = ops.nerf_combine_bwd(sv.g, sv.hpre, sv.gidx, sv.gwgt, sv.vlogit, ds, b, n, hw, d, c)
     # hpre = pe W1p^T + b1  |  G = xref [W1f ; w_nv_f]^T
     dw1 = _grad_buf(model.plane_coefs[0].weight)                                   # [c, c + 198]
-    dw1p = ops.gemm(ops.transpose_to_bf16(dhpre), ops.transpose_to_bf16(sv.pe), out_fp32=True)  # [c, KPE]
+    dw1p = _wgrad(dhpre, sv.pe)                                                    # [c, KPE]
     dw1[:, c:].copy_(dw1p[:, :198])
     ops.colsum(dhpre, out=_grad_buf(model.plane_coefs[0].bias).zero_())
-    dwg = ops.gemm(ops.transpose_to_bf16(dg[:, : c + 8]), ops.transpose_to_bf16(sv.xref), out_fp32=True)  # [c+8, c]
+    dwg = _wgrad(dg[:, : c + 8], sv.xref)                                          # [c+8, c]
     dw1[:, :c].copy_(dwg[:c])
     dnv = _grad_buf(model.nviews.weight)                                           # [1, c + 198]
     dnv[0, :c].copy_(dwg[c])
@@ -341,9 +352,8 @@ def block_backward(block: BasicTransformerBlock, sv, g, daux, stop_here: bool):
             _BWD["keep"].append((g, sv, daux))   # read on the side stream: alive until the join
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             dwp = _grad_buf(block.pose_emb_layers.weight)                       # [c, 2c]
-            gt = ops.transpose_to_bf16(g)
-            ops.gemm(gt, ops.transpose_to_bf16(sv.x2), out=dwp[:, :c])
-            ops.gemm(gt, ops.transpose_to_bf16(sv.rendered), out=dwp[:, c:])
+            _wgrad(g, sv.x2, dwp[:, :c])
+            _wgrad(g, sv.rendered, dwp[:, c:])
             nerf_backward(block, sv.nerf, ops.gemm(g, pp["wp_r_t"]), daux)
             ready = block.__dict__.get("_grads_ready")     # data-parallel: start this block's all-reduce now
             if ready is not None:

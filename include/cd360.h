@@ -113,6 +113,13 @@ typedef struct cd360_gemm_args {
    * cannot pull the weights at HBM rate, 140 can) and weight gradients (K = 10^5 rows). */
   int32_t k_splits;
   int64_t split_stride; /* elements, >= M * ldo */
+  /* tn != 0: out = A^T W with both operands stored contraction-outermost — a0 bf16 [k0, M] (row
+   * stride lda0), w bf16 [k0, N] (row stride ldw), M, N, lda0, ldw multiples of 8; k0 arbitrary.
+   * The weight gradients of the training step (dW = dY^T X over the token rows,
+   * torch autograd of nn.Linear in the reference) without transposed copies of dY and X: the tiles
+   * are consumed as MN-major tcgen05 operands.  Epilogue: bias / residual / act, or split-K. */
+  int32_t tn;
+  int64_t ldw;
 } cd360_gemm_args;
 
 int cd360_gemm_bf16(const cd360_gemm_args* args, cd360_stream_t stream);

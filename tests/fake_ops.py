@@ -43,6 +43,17 @@ class Fake:
             return out
         return torch.zeros(M, n_out, dtype=f32 if out_fp32 else bf16)
 
+    def gemm_tn(self, a_t, w_t, *, bias=None, out=None, out_fp32=True, k_splits=None):
+        assert a_t.dtype == bf16 and w_t.dtype == bf16 and a_t.shape[0] == w_t.shape[0]
+        assert a_t.stride(1) == 1 and w_t.stride(1) == 1
+        M, N = a_t.shape[1], w_t.shape[1]
+        assert M % 8 == 0 and N % 8 == 0 and a_t.stride(0) % 8 == 0 and w_t.stride(0) % 8 == 0
+        self._log("gemm_tn", M=M, N=N, K=a_t.shape[0])
+        if out is not None:
+            assert out.shape == (M, N)
+            return out
+        return torch.zeros(M, N, dtype=f32 if out_fp32 else bf16)
+
     def conv3x3(self, x, w, B, H, W, *, bias=None, row_bias=None, residual=None, out=None,
                 out_fp32=False, block_n=0, max_ctas=0):
         assert x.dtype == bf16 and x.shape[0] == B * H * W and w.shape[1] == 9 * x.shape[1]

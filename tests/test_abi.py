@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in _lib.header_symbols():
         assert hasattr(lib, name), name
-    assert lib.cd360_abi_version() == 6
+    assert lib.cd360_abi_version() == 7
     assert lib.cd360_strerror(0) == b"ok"
     assert b"aligned" in lib.cd360_strerror(-2)
 

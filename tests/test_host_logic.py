@@ -293,7 +293,8 @@ def test_splitk_plan_heuristic():
         assert plan(M, N, K) == 1, (M, N, K)
     assert plan(256, 1280, 5120) == 7           # FF2 of the level-2 main stream: 20 single CTAs -> 140
     assert plan(256, 1280, 10240) == 7          # dX of FF1
-    assert plan(1288, 1280, 24576) == 2         # weight gradient [c + 8, c] over 24 576 sample rows
+    assert plan(1288, 1280, 24576) == 1         # 110 single-CTA tiles: one wave already (gemm_tcgen05.cu pick_config)
+    assert plan(648, 640, 24576) == 4           # weight gradient [c + 8, c] over 24 576 sample rows: 30 tiles -> 120
     assert plan(256, 1280, 1280) == 1           # fixed launch cost dominates below K = 2560
     assert plan(256, 1280, 5120, plain=False) == 1
     assert plan(256, 1282, 5120) == 1           # finish kernel works on 4-column vectors

@@ -466,6 +466,47 @@ def test_gemm_split_k(M, N, K, K1, splits):
 
 
 @gpu
+@pytest.mark.parametrize("K,M,N,splits", [
+    (1024, 1280, 1280, 1),      # pose_emb_layers dW: CTA-pair tiles, MN-major A and B
+    (1024, 1280, 1280, None),
+    (24576, 640, 208, None),    # FeatureNeRF dW1p: K = sample rows, N tail (208 = 3 x 64 + 16), split-K
+    (98304, 640, 208, None),
+    (24576, 8, 1280, None),     # decoder dW: M = 8 (boxes past the first are entirely out of bounds)
+    (6144, 648, 640, 3),        # dG^T xref: ragged M (648), split count not dividing the k-blocks
+    (1000, 264, 72, 1),         # K tail (TMA zero-fills rows 1000..1023), single-CTA tiles
+    (4096, 2560, 1280, 1),      # several waves of pair tiles
+])
+def test_gemm_tn(K, M, N, splits):
+    """out = A^T W with both operands stored [K, .] row-major (cd360_gemm_args.tn: MN-major tcgen05 operands,
+    no transposed copies) == torch fp32 on the bf16-rounded inputs == the K-major kernel on transposed copies."""
+    from custom_diffusion360_b200 import ops
+    torch.manual_seed(2)
+    dev = _dev()
+    a_t, af = _rt(torch.randn(K, M, device=dev))
+    w_t, wf = _rt(torch.randn(K, N, device=dev) / math.sqrt(K))
+    ref = af.t() @ wf
+    out = ops.gemm_tn(a_t, w_t, k_splits=splits)
+    assert out.dtype == torch.float32 and out.shape == (M, N)
+    _assert_close(out, ref, rel=2e-3, abs_=2e-3, what="gemm_tn fp32")
+    base = ops.gemm(ops.transpose_to_bf16(a_t), ops.transpose_to_bf16(w_t), out_fp32=True, k_splits=1)
+    assert float((out - base).abs().max()) <= 1e-3 * float(base.abs().max()) + 1e-4
+    assert torch.equal(out, ops.gemm_tn(a_t, w_t, k_splits=splits)), "deterministic"
+    # operands as column slices of wider matrices (row stride > width), output into a strided fp32 view
+    wide_a = torch.randn(K, M + 24, device=dev).to(torch.bfloat16)
+    wide_w = torch.randn(K, N + 40, device=dev).to(torch.bfloat16)
+    wide_a[:, 8:8 + M] = a_t
+    wide_w[:, 16:16 + N] = w_t
+    big = torch.zeros(M, N + 8, device=dev)
+    ops.gemm_tn(wide_a[:, 8:8 + M], wide_w[:, 16:16 + N], out=big[:, :N], k_splits=splits)
+    _assert_close(big[:, :N], ref, rel=2e-3, abs_=2e-3, what="gemm_tn strided operands / out")
+    assert float(big[:, N:].abs().max()) == 0.0
+    # bf16 output with bias
+    bias = torch.randn(N, device=dev)
+    ob = ops.gemm_tn(a_t, w_t, bias=bias, out_fp32=False, k_splits=splits)
+    _assert_close(ob, ref + bias, what="gemm_tn bf16 + bias")
+
+
+@gpu
 def test_nerf_mask_ref_nearest_resize_multiply():
     """cd360_nerf_mask_ref == `xref * F.interpolate(mask_ref, [res, res], mode="nearest")`
     (nerfsd_pytorch3d.py:61-70), incl. non-integer scale factors and non-square masks; 0/1 masks
