@@ -150,38 +150,72 @@ __device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* x0, int c0, const
   return unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(src)));
 }
 
+// read a float at the same shared-memory offset in CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ float ld_cluster_f32(const float* p, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+// One (group, image) per CLUSTER of `splits` CTAs (1 = a plain CTA): each CTA owns a slice of the rows, the
+// two dependent reductions (moments, then the two gradient sums) are combined through distributed shared
+// memory in rank order — deterministic — so 32 x batch work items spread over up to 8 x as many SMs (one
+// CTA per group walked 4096 x 10 channels alone: 36 us per launch on the critical backward chain).
 __global__ void __launch_bounds__(512)
 groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
                            const __nv_bfloat16* __restrict__ x1, int c1,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
                            const __nv_bfloat16* __restrict__ dy, float* __restrict__ ws, int hw,
-                           float eps, int apply_silu) {
+                           float eps, int apply_silu, int splits) {
   pdl_wait();
   __shared__ float s_red[32];
-  const int g = blockIdx.x, b = blockIdx.y;
+  __shared__ float s_x[2], s_y[2], s_bc[2];
+  const int g = blockIdx.x / splits, b = blockIdx.y;
+  const uint32_t rank = splits > 1 ? cluster_ctarank() : 0u;
   const int ctot = c0 + c1;
   const int cg = ctot / GNB_GROUPS;
   const int pairs = cg >> 1;
   const long long img = static_cast<long long>(b) * hw;
-  const int items = hw * pairs;
+  const int rows_per = (hw + splits - 1) / splits;
+  const int r0 = static_cast<int>(rank) * rows_per;
+  const int r1 = min(hw, r0 + rows_per);
+  const int items = r1 > r0 ? (r1 - r0) * pairs : 0;
   float s = 0.f, ss = 0.f;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int r = i / pairs, j = i - r * pairs;
-    const float2 v = ld_pair(x0, c0, x1, c1, img + r, g * cg + 2 * j);
+    const float2 v = ld_pair(x0, c0, x1, c1, img + r0 + r, g * cg + 2 * j);
     s += v.x + v.y;
     ss = fmaf(v.x, v.x, fmaf(v.y, v.y, ss));
   }
+  s = block_sum(s, s_red);
+  ss = block_sum(ss, s_red);
+  if (splits > 1) {
+    if (threadIdx.x == 0) { s_x[0] = s; s_x[1] = ss; }
+    cluster_sync_all();
+    if (threadIdx.x == 0) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int k = 0; k < splits; ++k) {  // rank order: every CTA of the cluster gets the same bits
+        t0 += ld_cluster_f32(&s_x[0], k);
+        t1 += ld_cluster_f32(&s_x[1], k);
+      }
+      s_bc[0] = t0; s_bc[1] = t1;
+    }
+    __syncthreads();
+    s = s_bc[0]; ss = s_bc[1];
+  }
   const float n = static_cast<float>(hw) * cg;
-  const float mean = block_sum(s, s_red) / n;
-  float var = block_sum(ss, s_red) / n - mean * mean;
+  const float mean = s / n;
+  float var = ss / n - mean * mean;
   if (var < 0.f) var = 0.f;
   const float rstd = rsqrtf(var + eps);
   float a1 = 0.f, a2 = 0.f;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
     const int r = i / pairs, j = i - r * pairs;
     const int ch = g * cg + 2 * j;
-    const float2 v = ld_pair(x0, c0, x1, c1, img + r, ch);
-    const float2 d = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(dy + (img + r) * ctot + ch)));
+    const float2 v = ld_pair(x0, c0, x1, c1, img + r0 + r, ch);
+    const float2 d = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(dy + (img + r0 + r) * ctot + ch)));
     const float xh0 = (v.x - mean) * rstd, xh1 = (v.y - mean) * rstd;
     const float g0 = gamma[ch], g1 = gamma[ch + 1];
     float t0 = d.x * g0, t1 = d.y * g1;
@@ -192,12 +226,24 @@ groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
     a1 += t0 + t1;
     a2 = fmaf(t0, xh0, fmaf(t1, xh1, a2));
   }
-  a1 = block_sum(a1, s_red) / n;
-  a2 = block_sum(a2, s_red) / n;
-  if (threadIdx.x == 0) {
-    float* o = ws + (static_cast<long long>(b) * GNB_GROUPS + g) * 4;
-    o[0] = mean; o[1] = rstd; o[2] = a1; o[3] = a2;
+  a1 = block_sum(a1, s_red);
+  a2 = block_sum(a2, s_red);
+  if (splits > 1) {
+    if (threadIdx.x == 0) { s_y[0] = a1; s_y[1] = a2; }
+    cluster_sync_all();
+    if (rank == 0 && threadIdx.x == 0) {
+      a1 = 0.f; a2 = 0.f;
+      for (int k = 0; k < splits; ++k) {
+        a1 += ld_cluster_f32(&s_y[0], k);
+        a2 += ld_cluster_f32(&s_y[1], k);
+      }
+    }
   }
+  if (rank == 0 && threadIdx.x == 0) {
+    float* o = ws + (static_cast<long long>(b) * GNB_GROUPS + g) * 4;
+    o[0] = mean; o[1] = rstd; o[2] = a1 / n; o[3] = a2 / n;
+  }
+  if (splits > 1) cluster_sync_all();  // peers keep their shared memory alive until rank 0 has read it
 }
 
 __global__ void __launch_bounds__(256)
@@ -992,8 +1038,17 @@ extern "C" int cd360_groupnorm_silu_bwd_bf16(const void* x0, int32_t c0, const v
       (add0 && (reinterpret_cast<uintptr_t>(add0) & 3)) || (add1 && (reinterpret_cast<uintptr_t>(add1) & 3)))
     return CD360_ERR_ALIGN;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  launch_ex(groupnorm_bwd_stats_kernel, dim3(GNB_GROUPS, batch), dim3(512), 0, stream, 1, CD360_BF(x0), c0,
-            CD360_BF(x1), c1, gamma, beta, CD360_BF(dy), workspace, hw, eps, apply_silu);
+  // rows of one (group, image) divided among a cluster of up to 8 CTAs (>= 64 rows each)
+  static int split_ok = -1;
+  if (split_ok < 0) {
+    const char* e = getenv("CD360_GNB_CLUSTER");
+    split_ok = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  int splits = 1;
+  if (split_ok) while (splits < 8 && hw / (splits * 2) >= 64 && GNB_GROUPS * batch * splits * 2 <= 4 * kNumSMsB200) splits *= 2;
+  launch_ex(groupnorm_bwd_stats_kernel, dim3(GNB_GROUPS * splits, batch), dim3(splits > 1 ? 256 : 512), 0, stream,
+            splits, CD360_BF(x0), c0, CD360_BF(x1), c1, gamma, beta, CD360_BF(dy), workspace, hw, eps, apply_silu,
+            splits);
   CD360_CHECK_LAUNCH();
   const long long items = static_cast<long long>(batch) * hw * (ctot / 2);
   launch_ex(groupnorm_bwd_apply_kernel, dim3(grid_for(items, 256)), dim3(256), 0, stream, 1, CD360_BF(x0),

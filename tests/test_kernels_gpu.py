@@ -428,7 +428,8 @@ def test_cfg_euler_step():
     (256, 1280, 5120, 0, None),     # training-step FF2 of the level-2 main stream: heuristic must split
     (256, 1280, 1280, 1280, 4),     # two K segments (pose_emb_layers: [x | rendered])
     (200, 640, 4096, 0, 7),         # ragged M, split count that does not divide the k-blocks
-    (1288, 1280, 24576, 0, None),   # weight-gradient shape: K = rows of the sample batch
+    (648, 640, 24576, 0, None),     # weight-gradient shape: K = rows of the sample batch; 30 tiles: heuristic splits
+    (1288, 1280, 24576, 0, 2),      # 110 single-CTA tiles (one wave): split only on request
     (256, 5120, 1280, 0, 3),        # dX of FF2: 40 CTAs, K below the heuristic threshold
     (96, 72, 2048, 0, 8),           # single-CTA config, N tail
 ])

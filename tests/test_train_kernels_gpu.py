@@ -57,6 +57,8 @@ def test_layernorm_bwd(rows, c):
     (3, 256, 640, 320, True, 1e-5),     # decoder concat
     (1, 256, 1280, 0, False, 1e-6),     # SpatialTransformer.norm
     (2, 100, 128, 64, False, 1e-5),
+    (1, 4096, 320, 0, True, 1e-5),      # level 0 of the training step: 8-CTA clusters, 512 rows each
+    (1, 900, 128, 64, True, 1e-5),      # rows not divisible by the cluster size (last rank: 109 of 113)
 ])
 def test_groupnorm_bwd(B, HW, c0, c1, silu, eps):
     from custom_diffusion360_b200 import ops
