@@ -118,7 +118,7 @@ class FusedGuidedStep:
     SCAL_SLOTS = 16   # depth of the pinned staging ring of per-step scalars (bounds the host's run-ahead)
 
     def __init__(self, network, denoiser, guider, cond: dict, uc: dict, pose=None, n_img: int = 1,
-                 latent_shape=(4, 128, 128), use_graph: bool = True):
+                 latent_shape=(4, 128, 128), use_graph: bool = True, dedup_rows: bool = True):
         self.net = network
         self.guider = guider
         self.rows = guider.rows
@@ -158,6 +158,11 @@ class FusedGuidedStep:
         self.graph0 = None           # step 0 of an image (FeatureNeRF in every pose block), captured on the 2nd image
         self.n_step0 = 0
         self._step0_key = None
+        self.dedup_rows = dedup_rows
+        self._classes = None         # (representative row per class, class of every row) on the device
+        self._class_key = None
+        if pose is not None:
+            self._set_row_classes(pose)
 
     def matches(self, network, guider, cond: dict, uc: dict, pose, n_img: int, latent_shape) -> bool:
         """True when this object (its buffers and captured graphs) can serve another image with these
@@ -176,6 +181,33 @@ class FusedGuidedStep:
                 return False
         return True
 
+    def _set_row_classes(self, pose):
+        """Classes of UNet rows whose FeatureNeRF encoding is identical: same cameras (compared on the host,
+        bit for bit) and same reference tokens — the null reference for the first row group, the chosen real
+        references for the others (`context_ref_tokens`, sample.py:85-96, incl. its `batch % 3` rule).  The
+        pose blocks encode one row per class (BasicTransformerBlock.reference_tokens).  The index tensors are
+        kept while the class structure is unchanged (the step-0 graph reads them; a new structure re-captures)."""
+        if not self.dedup_rows:
+            return
+        cams = pack_pose(pose, "cpu")
+        cams = cams.reshape(cams.shape[0], -1)
+        _, geo = torch.unique(cams, dim=0, return_inverse=True)        # class of every IMAGE's cameras
+        rows_ref = 3 if self.B % 3 == 0 else 2
+        bs = self.B // rows_ref
+        keys, uniq, inverse = {}, [], []
+        for row in range(self.B):
+            key = (0 if row < bs else 1, int(geo[row % self.n_img]))
+            if key not in keys:
+                keys[key] = len(uniq)
+                uniq.append(row)
+            inverse.append(keys[key])
+        structure = (tuple(uniq), tuple(inverse))
+        if structure != self._class_key:
+            self._class_key = structure
+            self._classes = (torch.tensor(uniq, device=self.dev), torch.tensor(inverse, device=self.dev))
+        if len(uniq) == self.B:
+            self._classes = None
+
     def set_pose(self, pose):
         """New target / reference cameras for the NEXT image(s) (the 360-degree sweep of BASELINE
         configs[4]: same prompts, another target camera).  The packed cameras are overwritten IN PLACE
@@ -185,6 +217,7 @@ class FusedGuidedStep:
         if self.cams is None or self.cams.shape != cams.shape:
             raise ValueError("set_pose: camera batch shape differs from the one this step was built with")
         self.cams.copy_(cams)
+        self._set_row_classes(pose)
         self.net.clear_rendered_feat()
 
     def set_cond(self, cond: dict, uc: dict):
@@ -245,7 +278,7 @@ class FusedGuidedStep:
         # (the per-row reference tokens are a cache of the block, built OUTSIDE the capture; the graph reads
         # them by address, so a cache rebuilt in between — another batch size went through the block — re-captures)
         key = tuple((tuple(m.choices) if m.choices is not None else None, m.references.data_ptr(),
-                     m.context_ref_tokens(self.B).data_ptr()) for m in self._pose_blocks)
+                     m.context_ref_tokens(self.B).data_ptr()) for m in self._pose_blocks) + (self._class_key,)
         self.n_step0 += 1
         if self.n_step0 < 2 or self.x_static is None or self.graph is None:
             self._step0_key = key
@@ -290,10 +323,18 @@ class FusedGuidedStep:
         if self._pose_blocks is None:
             self._pose_blocks = [m for _, m in self.net.pose_blocks()]
         pose_pending = self.cams is not None and any(m.rendered_feat is None for m in self._pose_blocks)
+        if pose_pending:
+            # the row classes are valid for THIS object's cameras only: installed on the blocks for the
+            # duration of its step 0 (eager or captured), never left behind for other callers of the network
+            for m in self._pose_blocks:
+                m.__dict__["_row_classes"] = self._classes
+            try:
+                return self._step0(x) if self.use_graph else self._body(x)
+            finally:
+                for m in self._pose_blocks:
+                    m.__dict__.pop("_row_classes", None)
         if not self.use_graph:
             return self._body(x)
-        if pose_pending:
-            return self._step0(x)
         if self.graph is None:
             self.n_steady += 1
             if self.n_steady < 2:  # one eager steady-state step warms allocator + packed weights

@@ -300,6 +300,35 @@ def test_splitk_plan_heuristic():
     assert plan(256, 1282, 5120) == 1           # finish kernel works on 4-column vectors
 
 
+def test_featurenerf_row_classes():
+    """FusedGuidedStep._set_row_classes: UNet rows that share one FeatureNeRF encoding = same cameras (bitwise)
+    and same reference tokens (first row group: the null reference; the others: the real ones — the grouping
+    rule of `context_ref_tokens` / sample.py:85-96, `batch % 3` included)."""
+    import types
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    mk = lambda B, n: types.SimpleNamespace(dedup_rows=True, B=B, n_img=n, dev="cpu", _class_key=None, _classes=None)
+    cams = torch.randn(4, 5, 16)
+    o = mk(3, 1)                                   # sample.py car0: rows (u, ic, c) of one image
+    FusedGuidedStep._set_row_classes(o, cams[:1])
+    assert o._class_key == ((0, 1), (0, 1, 1)) and o._classes[0].tolist() == [0, 1]
+    o = mk(12, 4)                                  # sweep unit: four prompts, one target camera
+    FusedGuidedStep._set_row_classes(o, cams[:1].repeat(4, 1, 1))
+    assert o._class_key == ((0, 4), (0,) * 4 + (1,) * 8)
+    o = mk(12, 4)                                  # four different cameras: rows 1 and 2 of each image still pair up
+    FusedGuidedStep._set_row_classes(o, cams)
+    assert o._class_key == (tuple(range(8)), (0, 1, 2, 3, 4, 5, 6, 7, 4, 5, 6, 7))
+    o = mk(2, 1)                                   # two-row guider: nothing to share
+    FusedGuidedStep._set_row_classes(o, cams[:1])
+    assert o._class_key == ((0, 1), (0, 1)) and o._classes is None
+    o = mk(6, 3)                                   # two-row guider, three images: the reference's batch % 3 rule
+    FusedGuidedStep._set_row_classes(o, cams[:1].repeat(3, 1, 1))      # makes rows 0-1 the "null" group
+    assert o._class_key == ((0, 2), (0, 0, 1, 1, 1, 1))
+    o = mk(3, 1)
+    o.dedup_rows = False
+    FusedGuidedStep._set_row_classes(o, cams[:1])
+    assert o._classes is None
+
+
 def test_engine_rejects_unbuilt_training_options():
     """Options whose silent acceptance would corrupt training: any trainkeys other than
     'pose' would put frozen SDXL weights under AdamW weight decay with zero gradients."""

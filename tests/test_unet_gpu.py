@@ -374,6 +374,65 @@ def test_fused_step_long_schedule_graph_vs_eager():
 
 
 @gpu
+def test_fused_step_row_class_dedup():
+    """Rows with the same cameras and the same reference tokens share ONE FeatureNeRF encoding (guidance rows
+    1 and 2 of every image; all prompts of one target camera in a sweep batch): 2 images x 3 rows with identical
+    cameras = 2 classes of 6 rows.  Same trajectory as with every row encoded (the only difference is the GEMM
+    tiling of the smaller encode batch), and a change of the class structure through set_pose is followed."""
+    from custom_diffusion360_b200.sgm.models.diffusion import DiffusionEngine
+    from custom_diffusion360_b200.sgm.modules.diffusionmodules.sampling import FusedGuidedStep
+    dev = torch.device("cuda:0")
+    cfg = dict(O.TINY_CFG)
+    L, nv, steps, n_img = 16, 4, 4, 2
+    sd = O.synthetic_state_dict(cfg, seed=0, latent=L, num_references=nv + 1)
+    P = "custom_diffusion360_b200.sgm.modules.diffusionmodules."
+    disc = {"target": P + "discretizer.LegacyDDPMDiscretization"}
+    engine = DiffusionEngine(
+        network_config={"target": P + "openaimodel.UNetModel", "params": cfg},
+        denoiser_config={"target": P + "denoiser.DiscreteDenoiser", "params": {
+            "num_idx": 1000, "weighting_config": {"target": P + "denoiser_weighting.EpsWeighting"},
+            "scaling_config": {"target": P + "denoiser_scaling.EpsScaling"}, "discretization_config": disc}},
+        sampler_config={"target": P + "sampling.EulerEDMSampler", "params": {
+            "num_steps": steps, "discretization_config": disc,
+            "guider_config": {"target": P + "guiders.ScheduledCFGImgTextRef", "params": {"scale": 7.5, "scale_im": 3.5}}}})
+    net = engine.model.diffusion_model
+    net.load_state_dict({k: v for k, v in sd.items() if not k.endswith("references")}, strict=False)
+    engine = engine.to(dev).eval()
+    net.register_references({k: v.to(dev) for k, v in sd.items() if k.endswith("references")})
+    engine.set_reference_choices(list(range(nv)))
+    inp = O.synthetic_inputs(cfg, L, n_img=n_img, seed=0, n_views=nv)
+    c = {"crossattn": inp["crossattn"], "vector": inp["vector"]}
+    uc = {"crossattn": torch.zeros_like(inp["crossattn"]), "vector": inp["vector"].clone()}
+    sig = engine.sampler.discretization(steps, device="cpu")
+    same = [inp["cams"][0], inp["cams"][0]]
+    other = [inp["cams"][0], inp["cams"][1]]
+
+    def image(step):
+        x = inp["x"].clone().to(dev) * float(torch.sqrt(1 + sig[0] ** 2))
+        for i in range(steps):
+            step(x, float(sig[i]), float(sig[i + 1]))
+        net.clear_rendered_feat()
+        return x.clone()
+
+    with torch.no_grad():
+        kw = dict(n_img=n_img, latent_shape=(4, L, L))
+        full = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, c, uc, pose=same, dedup_rows=False, **kw)
+        ded = FusedGuidedStep(net, engine.denoiser, engine.sampler.guider, c, uc, pose=same, **kw)
+        assert full._classes is None and ded._class_key == ((0, 2), (0, 0, 1, 1, 1, 1))
+        ref_same = image(full)
+        _check("row_dedup_same_cameras", image(ded), ref_same, rel_tol=2e-2, max_frac=0.1)
+        _check("row_dedup_same_cameras_graph0", image(ded), ref_same, rel_tol=2e-2, max_frac=0.1)   # step-0 graph
+        full.set_pose(other)
+        ded.set_pose(other)
+        assert ded._class_key == ((0, 1, 2, 3), (0, 1, 2, 3, 2, 3))
+        ref_other = image(full)
+        _check("row_dedup_two_cameras", image(ded), ref_other, rel_tol=2e-2, max_frac=0.1)
+        _check("row_dedup_two_cameras_graph0", image(ded), ref_other, rel_tol=2e-2, max_frac=0.1)
+        assert float((ref_other - ref_same).abs().max()) > 1e-2          # the cameras matter
+    assert all("_row_classes" not in m.__dict__ for _, m in net.pose_blocks())
+
+
+@gpu
 def test_sdxl_unet_config1_vs_oracle():
     """BASELINE.json configs[0]: the full SDXL UNet (2.57 B params), one forward, 64x64 latent,
     batch 1, FeatureNeRF off — CUDA path vs the fp32 CPU oracle on the same seeded weights.
