@@ -28,6 +28,13 @@ def test_argument_validation_needs_no_gpu():
     assert lib.cd360_attention_bf16(None, 0, None, 0, None, 0, None, 0, 1, 1, 1, 1, None) == -5
     assert lib.cd360_layernorm_bf16(16, 16, 16, 16, 4, 63, 1e-5, None) == -1  # c not multiple of 8
     assert lib.cd360_geglu_pack_block(5120) == 128 and lib.cd360_geglu_pack_block(100) == -1
+    # TN mode (weight gradients): plain epilogues only, 16-byte aligned rows — checked before any CUDA call
+    tn = dict(a0=256, w=256, out=256, M=640, N=208, k0=1024, lda0=640, ldw=208, ldo=208, out_fp32=1, tn=1)
+    assert lib.cd360_gemm_bf16(ctypes.byref(_lib.GemmArgs(**{**tn, "geglu": 1, "N": 256, "ldw": 256, "ldo": 128})), None) == -3
+    assert lib.cd360_gemm_bf16(ctypes.byref(_lib.GemmArgs(**{**tn, "conv": 1})), None) == -3
+    assert lib.cd360_gemm_bf16(ctypes.byref(_lib.GemmArgs(**{**tn, "ldw": 204})), None) == -2   # ldw < N / not 8-aligned
+    assert lib.cd360_gemm_bf16(ctypes.byref(_lib.GemmArgs(**{**tn, "M": 636})), None) == -2     # M not a multiple of 8
+    assert lib.cd360_gemm_bf16(ctypes.byref(_lib.GemmArgs(**{**tn, "lda0": 632})), None) == -2  # lda0 < M
     assert lib.cd360_groupnorm_workspace_floats(3, 4096) >= 3 * 64
 
 
