@@ -113,6 +113,10 @@ class FusedGuidedStep:
     network: UNetModel (this package); denoiser: DiscreteDenoiser (σ table); guider: provides
     `rows`, `scale`, `scale_im` and `prepare_inputs`.  cond / uc: dicts with "crossattn" [N,77,ctx]
     and "vector" [N,adm] for the N images; pose: list of N camera batches or packed [N, n+1, 16].
+    dedup_rows: UNet rows with the same cameras and the same reference tokens share one FeatureNeRF
+    encoding at step 0 (`_set_row_classes`); False encodes every row like the reference does.
+    One object serves many images: `set_cond` / `set_pose` rewrite its buffers in place, the steady-state
+    step and (from the second image on) step 0 are CUDA-graph replays.
     """
 
     SCAL_SLOTS = 16   # depth of the pinned staging ring of per-step scalars (bounds the host's run-ahead)
