@@ -69,6 +69,23 @@ def test_unet_pose_on_and_cache(gold):
         assert (rgb - grgb).abs().max() < 2e-6
 
 
+def test_guidance_rows_structure_in_the_reference_golden(gold):
+    """What may and what may not be shared between the three guidance rows of sample.py (pins the premise of
+    FusedGuidedStep's row classes on the REFERENCE's own outputs): the rows are (uc text + null references,
+    uc text + real references, c text + real references) — sample.py:85-96, guiders.py:114-128.  Rows 1 and 2
+    therefore see the same cameras and reference tokens: their FeatureNeRF opacity maps (computed before any
+    text enters: alphas come from the decoder's sigma, reference_attn order :571-598 — the text attention runs
+    on the features, the densities are decoded from the encoding alone) are identical; row 0 differs; and the
+    eps rows are pairwise different (no two rows can be merged)."""
+    eps = gold["unet_eps_step0"]
+    assert eps.shape[0] == 3
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        assert (eps[i] - eps[j]).abs().max() > 1e-3, (i, j)
+    for al in gold["alphas"]:
+        assert (al[1] - al[2]).abs().max() < 1e-6     # same encoding (the reference's batched matmuls differ by an ulp)
+        assert (al[0] - al[1]).abs().max() > 1e-2     # null vs real references
+
+
 def test_guided_euler_sampler(gold):
     """EulerEDMSampler + DiscreteDenoiser + ScheduledCFGImgTextRef around the UNet, 4 steps."""
     cfg = dict(O.TINY_CFG)
